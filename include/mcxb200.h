@@ -1,0 +1,230 @@
+/*
+ * mcxb200.h -- C ABI of the B200-native photon-transport engine (libmcxb200.so).
+ *
+ * This is the drop-in boundary for ONE path of fangq/mcxcl: the work of the OpenCL kernel
+ * mcx_main_loop (reference src/mcx_core.cl:2307-3307) together with the host runtime that feeds it
+ * (reference src/mcx_host.cpp:438-1849, mcx_run_simulation) and device enumeration
+ * (src/mcx_host.cpp:252-432, mcx_list_gpu).  Plain pointers and sizes only -- no OpenCL, torch or
+ * C++ types appear in any signature.
+ *
+ * Every field of mcxb_config mirrors a member of the reference's `Config`
+ * (src/mcx_utils.h:165-281) AFTER mcx_preprocess()/mcx_validatecfg() ran on it
+ * (src/mcx_utils.c:1521-1809): source direction normalised, mua/mus scaled by unitinmm,
+ * mus==0 -> 1e-10, detector voxels flagged in bit 31 of `vol` (mcx_maskdet, :4085-4198), boundary
+ * conditions converted to integer codes, and -- for point-like sources -- the launch voxel index
+ * and its label stored as raw uint bit patterns in srcparam2.z / srcparam2.w (:1718-1749).
+ * INTEGRATION.md shows the 60-line adapter that fills this struct from a reference `Config*` and
+ * thereby re-exports mcx_run_simulation / mcx_list_gpu / ocl_assess unchanged
+ * (src/mcx_host.h:168-170).
+ */
+#ifndef MCXB200_H
+#define MCXB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCXB_ABI_VERSION 1
+
+/* error codes returned by every entry point (0 = success).  The reference reports OpenCL errors
+ * negated through ocl_assess (src/mcx_host.cpp:213-217); CUDA runtime errors are reported the same
+ * way: -(int)cudaError_t - 1000. */
+#define MCXB_OK             0
+#define MCXB_ERR_ARG       -1    /* invalid argument / unsupported configuration  */
+#define MCXB_ERR_NODEVICE  -99   /* "Specified GPU does not exist" (src/mcx_host.cpp:533) */
+#define MCXB_ERR_NOMEM     -6
+#define MCXB_ERR_CUDA_BASE -1000
+
+typedef struct mcxb_f4 {
+    float x, y, z, w;
+} mcxb_f4;
+
+/* one source record == MCXSrc (src/mcx_host.h:99-104) == ExtraSrc (src/mcx_utils.h:101-106) */
+typedef struct mcxb_source {
+    mcxb_f4 pos;      /* xyz in voxel units (0-based), w = initial weight */
+    mcxb_f4 dir;      /* unit vector, w = focal length / angular-mode selector */
+    mcxb_f4 param1;
+    mcxb_f4 param2;   /* .z/.w = launch voxel idx / label as uint bits for point-like sources */
+} mcxb_source;
+
+/* source types: same numbering as MCX_SRC_* (src/mcx_const.h:75-92) */
+enum mcxb_srctype {
+    MCXB_SRC_PENCIL = 0, MCXB_SRC_ISOTROPIC, MCXB_SRC_CONE, MCXB_SRC_GAUSSIAN, MCXB_SRC_PLANAR,
+    MCXB_SRC_PATTERN, MCXB_SRC_FOURIER, MCXB_SRC_ARCSINE, MCXB_SRC_DISK, MCXB_SRC_FOURIERX,
+    MCXB_SRC_FOURIERX2D, MCXB_SRC_ZGAUSSIAN, MCXB_SRC_LINE, MCXB_SRC_SLIT, MCXB_SRC_PENCILARRAY,
+    MCXB_SRC_PATTERN3D, MCXB_SRC_HYPERBOLOID_GAUSSIAN, MCXB_SRC_RING
+};
+
+/* output types: same numbering as TOutputType (src/mcx_utils.h:58-60); only the first three and
+ * otL are on the hot path of this build */
+enum mcxb_outputtype { MCXB_OT_FLUX = 0, MCXB_OT_FLUENCE = 1, MCXB_OT_ENERGY = 2, MCXB_OT_L = 7 };
+
+/* boundary codes: TBoundary (src/mcx_utils.h:65) */
+enum mcxb_boundary { MCXB_BC_UNKNOWN = 0, MCXB_BC_REFLECT, MCXB_BC_ABSORB, MCXB_BC_MIRROR, MCXB_BC_CYCLIC };
+
+/* photon -> thread scheduling */
+enum mcxb_sched {
+    MCXB_SCHED_DYNAMIC = 0,  /* persistent threads pull photons from a per-GPU counter (default) */
+    MCXB_SCHED_STATIC  = 1   /* the reference's threadphoton/oddphoton split
+                                (src/mcx_host.cpp:1011-1012, src/mcx_core.cl:2442) -- reproducible
+                                stream->photon mapping, used by the oracle-parity tests */
+};
+
+typedef struct mcxb_config {
+    uint32_t abi_version;          /* must be MCXB_ABI_VERSION */
+
+    /* ---- domain: Config.dim / vol / unitinmm ---- */
+    uint32_t dimx, dimy, dimz;
+    const uint32_t* vol;           /* dimx*dimy*dimz words, x fastest; bits 0..30 label, bit 31 detector mask */
+    float    unitinmm;
+
+    /* ---- media table: Config.prop / medianum ({mua,mus,g,n}, row 0 = background) ---- */
+    uint32_t medianum;
+    const mcxb_f4* prop;
+
+    /* ---- sources: Config.srctype/srcpos/srcdir/srcparam1/srcparam2/srcdata/srcid/srcpattern ---- */
+    int32_t  srctype;
+    mcxb_source src;
+    uint32_t extrasrclen;
+    const mcxb_source* srcdata;    /* extrasrclen records or NULL */
+    int32_t  srcid;                /* 0: pick randomly, one volume; k>0: only source k; -1: one volume per source */
+    uint32_t srcnum;               /* number of patterns (photon sharing when >1; only 1 supported) */
+    const float* srcpattern;       /* pattern / pattern3d intensity table or NULL */
+
+    /* ---- detectors: Config.detpos/detnum/issavedet/savedetflag/maxdetphoton ---- */
+    uint32_t detnum;
+    const mcxb_f4* detpos;         /* xyz centre (voxel units, 0-based), w = radius */
+    int32_t  issavedet;
+    uint32_t savedetflag;          /* bits D S P M X V W (I unsupported), src/mcx_const.h:94-101 */
+    uint32_t maxdetphoton;
+    int32_t  issaveseed;
+    int32_t  issaveref;
+
+    /* ---- time gates ---- */
+    float tstart, tstep, tend;
+
+    /* ---- photon budget and RNG ---- */
+    uint64_t nphoton;
+    int32_t  seed;                 /* >0: srand(seed)-compatible stream; <=0: time(0) like the reference */
+    uint64_t seed_skip;            /* number of per-thread seed records (4 x rand()) to discard first:
+                                      rank r of a multi-GPU job passes r*nthread so that every GPU gets the
+                                      next slice of ONE rand() stream (src/mcx_host.cpp:759-768) */
+
+    /* ---- physics switches ---- */
+    int32_t  isreflect;
+    uint8_t  bc[12];               /* [0..5] boundary codes -x,-y,-z,+x,+y,+z; [6..11] detect-on-face flags */
+    int32_t  isspecular;
+    float    minenergy;
+    uint32_t gscatter;
+    int32_t  maxvoidstep;
+    int32_t  voidtime;
+    int32_t  outputtype;
+    int32_t  isnormalized;
+    int32_t  issave2pt;
+    uint32_t debuglevel;           /* bit 0 (MCX_DEBUG_RNG): fill field with rand_uniform01 draws and return */
+
+    /* ---- launch shape ---- */
+    uint32_t nthread;              /* 0 = autopilot (persistent grid sized from the SM count) */
+    uint32_t nblocksize;           /* 0 = autopilot */
+    int32_t  sched;                /* enum mcxb_sched */
+} mcxb_config;
+
+typedef struct mcxb_output {
+    /* caller-owned buffers (may be NULL to skip that output) */
+    float*    field;               /* fieldlen floats; results are ADDED to the existing contents, as the
+                                      reference does with cfg->exportfield (src/mcx_host.cpp:1292-1296),
+                                      then normalised in place when isnormalized */
+    uint64_t  fieldlen;            /* in: capacity; out: dimxyz*maxgate*(number of output volumes) */
+    float*    detphoton;           /* maxdetphoton*reclen floats */
+    uint64_t* seeddata;            /* maxdetphoton*2 words when issaveseed */
+    /* results */
+    uint32_t  detected;            /* photons that hit a detector (may exceed maxdetphoton) */
+    uint32_t  saved;               /* records actually stored = min(detected, maxdetphoton) */
+    uint32_t  reclen;              /* floats per record (hostdetreclen, src/mcx_host.cpp:496) */
+    uint32_t  maxgate;
+    double    energytot, energyesc, energyabs;
+    float     normalizer;
+    float     runtime_ms;          /* kernel window only, the reference's `runtime` (src/mcx_host.cpp:1078-1168) */
+    uint32_t  nthread, nblocksize; /* launch shape actually used */
+    uint64_t  kernel_launches;     /* number of CUDA kernels this call launched */
+} mcxb_output;
+
+/* subset of GPUInfo (src/mcx_utils.h:143-163) */
+typedef struct mcxb_gpuinfo {
+    char     name[64];
+    int32_t  id, devcount, major, minor;
+    uint64_t globalmem, constmem, sharedmem;
+    int32_t  regcount, clock_khz, sm, core;
+    uint64_t autoblock, autothread;
+    int32_t  maxmpthread;
+    uint64_t l2cache;
+} mcxb_gpuinfo;
+
+/* ---- one-shot API: what mcx_run_simulation / mcx_list_gpu bind to ---------------------------- */
+
+/* replaces mcx_list_gpu (src/mcx_host.cpp:252-432): fills up to `maxinfo` records, returns the
+ * number of CUDA devices (>=0) or a negative error code. */
+int mcxb_list_gpu(mcxb_gpuinfo* info, int maxinfo);
+
+/* replaces mcx_run_simulation (src/mcx_host.cpp:438-1849) on CUDA device `device`: uploads the
+ * HOST buffers of cfg, runs the photon kernel, reads back, folds and normalises into `out`. */
+int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_output* out);
+
+/* last error message of the calling thread ("" if none) */
+const char* mcxb_last_error(void);
+
+/* ---- staged API: the same path with inputs resident in HBM (bench `value`, multi-GPU plumbing) */
+typedef struct mcxb_sim mcxb_sim;
+
+int  mcxb_sim_create(const mcxb_config* cfg, int device, mcxb_sim** sim);   /* H2D of media, tables, seeds */
+int  mcxb_sim_reset(mcxb_sim* sim, void* cuda_stream);                      /* zero field / energy / counters, restore seeds */
+int  mcxb_sim_launch(mcxb_sim* sim, void* cuda_stream);                     /* enqueue the photon kernel; asynchronous */
+int  mcxb_sim_fetch(mcxb_sim* sim, void* cuda_stream, mcxb_output* out);    /* sync, D2H, normalise */
+/* raw device pointers, so a host framework (torch.distributed/NCCL) can reduce/gather in place */
+void*    mcxb_sim_field_devptr(mcxb_sim* sim);      /* float32[fieldlen] raw (un-normalised) deposits */
+void*    mcxb_sim_energy_devptr(mcxb_sim* sim);     /* double[2] = {escaped, launched} after mcxb_sim_reduce_energy */
+void*    mcxb_sim_detphoton_devptr(mcxb_sim* sim);  /* float32[maxdetphoton*reclen] */
+void*    mcxb_sim_detcount_devptr(mcxb_sim* sim);   /* uint32[1] */
+uint64_t mcxb_sim_fieldlen(mcxb_sim* sim);
+uint32_t mcxb_sim_reclen(mcxb_sim* sim);
+int  mcxb_sim_reduce_energy(mcxb_sim* sim, void* cuda_stream);              /* per-thread energy -> double[2] on device */
+float mcxb_sim_last_kernel_ms(mcxb_sim* sim);       /* CUDA-event time of the most recent launch (after sync) */
+void mcxb_sim_destroy(mcxb_sim* sim);
+
+/* host-side normalisation shared by fetch and by the multi-GPU reducer (src/mcx_host.cpp:1382-1465):
+ * returns the scale factor for the given totals */
+float mcxb_normalizer(const mcxb_config* cfg, double energytot);
+
+/* ---- unit-level hooks used by the parity tests (they run the SAME device functions the photon
+ *      kernel is built from) ------------------------------------------------------------------ */
+
+/* n RNG streams seeded with seeds[4*i..4*i+3] (xorshift128p_seed, src/mcx_core.cl:709-712); writes
+ * ndraw floats per stream to out[i*ndraw + k] and the final 128-bit state to state_out[2*i..] */
+int mcxb_test_rng(int device, const uint32_t* seeds, uint32_t n, uint32_t ndraw, float* out, uint64_t* state_out);
+
+/* voxel traversal of n fixed rays for nstep segments each, no scattering: per step writes
+ * dist, p.xyz (as float bit patterns), voxel ijk, face id and idx1d.  musp = the mus' used in the
+ * (dist*mus')/mus' round trip of src/mcx_core.cl:2678-2680. */
+typedef struct mcxb_trace_step {
+    float    dist;
+    float    px, py, pz;
+    int16_t  ix, iy, iz, face;
+    uint32_t idx1d;
+} mcxb_trace_step;
+int mcxb_test_trace(int device, const mcxb_f4* p0, const mcxb_f4* v0, uint32_t n, uint32_t nstep,
+                    uint32_t dimx, uint32_t dimy, uint32_t dimz, float musp, mcxb_trace_step* out);
+
+/* scalar helpers: mcx_nextafterf (src/mcx_core.cl:965-973), reflectcoeff (:1057-1075) */
+int mcxb_test_scalar(int device, const float* a, const int32_t* dir, uint32_t n, float* nextafter_out,
+                     const mcxb_f4* v, const float* n1, const float* n2, const int32_t* face, uint32_t m, float* rcoef_out);
+
+/* glibc rand()-compatible seed table used by mcxb_sim_create (src/mcx_host.cpp:696-700, 759-768) */
+void mcxb_fill_seeds(int32_t seed, uint64_t skip_records, uint64_t nrecords, uint32_t* out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

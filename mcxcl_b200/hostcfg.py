@@ -1,0 +1,371 @@
+"""Host-side mirror of the reference's configuration layer for the photon-transport path.
+
+`prepare(cfg_dict)` accepts the same keys as ``pmcxcl.run(**cfg)`` (reference src/pmcxcl.cpp:428-1110),
+applies the defaults of ``mcx_initcfg`` (src/mcx_utils.c:203-366), the checks of ``mcx_validatecfg``
+(:1822-1964) and the transformations of ``mcx_preprocess`` (:1521-1809) and ``mcx_maskdet``
+(:4085-4198), and returns a `Prepared` object that owns the numpy buffers and the ctypes
+``mcxb_config`` handed to the C ABI (include/mcxb200.h).  Only what the hot path consumes is
+mirrored; file formats, shapes, replay and polarised input stay with the reference's own host code
+(INTEGRATION.md shows how that code binds to the same ABI).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import abi
+
+SRCTYPES = ["pencil", "isotropic", "cone", "gaussian", "planar", "pattern", "fourier", "arcsine", "disk",
+            "fourierx", "fourierx2d", "zgaussian", "line", "slit", "pencilarray", "pattern3d", "hyperboloid", "ring"]
+OUTPUTTYPES = {"flux": 0, "fluence": 1, "energy": 2, "length": 7, "x": 0, "f": 1, "e": 2, "l": 7}
+BC_CODES = "_ramc"           # boundarycond[] (src/mcx_utils.c:170)
+SAVEFLAGS = "DSPMXVWI"       # saveflag[]     (src/mcx_utils.c:134)
+DET_MASK = 0x80000000
+MED_MASK = 0x7FFFFFFF
+HOST_EPS = np.float32(1e-10)  # EPS of src/mcx_const.h:33 (host side)
+
+
+class ConfigError(ValueError):
+    """Raised where the reference calls MCX_ERROR(id, msg); .code carries the id."""
+
+    def __init__(self, code, msg):
+        super().__init__("MCXCL ERROR(%d):%s" % (code, msg))
+        self.code = code
+
+
+def _f4(v, w_default=0.0):
+    v = [float(x) for x in np.asarray(v, dtype=np.float64).ravel()]
+    if len(v) == 3:
+        v.append(w_default)
+    if len(v) != 4:
+        raise ConfigError(-6, "vector fields must have 3 or 4 elements")
+    return np.array(v, dtype=np.float32)
+
+
+def parse_savedetflag(flag):
+    if isinstance(flag, str):
+        out = 0
+        for ch in flag.upper():
+            i = SAVEFLAGS.find(ch)
+            if i < 0:
+                raise ConfigError(-6, "unknown savedetflag letter %r" % ch)
+            out |= 1 << i
+        return out
+    return int(flag)
+
+
+def parse_bc(bc):
+    """'aarraa' / '______111111' -> 12 integer codes (mcx_lookupindex, src/mcx_utils.c:1562-1575)."""
+    codes = np.zeros(12, dtype=np.uint8)
+    if bc is None:
+        return codes
+    if not isinstance(bc, str):
+        arr = np.asarray(bc, dtype=np.uint8).ravel()
+        codes[:len(arr)] = arr[:12]
+        return codes
+    for i, ch in enumerate(bc[:12]):
+        if i < 6:
+            k = BC_CODES.find(ch)
+            if k < 0:
+                raise ConfigError(-4, "unknown boundary condition specifier")
+        else:
+            k = "01".find(ch)
+            if k < 0:
+                raise ConfigError(-4, "unknown boundary detection flags")
+        codes[i] = k
+    return codes
+
+
+def maskdet(vol, dims, detpos):
+    """Flag the surface voxels covered by each detector sphere in bit 31 (mcx_maskdet).
+
+    vol: uint32[dimxyz] x-fastest (modified in place); returns the per-detector voxel counts.
+    Follows src/mcx_utils.c:4085-4198 statement by statement, in float32 like the C code.
+    """
+    nx, ny, nz = dims
+    f32 = np.float32
+    pad = np.zeros((nz + 2, ny + 2, nx + 2), dtype=np.uint32)
+    pad[1:-1, 1:-1, 1:-1] = vol.reshape(nz, ny, nx)
+    isonecube = (nx == 1 and ny == 1 and nz == 1)
+    corners = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1)]
+    nb = [(dz, dy, dx) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dz, dy, dx) != (0, 0, 0)]
+    counts = []
+    vol3 = vol.reshape(nz, ny, nx)
+    for d in range(len(detpos)):
+        cx, cy, cz, r = [f32(t) for t in detpos[d]]
+        count = 0
+        d2max = (r + f32(1.7321)) * (r + f32(1.7321))
+        lim = (r + f32(0.5) * f32(1 + isonecube)) ** 2
+        z = -r - f32(1)
+        while z <= r + f32(1):
+            iz = z + cz
+            y = -r - f32(1)
+            while y <= r + f32(1):
+                iy = y + cy
+                x = -r - f32(1)
+                while x <= r + f32(1):
+                    ix = x + cx
+                    xx = x
+                    x = x + f32(0.5)
+                    if (iz < 0 or ix < 0 or iy < 0 or ix >= nx or iy >= ny or iz >= nz or
+                            xx * xx + y * y + z * z > (r + f32(1)) * (r + f32(1))):
+                        continue
+                    mind2 = None
+                    for c in corners:
+                        rx = f32(int(ix)) - cx + f32(c[0])
+                        ry = f32(int(iy)) - cy + f32(c[1])
+                        rz = f32(int(iz)) - cz + f32(c[2])
+                        d2 = rx * rx + ry * ry + rz * rz
+                        if d2 > d2max:
+                            mind2 = None
+                            break
+                        if mind2 is None or d2 < mind2:
+                            mind2 = d2
+                    if mind2 is None or mind2 >= lim:
+                        continue
+                    pz, py, px = int(iz + f32(1)), int(iy + f32(1)), int(ix + f32(1))
+                    if pad[pz, py, px]:
+                        if not all(pad[pz + a, py + b, px + c2] for a, b, c2 in nb):
+                            vol3[int(iz), int(iy), int(ix)] |= np.uint32(DET_MASK)
+                            count += 1
+                y = y + f32(0.5)
+            z = z + f32(0.5)
+        counts.append(count)
+    return counts
+
+
+class Prepared:
+    """Validated, pre-processed simulation input; owns every buffer the ctypes config points to."""
+
+    def __init__(self):
+        self.c = abi.Config()
+        self.keep = {}
+        self.session = ""
+        self.det_voxels = []
+
+    # derived quantities, computed exactly like src/mcx_host.cpp:474, 494-496, 647
+    @property
+    def dims(self):
+        return (self.c.dimx, self.c.dimy, self.c.dimz)
+
+    @property
+    def dimxyz(self):
+        return self.c.dimx * self.c.dimy * self.c.dimz
+
+    @property
+    def maxgate(self):
+        return int((np.float32(self.c.tend) - np.float32(self.c.tstart)) / np.float32(self.c.tstep) + 0.5)
+
+    @property
+    def nsrcvol(self):
+        if self.c.srctype in (5, 15):
+            return max(1, self.c.srcnum)
+        return self.c.extrasrclen + 1 if self.c.srcid < 0 else 1
+
+    @property
+    def fieldlen(self):
+        return self.dimxyz * self.maxgate * self.nsrcvol
+
+    @property
+    def partialdata(self):
+        f = self.c.savedetflag if self.c.issavedet else 0
+        return (self.c.medianum - 1) * ((f >> 1 & 1) + (f >> 2 & 1) + (f >> 3 & 1))
+
+    @property
+    def reclen(self):
+        f = self.c.savedetflag if self.c.issavedet else 0
+        return self.partialdata + (f & 1) + 3 * ((f >> 4 & 1) + (f >> 5 & 1)) + (f >> 6 & 1) + 4 * (f >> 7 & 1)
+
+    def clone_for(self, nphoton=None, seed=None, seed_skip=None, **overrides):
+        """Shallow copy sharing the big buffers, with a different photon budget / seed slice."""
+        other = Prepared()
+        C.memmove(C.byref(other.c), C.byref(self.c), C.sizeof(abi.Config))
+        other.keep = self.keep
+        other.session = self.session
+        other.det_voxels = self.det_voxels
+        if nphoton is not None:
+            other.c.nphoton = int(nphoton)
+        if seed is not None:
+            other.c.seed = int(seed)
+        if seed_skip is not None:
+            other.c.seed_skip = int(seed_skip)
+        for k, v in overrides.items():
+            setattr(other.c, k, v)
+        return other
+
+
+def prepare(cfg):
+    """dict -> Prepared.  Mirrors parse_config + mcx_validatecfg + mcx_preprocess for the hot path."""
+    if "vol" not in cfg or "prop" not in cfg:
+        raise ConfigError(-4, "You must define 'vol' and 'prop' field.")
+    p = Prepared()
+    c = p.c
+    c.abi_version = abi.ABI_VERSION
+    p.session = str(cfg.get("session", ""))
+
+    vol = np.asarray(cfg["vol"])
+    if vol.ndim != 3:
+        raise ConfigError(-4, "the 'vol' field must be a 3D array (label-based media only)")
+    if vol.size == 0:
+        raise ConfigError(-4, "the 'vol' field in the input structure can not be empty")
+    nx, ny, nz = vol.shape
+    flat = np.ascontiguousarray(vol.astype(np.uint32, copy=False).ravel(order="F")).copy()
+    c.dimx, c.dimy, c.dimz = nx, ny, nz
+
+    prop = np.array(cfg["prop"], dtype=np.float32).reshape(-1, 4).copy()
+    if prop.shape[0] == 0:
+        raise ConfigError(-4, "you must define the 'prop' field in the input structure")
+    c.medianum = prop.shape[0]
+
+    # --- defaults of mcx_initcfg -------------------------------------------------------------
+    c.tstart = float(cfg.get("tstart", 0.0))
+    c.tend = float(cfg.get("tend", 5e-9))
+    c.tstep = float(cfg.get("tstep", 5e-9))
+    c.nphoton = int(cfg.get("nphoton", 0))
+    c.seed = int(cfg.get("seed", 0x623F9A9E))
+    c.seed_skip = int(cfg.get("seed_skip", 0))
+    c.isreflect = int(cfg.get("isreflect", 1))
+    c.isnormalized = int(cfg.get("isnormalized", 1))
+    c.issavedet = int(cfg.get("issavedet", 1))
+    c.issave2pt = int(cfg.get("issave2pt", 1))
+    c.unitinmm = float(cfg.get("unitinmm", 1.0))
+    c.minenergy = float(cfg.get("minenergy", 0.0))
+    c.savedetflag = parse_savedetflag(cfg.get("savedetflag", 0x5))
+    c.gscatter = int(cfg.get("gscatter", 1000000000))
+    c.isspecular = int(cfg.get("isspecular", 0))
+    c.maxvoidstep = int(cfg.get("maxvoidstep", 1000))
+    c.voidtime = int(cfg.get("voidtime", 1))
+    c.maxdetphoton = int(cfg.get("maxdetphoton", 1000000))
+    c.srcnum = int(cfg.get("srcnum", 1))
+    c.srcid = int(cfg.get("srcid", 0))
+    c.issaveseed = int(cfg.get("issaveseed", 0))
+    c.issaveref = int(cfg.get("issaveref", 0))
+    c.nthread = int(cfg.get("nthread", 0)) if not cfg.get("autopilot", 1) or "nthread" in cfg else 0
+    c.nblocksize = int(cfg.get("nblocksize", 0)) if "nblocksize" in cfg else 0
+    c.sched = int(cfg.get("sched", 0))
+    dbg = cfg.get("debuglevel", 0)
+    if isinstance(dbg, str):
+        dbg = sum(1 << "RMPT".find(ch) for ch in dbg.upper() if ch in "RMPT")
+    c.debuglevel = int(dbg)
+    ot = cfg.get("outputtype", "flux")
+    if isinstance(ot, str):
+        if ot.lower() not in OUTPUTTYPES:
+            raise ConfigError(-6, "output type %r is outside the photon-transport hot path of this build" % ot)
+        ot = OUTPUTTYPES[ot.lower()]
+    c.outputtype = int(ot)
+    st = cfg.get("srctype", "pencil")
+    if isinstance(st, str):
+        if st not in SRCTYPES:
+            raise ConfigError(-6, "the specified source type is not supported")
+        st = SRCTYPES.index(st)
+    c.srctype = int(st)
+    if int(cfg.get("respin", 1)) != 1:
+        raise ConfigError(-1, "respin != 1 is not supported by this build (see DESIGN.md, reference quirk C)")
+
+    # --- sources: N x 4 arrays define extra sources (src/pmcxcl.cpp:477-660) -------------------
+    def rows(key, default, wdef):
+        a = np.atleast_2d(np.asarray(cfg.get(key, default), dtype=np.float64))
+        return np.stack([_f4(r, wdef) for r in a])
+
+    srcpos = rows("srcpos", [0, 0, 0, 1], 1.0)
+    nsrc = srcpos.shape[0]
+    srcdir = rows("srcdir", [0, 0, 1, 0], 0.0)
+    srcp1 = rows("srcparam1", [0, 0, 0, 0], 0.0)
+    srcp2 = rows("srcparam2", [0, 0, 0, 0], 0.0)
+
+    def bcast(a):
+        return a if a.shape[0] == nsrc else np.repeat(a[:1], nsrc, axis=0)
+
+    srcdir, srcp1, srcp2 = bcast(srcdir), bcast(srcp1), bcast(srcp2)
+    issrcfrom0 = int(cfg.get("issrcfrom0", 0))
+    if not issrcfrom0:                      # mcx_validatecfg: convert to 0-based grid coordinates
+        srcpos[:, :3] -= 1.0
+
+    if c.tstart > c.tend or c.tstep == 0.0:
+        raise ConfigError(-6, "incorrect time gate settings")
+    if c.tend <= c.tstart:
+        raise ConfigError(-6, "field 'tend' must be greater than field 'tstart'")
+
+    # mcx_preprocess: normalise direction (double precision like the C code)
+    # (only the main source, :1524-1533; extra sources are taken as given)
+    d = srcdir[0, :3].astype(np.float64)
+    n = math.sqrt(float((d * d).sum()))
+    if n < 1e-10:
+        raise ConfigError(-4, "source initial direction vector can not have a length of 0")
+    srcdir[0, :3] = (d * (1.0 / n)).astype(np.float32)
+
+    if c.debuglevel & 1:                    # MCX_DEBUG_RNG
+        c.isnormalized = 0
+        c.issavedet = 0
+
+    bc = parse_bc(cfg.get("bc"))
+    isbcdet = bool(bc[6:].any())
+    for i in range(12):
+        c.bc[i] = int(bc[i])
+
+    if c.unitinmm != 1.0:
+        u = np.float32(c.unitinmm)
+        prop[1:, 0] *= u
+        prop[1:, 1] *= u
+    detpos = np.array(cfg.get("detpos", np.zeros((0, 4))), dtype=np.float32).reshape(-1, 4).copy()
+    if not issrcfrom0 and len(detpos):
+        detpos[:, :3] -= 1.0
+    c.detnum = detpos.shape[0]
+    if c.issavedet and c.detnum == 0 and not isbcdet:
+        c.issavedet = 0
+    if c.issavedet == 0:
+        c.savedetflag = 0
+    prop[prop[:, 1] == 0.0, 1] = HOST_EPS
+    srcpos[srcpos[:, 3] == 0.0, 3] = 1.0
+    if nsrc > 1:
+        if c.srcnum > 1:
+            raise ConfigError(-4, "simulating multiple sources currently can not be used with photon-sharing")
+        if c.srcid > nsrc:
+            raise ConfigError(-4, "srcid exceeds total defined source count")
+    if c.srcnum > 1:
+        raise ConfigError(-4, "photon-sharing pattern sources (srcnum>1) are outside the hot path of this build")
+
+    maxlabel = int((flat & MED_MASK).max())
+    if c.medianum <= maxlabel:
+        raise ConfigError(-4, "input media optical properties are less than the labels in the volume")
+    if c.srctype in (5, 15) and cfg.get("srcpattern") is None:
+        raise ConfigError(-4, "the 'srcpattern' field can not be empty when your 'srctype' is 'pattern'")
+
+    # launch voxel / label of point-like sources, as raw uint bits in param2.z/.w (:1718-1749)
+    if c.srctype <= 2 or c.srctype in (7, 11):
+        for i in range(nsrc):
+            x, y, z = srcpos[i, :3]
+            if x < 0 or y < 0 or z < 0 or x >= nx or y >= ny or z >= nz:
+                idx, lab = 0, 0
+            else:
+                idx = int(math.floor(z)) * (ny * nx) + int(math.floor(y)) * nx + int(math.floor(x))
+                lab = int(flat[idx] & MED_MASK)
+            srcp2[i, 2:4] = np.array([idx, lab], dtype=np.uint32).view(np.float32)
+
+    if c.issavedet:
+        p.det_voxels = maskdet(flat, (nx, ny, nz), detpos)
+    if c.issavedet and c.savedetflag == 0:
+        c.savedetflag = 0x5
+    c.savedetflag &= ~0x80                  # no Stokes vector without polarised media
+    if c.issaveref > 1:
+        raise ConfigError(-4, "issaveref > 1 is outside the hot path of this build")
+
+    # --- publish buffers ---------------------------------------------------------------------
+    src = np.zeros((nsrc, 16), dtype=np.float32)
+    src[:, 0:4], src[:, 4:8], src[:, 8:12], src[:, 12:16] = srcpos, srcdir, srcp1, srcp2
+    C.memmove(C.byref(c.src), src[0].ctypes.data, 64)
+    c.extrasrclen = nsrc - 1
+    extra = np.ascontiguousarray(src[1:])
+    p.keep.update(vol=flat, prop=prop, detpos=detpos, srcall=src, extra=extra)
+    c.vol = flat.ctypes.data_as(C.POINTER(C.c_uint32))
+    c.prop = prop.ctypes.data_as(C.POINTER(abi.F4))
+    c.detpos = detpos.ctypes.data_as(C.POINTER(abi.F4)) if c.detnum else None
+    c.srcdata = extra.ctypes.data_as(C.POINTER(abi.Source)) if nsrc > 1 else None
+    if cfg.get("srcpattern") is not None:
+        pat = np.asarray(cfg["srcpattern"], dtype=np.float32)
+        pat = np.ascontiguousarray(pat.ravel(order="F")).copy()
+        p.keep["srcpattern"] = pat
+        c.srcpattern = pat.ctypes.data_as(C.POINTER(C.c_float))
+        if c.srctype == 5 and pat.size < int(srcp1[0, 3]) * int(srcp2[0, 3]):
+            raise ConfigError(-4, "srcpattern is smaller than srcparam1.w x srcparam2.w")
+    return p
