@@ -73,6 +73,16 @@ enum mcxb_sched {
                                 stream->photon mapping, used by the oracle-parity tests */
 };
 
+/* fluence accumulator precision on the device.  The reference keeps fp32 accumulators accurate at 1e8+
+ * photons by spilling +-1000 into a shadow copy of the volume using the value returned by the atomic
+ * (MAX_ACCUM, src/mcx_core.cl:516, 2882-2887; folded by the host, src/mcx_host.cpp:1252-1258).  This
+ * engine's default is fire-and-forget fp64 reductions (same memory as field+shadow, no return trip);
+ * MCXB_ACCUM_F32 selects plain fp32 reductions (half the L2 footprint, fine below ~1e7 photons). */
+enum mcxb_accum { MCXB_ACCUM_F64 = 0, MCXB_ACCUM_F32 = 1 };
+
+#define MCXB_DEBUG_RNG   1u
+#define MCXB_DEBUG_STATS 0x10000u
+
 typedef struct mcxb_config {
     uint32_t abi_version;          /* must be MCXB_ABI_VERSION */
 
@@ -93,6 +103,12 @@ typedef struct mcxb_config {
     int32_t  srcid;                /* 0: pick randomly, one volume; k>0: only source k; -1: one volume per source */
     uint32_t srcnum;               /* number of patterns (photon sharing when >1; only 1 supported) */
     const float* srcpattern;       /* pattern / pattern3d intensity table or NULL */
+    uint64_t srcpattern_len;       /* number of floats in srcpattern */
+    /* optional inverse-CDF tables: Config.invcdf/nphase (scattering cos(theta)), Config.angleinvcdf/nangle
+     * (launch zenith angle / pi); src/mcx_core.cl:2102-2118, 2475-2482 */
+    uint32_t nphase, nangle;
+    const float* invcdf;
+    const float* angleinvcdf;
 
     /* ---- detectors: Config.detpos/detnum/issavedet/savedetflag/maxdetphoton ---- */
     uint32_t detnum;
@@ -124,12 +140,15 @@ typedef struct mcxb_config {
     int32_t  outputtype;
     int32_t  isnormalized;
     int32_t  issave2pt;
-    uint32_t debuglevel;           /* bit 0 (MCX_DEBUG_RNG): fill field with rand_uniform01 draws and return */
+    uint32_t debuglevel;           /* bit 0 (MCX_DEBUG_RNG): fill field with rand_uniform01 draws and return;
+                                      MCXB_DEBUG_STATS: run the instrumented kernel that counts segments,
+                                      deposits and scattering events (mcxb_output.stats) */
 
     /* ---- launch shape ---- */
     uint32_t nthread;              /* 0 = autopilot (persistent grid sized from the SM count) */
     uint32_t nblocksize;           /* 0 = autopilot */
     int32_t  sched;                /* enum mcxb_sched */
+    int32_t  accum;                /* enum mcxb_accum: precision of the device fluence accumulators */
 } mcxb_config;
 
 typedef struct mcxb_output {
@@ -150,6 +169,7 @@ typedef struct mcxb_output {
     float     runtime_ms;          /* kernel window only, the reference's `runtime` (src/mcx_host.cpp:1078-1168) */
     uint32_t  nthread, nblocksize; /* launch shape actually used */
     uint64_t  kernel_launches;     /* number of CUDA kernels this call launched */
+    uint64_t  stats[3];            /* MCXB_DEBUG_STATS: ray segments, fluence deposits, scattering events */
 } mcxb_output;
 
 /* subset of GPUInfo (src/mcx_utils.h:143-163) */
@@ -182,16 +202,22 @@ typedef struct mcxb_sim mcxb_sim;
 int  mcxb_sim_create(const mcxb_config* cfg, int device, mcxb_sim** sim);   /* H2D of media, tables, seeds */
 int  mcxb_sim_reset(mcxb_sim* sim, void* cuda_stream);                      /* zero field / energy / counters, restore seeds */
 int  mcxb_sim_launch(mcxb_sim* sim, void* cuda_stream);                     /* enqueue the photon kernel; asynchronous */
-int  mcxb_sim_fetch(mcxb_sim* sim, void* cuda_stream, mcxb_output* out);    /* sync, D2H, normalise */
-/* raw device pointers, so a host framework (torch.distributed/NCCL) can reduce/gather in place */
+int  mcxb_sim_set_photons(mcxb_sim* sim, uint64_t nphoton);                 /* change the photon budget of the next launch */
+int  mcxb_sim_finalize(mcxb_sim* sim, void* cuda_stream);                   /* accumulators -> float32 volume on the device; asynchronous */
+int  mcxb_sim_fetch(mcxb_sim* sim, void* cuda_stream, mcxb_output* out);    /* finalize if needed, sync, D2H, add into out->field, normalise */
+/* raw device pointers, valid after mcxb_sim_finalize, so that a host framework (torch.distributed / NCCL)
+ * can reduce the volume and the energy totals across GPUs in place before rank 0 calls mcxb_sim_fetch
+ * (the reference sums per-device results on the host, src/mcx_host.cpp:1292-1306) */
 void*    mcxb_sim_field_devptr(mcxb_sim* sim);      /* float32[fieldlen] raw (un-normalised) deposits */
-void*    mcxb_sim_energy_devptr(mcxb_sim* sim);     /* double[2] = {escaped, launched} after mcxb_sim_reduce_energy */
+void*    mcxb_sim_energy_devptr(mcxb_sim* sim);     /* double[2] = {escaped, launched} */
 void*    mcxb_sim_detphoton_devptr(mcxb_sim* sim);  /* float32[maxdetphoton*reclen] */
 void*    mcxb_sim_detcount_devptr(mcxb_sim* sim);   /* uint32[1] */
+void*    mcxb_sim_seeddata_devptr(mcxb_sim* sim);   /* uint64[maxdetphoton*2] or NULL */
 uint64_t mcxb_sim_fieldlen(mcxb_sim* sim);
 uint32_t mcxb_sim_reclen(mcxb_sim* sim);
-int  mcxb_sim_reduce_energy(mcxb_sim* sim, void* cuda_stream);              /* per-thread energy -> double[2] on device */
-float mcxb_sim_last_kernel_ms(mcxb_sim* sim);       /* CUDA-event time of the most recent launch (after sync) */
+uint32_t mcxb_sim_nthread(mcxb_sim* sim);           /* threads (= RNG streams) this simulation uses */
+const char* mcxb_sim_kernel_name(mcxb_sim* sim);    /* which specialisation was selected */
+float mcxb_sim_last_kernel_ms(mcxb_sim* sim);       /* CUDA-event time of the most recent launch (syncs on it) */
 void mcxb_sim_destroy(mcxb_sim* sim);
 
 /* host-side normalisation shared by fetch and by the multi-GPU reducer (src/mcx_host.cpp:1382-1465):
@@ -220,6 +246,18 @@ int mcxb_test_trace(int device, const mcxb_f4* p0, const mcxb_f4* v0, uint32_t n
 /* scalar helpers: mcx_nextafterf (src/mcx_core.cl:965-973), reflectcoeff (:1057-1075) */
 int mcxb_test_scalar(int device, const float* a, const int32_t* dir, uint32_t n, float* nextafter_out,
                      const mcxb_f4* v, const float* n1, const float* n2, const int32_t* face, uint32_t m, float* rcoef_out);
+
+/* rotatevector (src/mcx_core.cl:1025-1042) and transmit (:1044-1055) on n vectors, in place (fast tier:
+ * compared with a tolerance, not bit-exactly) */
+int mcxb_test_rotate(int device, mcxb_f4* v, const float* stheta, const float* ctheta, const float* sphi, const float* cphi, uint32_t n);
+int mcxb_test_refract(int device, mcxb_f4* v, const float* n1, const float* n2, const int32_t* face, uint32_t n);
+
+/* L2 reduction microbenchmark (the measured denominator of the RED roofline in bench.py): nblock*256
+ * threads each issue `iters` red.global.add of 4- or 8-byte elements to pseudo-random addresses inside a
+ * span_elems buffer; hot_permille of them are clustered on 64 elements.  Returns the mean time of one
+ * launch in ms and the number of reductions per launch. */
+int mcxb_bench_red(int device, int elem_bytes, uint64_t span_elems, uint32_t nblock, uint32_t iters,
+                   uint32_t hot_permille, uint32_t repeats, float* ms_out, uint64_t* ops_out);
 
 /* glibc rand()-compatible seed table used by mcxb_sim_create (src/mcx_host.cpp:696-700, 759-768) */
 void mcxb_fill_seeds(int32_t seed, uint64_t skip_records, uint64_t nrecords, uint32_t* out4);

@@ -7,6 +7,10 @@ import ctypes as C
 import os
 
 ABI_VERSION = 1
+DEBUG_RNG = 1
+DEBUG_STATS = 0x10000
+ACCUM_F64, ACCUM_F32 = 0, 1
+SCHED_DYNAMIC, SCHED_STATIC = 0, 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcxb200.so")
 
@@ -41,6 +45,10 @@ class Config(C.Structure):
         ("srcid", C.c_int32),
         ("srcnum", C.c_uint32),
         ("srcpattern", C.POINTER(C.c_float)),
+        ("srcpattern_len", C.c_uint64),
+        ("nphase", C.c_uint32), ("nangle", C.c_uint32),
+        ("invcdf", C.POINTER(C.c_float)),
+        ("angleinvcdf", C.POINTER(C.c_float)),
         ("detnum", C.c_uint32),
         ("detpos", C.POINTER(F4)),
         ("issavedet", C.c_int32),
@@ -66,6 +74,7 @@ class Config(C.Structure):
         ("nthread", C.c_uint32),
         ("nblocksize", C.c_uint32),
         ("sched", C.c_int32),
+        ("accum", C.c_int32),
     ]
 
 
@@ -85,6 +94,7 @@ class Output(C.Structure):
         ("runtime_ms", C.c_float),
         ("nthread", C.c_uint32), ("nblocksize", C.c_uint32),
         ("kernel_launches", C.c_uint64),
+        ("stats", C.c_uint64 * 3),
     ]
 
 
@@ -119,14 +129,18 @@ SYMBOLS = [
     ("mcxb_sim_create", C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(_VP)]),
     ("mcxb_sim_reset", C.c_int, [_VP, _VP]),
     ("mcxb_sim_launch", C.c_int, [_VP, _VP]),
+    ("mcxb_sim_set_photons", C.c_int, [_VP, C.c_uint64]),
+    ("mcxb_sim_finalize", C.c_int, [_VP, _VP]),
     ("mcxb_sim_fetch", C.c_int, [_VP, _VP, C.POINTER(Output)]),
     ("mcxb_sim_field_devptr", _VP, [_VP]),
     ("mcxb_sim_energy_devptr", _VP, [_VP]),
     ("mcxb_sim_detphoton_devptr", _VP, [_VP]),
     ("mcxb_sim_detcount_devptr", _VP, [_VP]),
+    ("mcxb_sim_seeddata_devptr", _VP, [_VP]),
     ("mcxb_sim_fieldlen", C.c_uint64, [_VP]),
     ("mcxb_sim_reclen", C.c_uint32, [_VP]),
-    ("mcxb_sim_reduce_energy", C.c_int, [_VP, _VP]),
+    ("mcxb_sim_nthread", C.c_uint32, [_VP]),
+    ("mcxb_sim_kernel_name", C.c_char_p, [_VP]),
     ("mcxb_sim_last_kernel_ms", C.c_float, [_VP]),
     ("mcxb_sim_destroy", None, [_VP]),
     ("mcxb_normalizer", C.c_float, [C.POINTER(Config), C.c_double]),
@@ -134,6 +148,10 @@ SYMBOLS = [
     ("mcxb_test_trace", C.c_int, [C.c_int, _VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_float, _VP]),
     ("mcxb_test_scalar", C.c_int, [C.c_int, _VP, _VP, C.c_uint32, _VP, _VP, _VP, _VP, _VP, C.c_uint32, _VP]),
+    ("mcxb_test_rotate", C.c_int, [C.c_int, _VP, _VP, _VP, _VP, _VP, C.c_uint32]),
+    ("mcxb_test_refract", C.c_int, [C.c_int, _VP, _VP, _VP, _VP, C.c_uint32]),
+    ("mcxb_bench_red", C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                 C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     ("mcxb_fill_seeds", None, [C.c_int32, C.c_uint64, C.c_uint64, _VP]),
 ]
 

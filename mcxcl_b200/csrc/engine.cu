@@ -1,0 +1,922 @@
+/*
+ * engine.cu -- CUDA-runtime host module behind the C ABI of include/mcxb200.h.
+ *
+ * It replaces, for the photon-transport path only, what the reference's OpenCL host does inside
+ * mcx_run_simulation (src/mcx_host.cpp:438-1849): parameter packing (:494-524, 674-694), thread/block
+ * autoconfiguration (:586-633), per-thread seeding from one glibc rand() stream (:696-700, 759-768),
+ * buffer upload (:739-830), kernel launch and timing window (:1078-1168), readback, accumulation
+ * (:1242-1306) and normalisation (:1382-1465); and device enumeration (mcx_list_gpu, :252-432).
+ *
+ * There is no CPU path: every entry point that needs a device fails with a CUDA error code when no
+ * device is present.
+ */
+#include "../../include/mcxb200.h"
+#include "kernel_registry.h"
+
+#include <cstdio>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <ctime>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace mcxb;
+
+/* ------------------------------------------------------------------------------------------------- */
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(call)                                                                                         \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            return fail(MCXB_ERR_CUDA_BASE - (int)e__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                                 \
+        }                                                                                                    \
+    } while (0)
+
+extern "C" const char* mcxb_last_error(void) {
+    return g_last_error.c_str();
+}
+
+/* -------------------------------------------------------------------------------------------------
+ * glibc-compatible rand() stream (TYPE_3 additive feedback generator, degree 31, separation 3), so the
+ * per-thread seeds are the ones the reference host produces with srand(seed); rand() without
+ * depending on the C library's hidden global state.
+ * ------------------------------------------------------------------------------------------------- */
+namespace {
+struct GlibcRand {
+    uint32_t r[31];
+    int f, b;
+    explicit GlibcRand(uint32_t seed) {
+        if (seed == 0) {
+            seed = 1;
+        }
+
+        int32_t word = (int32_t)seed;
+        r[0] = (uint32_t)word;
+
+        for (int i = 1; i < 31; i++) {
+            const long hi = word / 127773, lo = word % 127773;
+            long w = 16807 * lo - 2836 * hi;
+
+            if (w < 0) {
+                w += 2147483647;
+            }
+
+            word = (int32_t)w;
+            r[i] = (uint32_t)word;
+        }
+
+        f = 3;
+        b = 0;
+
+        for (int i = 0; i < 310; i++) {
+            next();
+        }
+    }
+    uint32_t next() {
+        r[f] += r[b];
+        const uint32_t out = r[f] >> 1;
+        f = (f + 1 == 31) ? 0 : f + 1;
+        b = (b + 1 == 31) ? 0 : b + 1;
+        return out;
+    }
+};
+} // namespace
+
+extern "C" void mcxb_fill_seeds(int32_t seed, uint64_t skip_records, uint64_t nrecords, uint32_t* out4) {
+    GlibcRand g(seed > 0 ? (uint32_t)seed : (uint32_t)time(NULL));
+
+    for (uint64_t i = 0; i < skip_records * 4; i++) {
+        (void)g.next();
+    }
+
+    for (uint64_t i = 0; i < nrecords * 4; i++) {
+        out4[i] = g.next();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------- */
+static int cores_per_sm(int major, int minor) {
+    /* same table idea as mcx_nv_corecount (src/mcx_host.cpp:224-240), extended to Hopper/Blackwell */
+    if (major < 2) {
+        return 8;
+    }
+
+    if (major == 2) {
+        return minor == 0 ? 32 : 48;
+    }
+
+    if (major == 3) {
+        return 192;
+    }
+
+    if (major == 5) {
+        return 128;
+    }
+
+    if (major == 6) {
+        return minor == 0 ? 64 : 128;
+    }
+
+    if (major == 7) {
+        return 64;
+    }
+
+    if (major == 8) {
+        return minor == 0 ? 64 : 128;
+    }
+
+    return 128;
+}
+
+extern "C" int mcxb_list_gpu(mcxb_gpuinfo* info, int maxinfo) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+
+    if (e != cudaSuccess) {
+        if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
+            cudaGetLastError();
+            return 0;
+        }
+
+        return fail(MCXB_ERR_CUDA_BASE - (int)e, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+
+    for (int i = 0; i < n && i < maxinfo && info; i++) {
+        cudaDeviceProp p;
+        CU_TRY(cudaGetDeviceProperties(&p, i));
+        mcxb_gpuinfo* g = info + i;
+        memset(g, 0, sizeof(*g));
+        strncpy(g->name, p.name, sizeof(g->name) - 1);
+        g->id = i + 1;
+        g->devcount = n;
+        g->major = p.major;
+        g->minor = p.minor;
+        g->globalmem = p.totalGlobalMem;
+        g->constmem = p.totalConstMem;
+        g->sharedmem = p.sharedMemPerBlock;
+        g->regcount = p.regsPerBlock;
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, i);
+        g->clock_khz = khz;
+        g->sm = p.multiProcessorCount;
+        g->core = p.multiProcessorCount * cores_per_sm(p.major, p.minor);
+        g->maxmpthread = p.maxThreadsPerMultiProcessor;
+        g->autoblock = kBlock;
+        g->autothread = (uint64_t)kBlock * 3 * p.multiProcessorCount;
+        g->l2cache = (uint64_t)p.l2CacheSize;
+    }
+
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------------- */
+struct mcxb_sim {
+    int device = 0;
+    mcxb_config cfg;                 /* scalar fields only; host pointers are not kept */
+    SimParam P;
+    PhotonKernelFn fn = nullptr;
+    const char* kname = "";
+    bool acc64 = true, media16 = false, rngdebug = false;
+    uint32_t nblock = 0, nthread = 0;
+    size_t smem = 0;
+    uint64_t fieldlen = 0;
+    uint32_t reclen = 0, maxgate = 0, nsrcvol = 1;
+    /* device buffers */
+    void* d_media = nullptr;
+    void* d_field = nullptr;
+    float* d_field32 = nullptr;
+    float4* d_tables = nullptr;
+    uint32_t* d_seeds = nullptr;
+    float* d_det = nullptr;
+    uint32_t* d_detcount = nullptr;
+    unsigned long long* d_seedout = nullptr;
+    unsigned long long* d_counter = nullptr;
+    double* d_energy = nullptr;
+    float* d_pattern = nullptr;
+    float* d_invcdf = nullptr;
+    unsigned long long* d_stats = nullptr;
+    /* pinned staging */
+    float* h_field = nullptr;
+    double* h_small = nullptr;       /* energy[2], detcount, stats[3] */
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool finalized = false, launched = false;
+    uint64_t launches = 0;
+    float last_ms = 0.f;
+};
+
+static const KernelEntry* find_kernel(int src, bool refl, bool det, bool m16, bool acc64, bool stats) {
+    typedef const KernelEntry* (*GroupFn)(int*);
+    static const GroupFn groups[kNumGroups] = { mcxb_kernel_group_0, mcxb_kernel_group_1, mcxb_kernel_group_2,
+                                                mcxb_kernel_group_3, mcxb_kernel_group_4, mcxb_kernel_group_5
+                                              };
+
+    for (int pass = 0; pass < 2; pass++) {
+        const int want = pass == 0 ? src : (int)srcAny;
+
+        for (int g = 0; g < kNumGroups; g++) {
+            int n = 0;
+            const KernelEntry* e = groups[g](&n);
+
+            for (int i = 0; i < n; i++) {
+                if (e[i].src == want && e[i].reflect == refl && e[i].savedet == det && e[i].media16 == m16 &&
+                        e[i].acc64 == acc64 && e[i].stats == stats) {
+                    return e + i;
+                }
+            }
+        }
+    }
+
+    return nullptr;
+}
+
+/* the reference's rule for compiling the reflection code in (src/mcx_host.cpp:945-956) */
+static bool needs_reflection(const mcxb_config* cfg) {
+    bool allabsorb = true, allunknown = true;
+
+    for (int i = 0; i < 6; i++) {
+        if (cfg->bc[i] != MCXB_BC_ABSORB) {
+            allabsorb = false;
+        }
+
+        if (cfg->bc[i] != MCXB_BC_UNKNOWN) {
+            allunknown = false;
+        }
+    }
+
+    if (cfg->bc[0] == 0) {      /* the reference compares C strings: a leading NUL reads as "unknown" */
+        allunknown = true;
+        allabsorb = false;
+    }
+
+    return cfg->isreflect || (!allabsorb && !allunknown);
+}
+
+static uint32_t count_gates(const mcxb_config* cfg) {
+    return (uint32_t)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);
+}
+
+extern "C" float mcxb_normalizer(const mcxb_config* cfg, double energytot) {
+    /* src/mcx_host.cpp:1389-1396, 1449-1451; Vvox = steps.x*steps.y*steps.z with steps == unitinmm */
+    float scale = 1.f;
+    const float Vvox = cfg->unitinmm * cfg->unitinmm * cfg->unitinmm;
+
+    if (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE) {
+        scale = (float)(cfg->unitinmm / (energytot * Vvox * cfg->tstep));
+
+        if (cfg->outputtype == MCXB_OT_FLUENCE) {
+            scale *= cfg->tstep;
+        }
+    } else if (cfg->outputtype == MCXB_OT_ENERGY || cfg->outputtype == MCXB_OT_L) {
+        scale = (float)(1.0 / energytot);
+    }
+
+    if (cfg->extrasrclen && cfg->srcid < 0) {
+        scale *= (float)(cfg->extrasrclen + 1);
+    }
+
+    return scale;
+}
+
+/* ---- small device kernels -------------------------------------------------------------------- */
+template <typename AccT>
+__global__ void finalize_kernel(const AccT* __restrict__ acc, float* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        out[i] = (float)acc[i];
+    }
+}
+
+/* MCX_DEBUG_RNG mode of the reference kernel (src/mcx_core.cl:2408-2414) */
+__global__ void rngdebug_kernel(const uint32_t* __restrict__ seeds, float* __restrict__ out, uint32_t n, uint32_t nthread) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+
+    if (tid >= nthread) {
+        return;
+    }
+
+    Rng rng;
+    rng_seed(rng, seeds + 4 * (size_t)tid);
+
+    for (uint32_t i = tid; i < n; i += nthread) {
+        out[i] = rng_uniform(rng);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------- */
+static void sim_free(mcxb_sim* s) {
+    if (!s) {
+        return;
+    }
+
+    cudaSetDevice(s->device);
+    cudaFree(s->d_media);
+    cudaFree(s->d_field);
+    cudaFree(s->d_field32);
+    cudaFree(s->d_tables);
+    cudaFree(s->d_seeds);
+    cudaFree(s->d_det);
+    cudaFree(s->d_detcount);
+    cudaFree(s->d_seedout);
+    cudaFree(s->d_counter);
+    cudaFree(s->d_energy);
+    cudaFree(s->d_pattern);
+    cudaFree(s->d_invcdf);
+    cudaFree(s->d_stats);
+    cudaFreeHost(s->h_field);
+    cudaFreeHost(s->h_small);
+
+    if (s->ev0) {
+        cudaEventDestroy(s->ev0);
+    }
+
+    if (s->ev1) {
+        cudaEventDestroy(s->ev1);
+    }
+
+    delete s;
+}
+
+extern "C" void mcxb_sim_destroy(mcxb_sim* sim) {
+    sim_free(sim);
+}
+
+static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
+    if (!cfg || cfg->abi_version != MCXB_ABI_VERSION) {
+        return fail(MCXB_ERR_ARG, "mcxb_config.abi_version mismatch (library %d)", MCXB_ABI_VERSION);
+    }
+
+    if (!cfg->vol || !cfg->prop || cfg->dimx == 0 || cfg->dimy == 0 || cfg->dimz == 0 || cfg->medianum == 0) {
+        return fail(MCXB_ERR_ARG, "volume and media table are required");
+    }
+
+    if (cfg->dimx > 32767 || cfg->dimy > 32767 || cfg->dimz > 32767 || (uint64_t)cfg->dimx * cfg->dimy * cfg->dimz >= 0x7FFFFFFFull) {
+        return fail(MCXB_ERR_ARG, "grid dimensions exceed the 16-bit voxel coordinates of the photon kernel");
+    }
+
+    if (cfg->srctype < 0 || cfg->srctype > MCXB_SRC_RING) {
+        return fail(MCXB_ERR_ARG, "the specified source type is not supported");
+    }
+
+    if (cfg->tstep <= 0.f || cfg->tend <= cfg->tstart) {
+        return fail(MCXB_ERR_ARG, "incorrect time gate settings");
+    }
+
+    if (cfg->srcnum > 1) {
+        return fail(MCXB_ERR_ARG, "photon-sharing pattern sources (srcnum>1) are outside this build's hot path");
+    }
+
+    if ((cfg->srctype == MCXB_SRC_PATTERN || cfg->srctype == MCXB_SRC_PATTERN3D) && (!cfg->srcpattern || cfg->srcpattern_len == 0)) {
+        return fail(MCXB_ERR_ARG, "pattern sources need srcpattern");
+    }
+
+    if (cfg->outputtype != MCXB_OT_FLUX && cfg->outputtype != MCXB_OT_FLUENCE && cfg->outputtype != MCXB_OT_ENERGY && cfg->outputtype != MCXB_OT_L) {
+        return fail(MCXB_ERR_ARG, "output type %d is outside this build's hot path", cfg->outputtype);
+    }
+
+    if (cfg->extrasrclen && !cfg->srcdata) {
+        return fail(MCXB_ERR_ARG, "extrasrclen>0 but srcdata is NULL");
+    }
+
+    if (cfg->extrasrclen && cfg->srcid > (int32_t)cfg->extrasrclen + 1) {
+        return fail(MCXB_ERR_ARG, "srcid exceeds total defined source count");
+    }
+
+    if (cfg->issavedet && cfg->detnum && !cfg->detpos) {
+        return fail(MCXB_ERR_ARG, "detnum>0 but detpos is NULL");
+    }
+
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+
+    if (device < 0 || device >= ndev) {
+        return fail(MCXB_ERR_NODEVICE, "Specified GPU does not exist");
+    }
+
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+
+    if (prop.major < 10) {
+        return fail(MCXB_ERR_NODEVICE, "this engine is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    }
+
+    s->device = device;
+    s->cfg = *cfg;
+    s->cfg.vol = nullptr;
+    s->cfg.prop = nullptr;
+    s->cfg.srcdata = nullptr;
+    s->cfg.srcpattern = nullptr;
+    s->cfg.detpos = nullptr;
+    s->cfg.invcdf = nullptr;
+    s->cfg.angleinvcdf = nullptr;
+
+    const uint64_t dimxyz = (uint64_t)cfg->dimx * cfg->dimy * cfg->dimz;
+    const uint32_t maxgate = count_gates(cfg);
+
+    if (maxgate == 0) {
+        return fail(MCXB_ERR_ARG, "incorrect time gate settings");
+    }
+
+    const uint32_t nsrcvol = (cfg->srcid < 0) ? cfg->extrasrclen + 1 : 1;
+    s->maxgate = maxgate;
+    s->nsrcvol = nsrcvol;
+    s->fieldlen = dimxyz * maxgate * nsrcvol;
+    s->rngdebug = (cfg->debuglevel & 1u) != 0;
+    const bool savedet = cfg->issavedet != 0 && !s->rngdebug;
+    const uint32_t flag = savedet ? (cfg->savedetflag & 0x7Fu) : 0u;
+    const uint32_t nmed = cfg->medianum - 1;
+    const uint32_t partialdata = nmed * ((flag >> 1 & 1u) + (flag >> 2 & 1u) + (flag >> 3 & 1u));
+    s->reclen = partialdata + (flag & 1u) + 3 * ((flag >> 4 & 1u) + (flag >> 5 & 1u)) + (flag >> 6 & 1u);
+
+    /* ---- media volume: labels packed to 8 (or 16) bits with the detector flag in the top bit ---- */
+    uint32_t maxlabel = 0;
+
+    for (uint64_t i = 0; i < dimxyz; i++) {
+        maxlabel = std::max(maxlabel, cfg->vol[i] & 0x7FFFFFFFu);
+    }
+
+    if (maxlabel >= cfg->medianum) {
+        return fail(MCXB_ERR_ARG, "input media optical properties are less than the labels in the volume");
+    }
+
+    s->media16 = maxlabel > 127;
+
+    if (maxlabel > 32767) {
+        return fail(MCXB_ERR_ARG, "more than 32767 media labels are not supported");
+    }
+
+    {
+        std::vector<uint8_t> packed(dimxyz * (s->media16 ? 2 : 1));
+
+        if (s->media16) {
+            uint16_t* p = reinterpret_cast<uint16_t*>(packed.data());
+
+            for (uint64_t i = 0; i < dimxyz; i++) {
+                p[i] = (uint16_t)((cfg->vol[i] & 0x7FFFu) | ((cfg->vol[i] & 0x80000000u) ? 0x8000u : 0u));
+            }
+        } else {
+            for (uint64_t i = 0; i < dimxyz; i++) {
+                packed[i] = (uint8_t)((cfg->vol[i] & 0x7Fu) | ((cfg->vol[i] & 0x80000000u) ? 0x80u : 0u));
+            }
+        }
+
+        CU_TRY(cudaMalloc(&s->d_media, packed.size()));
+        CU_TRY(cudaMemcpy(s->d_media, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+    }
+
+    /* ---- tables: media, sources (main first), detectors ---- */
+    const uint32_t tablen = cfg->medianum + 4 * (1 + cfg->extrasrclen) + cfg->detnum;
+    {
+        std::vector<float4> tab(tablen);
+
+        for (uint32_t i = 0; i < cfg->medianum; i++) {
+            tab[i] = make_float4(cfg->prop[i].x, cfg->prop[i].y, cfg->prop[i].z, cfg->prop[i].w);
+        }
+
+        auto put = [&](uint32_t at, const mcxb_source & src) {
+            tab[at + 0] = make_float4(src.pos.x, src.pos.y, src.pos.z, src.pos.w);
+            tab[at + 1] = make_float4(src.dir.x, src.dir.y, src.dir.z, src.dir.w);
+            tab[at + 2] = make_float4(src.param1.x, src.param1.y, src.param1.z, src.param1.w);
+            tab[at + 3] = make_float4(src.param2.x, src.param2.y, src.param2.z, src.param2.w);
+        };
+        put(cfg->medianum, cfg->src);
+
+        for (uint32_t i = 0; i < cfg->extrasrclen; i++) {
+            put(cfg->medianum + 4 * (i + 1), cfg->srcdata[i]);
+        }
+
+        for (uint32_t i = 0; i < cfg->detnum; i++) {
+            tab[cfg->medianum + 4 * (1 + cfg->extrasrclen) + i] = make_float4(cfg->detpos[i].x, cfg->detpos[i].y, cfg->detpos[i].z, cfg->detpos[i].w);
+        }
+
+        CU_TRY(cudaMalloc(&s->d_tables, sizeof(float4) * tablen));
+        CU_TRY(cudaMemcpy(s->d_tables, tab.data(), sizeof(float4) * tablen, cudaMemcpyHostToDevice));
+    }
+
+    if (cfg->srcpattern && cfg->srcpattern_len) {
+        CU_TRY(cudaMalloc(&s->d_pattern, sizeof(float) * cfg->srcpattern_len));
+        CU_TRY(cudaMemcpy(s->d_pattern, cfg->srcpattern, sizeof(float) * cfg->srcpattern_len, cudaMemcpyHostToDevice));
+    }
+
+    const uint32_t nphase = cfg->invcdf ? cfg->nphase : 0, nangle = cfg->angleinvcdf ? cfg->nangle : 0;
+
+    if (nphase + nangle) {
+        std::vector<float> t(nphase + nangle);
+
+        if (nphase) {
+            memcpy(t.data(), cfg->invcdf, sizeof(float) * nphase);
+        }
+
+        if (nangle) {
+            memcpy(t.data() + nphase, cfg->angleinvcdf, sizeof(float) * nangle);
+        }
+
+        CU_TRY(cudaMalloc(&s->d_invcdf, sizeof(float) * t.size()));
+        CU_TRY(cudaMemcpy(s->d_invcdf, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
+    }
+
+    /* ---- kernel choice and launch shape ---- */
+    s->acc64 = cfg->accum != MCXB_ACCUM_F32;
+    const bool refl = needs_reflection(cfg);
+    const bool stats = (cfg->debuglevel & MCXB_DEBUG_STATS) != 0;
+    const KernelEntry* ke = stats ? find_kernel(srcAny, true, true, s->media16, true, true)
+                            : find_kernel(cfg->srctype, refl, savedet, s->media16, s->acc64, false);
+
+    if (!ke) {
+        return fail(MCXB_ERR_ARG, "no kernel specialisation for this configuration");
+    }
+
+    if (stats) {
+        s->acc64 = true;
+    }
+
+    s->fn = ke->fn;
+    s->kname = ke->name;
+    const uint32_t ftablen = (nphase + nangle + 1u) & ~1u;
+    s->smem = sizeof(float4) * tablen + sizeof(float) * ftablen + (ke->savedet ? sizeof(float) * partialdata * kBlock : 0)
+              + (cfg->issaveseed ? 2 * sizeof(unsigned long long) * kBlock : 0);
+
+    if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
+        return fail(MCXB_ERR_NOMEM, "configuration needs %zu bytes of shared memory per block (limit %zu)", s->smem, (size_t)prop.sharedMemPerBlockOptin);
+    }
+
+    if (s->smem > 48 * 1024) {
+        CU_TRY(cudaFuncSetAttribute((const void*)s->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    }
+
+    int perSM = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (const void*)s->fn, kBlock, s->smem));
+
+    if (perSM < 1) {
+        return fail(MCXB_ERR_NOMEM, "photon kernel does not fit on an SM");
+    }
+
+    if (cfg->nthread) {
+        s->nblock = std::max(1u, cfg->nthread / kBlock);
+    } else {
+        s->nblock = (uint32_t)(prop.multiProcessorCount * perSM);      /* persistent: exactly one resident wave */
+    }
+
+    s->nthread = s->nblock * kBlock;
+
+    /* ---- seeds ---- */
+    {
+        std::vector<uint32_t> seeds((size_t)s->nthread * 4);
+        mcxb_fill_seeds(cfg->seed, cfg->seed_skip, s->nthread, seeds.data());
+        CU_TRY(cudaMalloc(&s->d_seeds, seeds.size() * 4));
+        CU_TRY(cudaMemcpy(s->d_seeds, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice));
+    }
+
+    /* ---- outputs ---- */
+    CU_TRY(cudaMalloc(&s->d_field, (s->acc64 ? 8 : 4) * s->fieldlen));
+    CU_TRY(cudaMalloc(&s->d_field32, 4 * s->fieldlen));
+    CU_TRY(cudaMalloc(&s->d_energy, 2 * sizeof(double)));
+    CU_TRY(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
+    CU_TRY(cudaMalloc(&s->d_detcount, sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&s->d_stats, 3 * sizeof(unsigned long long)));
+
+    if (savedet) {
+        CU_TRY(cudaMalloc(&s->d_det, sizeof(float) * std::max<size_t>(1, (size_t)cfg->maxdetphoton * std::max(1u, s->reclen))));
+
+        if (cfg->issaveseed) {
+            CU_TRY(cudaMalloc(&s->d_seedout, 2 * sizeof(unsigned long long) * std::max<size_t>(1, cfg->maxdetphoton)));
+        }
+    }
+
+    CU_TRY(cudaMallocHost(&s->h_field, 4 * s->fieldlen));
+    CU_TRY(cudaMallocHost(&s->h_small, 8 * sizeof(double)));
+    CU_TRY(cudaEventCreate(&s->ev0));
+    CU_TRY(cudaEventCreate(&s->ev1));
+
+    /* ---- kernel parameters ---- */
+    SimParam& P = s->P;
+    memset(&P, 0, sizeof(P));
+    P.nx = cfg->dimx;
+    P.ny = cfg->dimy;
+    P.nz = cfg->dimz;
+    P.dimxy = cfg->dimx * cfg->dimy;
+    P.dimxyz = (uint32_t)dimxyz;
+    P.fieldlen = (uint32_t)std::min<uint64_t>(s->fieldlen, 0xFFFFFFFFu);
+    P.fnx = (float)cfg->dimx;
+    P.fny = (float)cfg->dimy;
+    P.fnz = (float)cfg->dimz;
+    P.twin0 = cfg->tstart;
+    P.twin1 = cfg->tstart + cfg->tstep * maxgate;        /* src/mcx_host.cpp:1076 */
+    P.Rtstep = 1.f / cfg->tstep;
+    const float R_C0 = 3.335640951981520e-12f;
+    P.oneoverc0 = R_C0 * cfg->unitinmm;
+    P.minaccumtime = cfg->unitinmm * R_C0 * cfg->unitinmm;
+    P.maxgate = maxgate;
+    P.minenergy = cfg->minenergy;
+    P.gscatter = cfg->gscatter;
+    P.doreflect = cfg->isreflect != 0;
+    P.save2pt = cfg->issave2pt != 0;
+    P.outputtype = (uint32_t)cfg->outputtype;
+    {
+        uint32_t is2d = (cfg->dimx == 1 ? 1 : (cfg->dimy == 1 ? 2 : (cfg->dimz == 1 ? 3 : 0)));
+
+        if (is2d) {
+            is2d = is2d * (((cfg->dimx > 1) + (cfg->dimy > 1) + (cfg->dimz > 1)) == 2);
+        }
+
+        P.is2d = is2d;
+    }
+    P.isspecular = cfg->isspecular > 0;
+    P.issaveref = (uint32_t)cfg->issaveref;
+    P.issaveseed = (savedet && cfg->issaveseed > 0) ? 1u : 0u;
+    P.voidtime = cfg->voidtime;
+    P.maxvoidstep = (uint32_t)cfg->maxvoidstep;
+    memcpy(P.bc, cfg->bc, 12);
+    P.srctype = cfg->srctype;
+    P.srcid = cfg->srcid;
+    P.extrasrclen = cfg->extrasrclen;
+    P.srcnum = std::max(1u, cfg->srcnum);
+    P.medianum = cfg->medianum;
+    P.detnum = cfg->detnum;
+    P.tablen = tablen;
+    P.tables = s->d_tables;
+    P.srcpattern = s->d_pattern;
+    P.nphase = nphase;
+    P.nangle = nangle;
+    P.ftablen = ftablen;
+    P.invcdf = s->d_invcdf;
+    P.angleinvcdf = s->d_invcdf ? s->d_invcdf + nphase : nullptr;
+    P.savedetflag = flag;
+    P.partialdata = partialdata;
+    P.reclen = s->reclen;
+    P.maxdetphoton = savedet ? cfg->maxdetphoton : 0;
+    P.detphoton = s->d_det;
+    P.detcount = s->d_detcount;
+    P.seedout = s->d_seedout;
+    P.nphoton = cfg->nphoton;
+    P.counter = s->d_counter;
+    P.sched = cfg->sched == MCXB_SCHED_STATIC ? 1 : 0;
+    P.threadphoton = (uint32_t)(cfg->nphoton / s->nthread);
+    P.oddphoton = (int32_t)(cfg->nphoton - (uint64_t)P.threadphoton * s->nthread);
+    {
+        /* photons claimed per refill: small enough that the last claims end together, large enough to keep
+         * the shared counter cold (about 16 refills per thread) */
+        const uint64_t per = cfg->nphoton / ((uint64_t)s->nthread * 16u);
+        P.chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(per, 1), 32);
+    }
+    P.media = s->d_media;
+    P.field = s->d_field;
+    P.seeds = s->d_seeds;
+    P.energy = s->d_energy;
+    P.stats = stats ? s->d_stats : nullptr;
+    return MCXB_OK;
+}
+
+extern "C" int mcxb_sim_create(const mcxb_config* cfg, int device, mcxb_sim** sim) {
+    if (!sim) {
+        return fail(MCXB_ERR_ARG, "sim is NULL");
+    }
+
+    *sim = nullptr;
+    mcxb_sim* s = new mcxb_sim();
+    const int rc = sim_create_impl(cfg, device, s);
+
+    if (rc != MCXB_OK) {
+        sim_free(s);
+        return rc;
+    }
+
+    *sim = s;
+    return MCXB_OK;
+}
+
+extern "C" int mcxb_sim_reset(mcxb_sim* s, void* cuda_stream) {
+    if (!s) {
+        return fail(MCXB_ERR_ARG, "sim is NULL");
+    }
+
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaMemsetAsync(s->d_field, 0, (s->acc64 ? 8 : 4) * s->fieldlen, st));
+    CU_TRY(cudaMemsetAsync(s->d_energy, 0, 2 * sizeof(double), st));
+    CU_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
+    CU_TRY(cudaMemsetAsync(s->d_detcount, 0, sizeof(uint32_t), st));
+    CU_TRY(cudaMemsetAsync(s->d_stats, 0, 3 * sizeof(unsigned long long), st));
+    s->finalized = false;
+    s->launched = false;
+    return MCXB_OK;
+}
+
+extern "C" int mcxb_sim_set_photons(mcxb_sim* s, uint64_t nphoton) {
+    if (!s) {
+        return fail(MCXB_ERR_ARG, "sim is NULL");
+    }
+
+    s->cfg.nphoton = nphoton;
+    s->P.nphoton = nphoton;
+    s->P.threadphoton = (uint32_t)(nphoton / s->nthread);
+    s->P.oddphoton = (int32_t)(nphoton - (uint64_t)s->P.threadphoton * s->nthread);
+    const uint64_t per = nphoton / ((uint64_t)s->nthread * 16u);
+    s->P.chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(per, 1), 32);
+    return MCXB_OK;
+}
+
+extern "C" int mcxb_sim_launch(mcxb_sim* s, void* cuda_stream) {
+    if (!s) {
+        return fail(MCXB_ERR_ARG, "sim is NULL");
+    }
+
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaEventRecord(s->ev0, st));
+
+    if (s->rngdebug) {
+        rngdebug_kernel <<< s->nblock, kBlock, 0, st>>>(s->d_seeds, s->d_field32, (uint32_t)s->fieldlen, s->nthread);
+        s->finalized = true;
+    } else {
+        void* args[] = { (void*)& s->P };
+        CU_TRY(cudaLaunchKernel((const void*)s->fn, dim3(s->nblock), dim3(kBlock), args, s->smem, st));
+    }
+
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(s->ev1, st));
+    s->launches++;
+    s->launched = true;
+    return MCXB_OK;
+}
+
+extern "C" int mcxb_sim_finalize(mcxb_sim* s, void* cuda_stream) {
+    if (!s) {
+        return fail(MCXB_ERR_ARG, "sim is NULL");
+    }
+
+    if (s->finalized) {
+        return MCXB_OK;
+    }
+
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU_TRY(cudaSetDevice(s->device));
+    const int grid = (int)std::min<uint64_t>((s->fieldlen + 255) / 256, 148 * 8);
+
+    if (s->acc64) {
+        finalize_kernel<double> <<< grid, 256, 0, st>>>((const double*)s->d_field, s->d_field32, s->fieldlen);
+    } else {
+        finalize_kernel<float> <<< grid, 256, 0, st>>>((const float*)s->d_field, s->d_field32, s->fieldlen);
+    }
+
+    CU_TRY(cudaGetLastError());
+    s->launches++;
+    s->finalized = true;
+    return MCXB_OK;
+}
+
+extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) {
+    if (!s || !out) {
+        return fail(MCXB_ERR_ARG, "sim/out is NULL");
+    }
+
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU_TRY(cudaSetDevice(s->device));
+    int rc = mcxb_sim_finalize(s, st);
+
+    if (rc != MCXB_OK) {
+        return rc;
+    }
+
+    const bool wantfield = out->field != nullptr && s->cfg.issave2pt;
+
+    if (out->field && out->fieldlen < s->fieldlen) {
+        return fail(MCXB_ERR_ARG, "field buffer too small: %llu < %llu", (unsigned long long)out->fieldlen, (unsigned long long)s->fieldlen);
+    }
+
+    if (wantfield) {
+        CU_TRY(cudaMemcpyAsync(s->h_field, s->d_field32, 4 * s->fieldlen, cudaMemcpyDeviceToHost, st));
+    }
+
+    CU_TRY(cudaMemcpyAsync(s->h_small, s->d_energy, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(s->h_small + 2, s->d_detcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(s->h_small + 3, s->d_stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+
+    if (s->launched) {
+        CU_TRY(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    }
+
+    uint32_t detected = 0;
+    memcpy(&detected, s->h_small + 2, sizeof(uint32_t));
+    out->energyesc = s->h_small[0];
+    out->energytot = s->h_small[1];
+    out->energyabs = out->energytot - out->energyesc;
+    out->detected = detected;
+    out->saved = s->d_det ? std::min(detected, s->cfg.maxdetphoton) : 0;
+    out->reclen = s->reclen;
+    out->maxgate = s->maxgate;
+    out->fieldlen = s->fieldlen;
+    out->runtime_ms = s->last_ms;
+    out->nthread = s->nthread;
+    out->nblocksize = kBlock;
+    out->kernel_launches = s->launches;
+    memcpy(out->stats, s->h_small + 3, 3 * sizeof(unsigned long long));
+
+    if (out->saved && out->detphoton) {
+        CU_TRY(cudaMemcpy(out->detphoton, s->d_det, sizeof(float) * (size_t)out->saved * s->reclen, cudaMemcpyDeviceToHost));
+    }
+
+    if (out->saved && out->seeddata && s->d_seedout) {
+        CU_TRY(cudaMemcpy(out->seeddata, s->d_seedout, 2 * sizeof(unsigned long long) * (size_t)out->saved, cudaMemcpyDeviceToHost));
+    }
+
+    out->normalizer = 1.f;
+
+    if (wantfield) {
+        /* cfg->exportfield[i] += field[i]  (src/mcx_host.cpp:1292-1296), then mcx_normalize (src/mcx_utils.c:1208-1218) */
+        float* dst = out->field;
+        const float* src = s->h_field;
+        const uint64_t n = s->fieldlen;
+
+        if (s->cfg.isnormalized && !s->rngdebug) {
+            const float scale = mcxb_normalizer(&s->cfg, out->energytot);
+            out->normalizer = scale;
+
+            for (uint64_t i = 0; i < n; i++) {
+                dst[i] = (dst[i] + src[i]) * scale;
+            }
+        } else {
+            for (uint64_t i = 0; i < n; i++) {
+                dst[i] += src[i];
+            }
+        }
+    }
+
+    return MCXB_OK;
+}
+
+extern "C" void* mcxb_sim_field_devptr(mcxb_sim* s) {
+    return s ? s->d_field32 : nullptr;
+}
+extern "C" void* mcxb_sim_energy_devptr(mcxb_sim* s) {
+    return s ? s->d_energy : nullptr;
+}
+extern "C" void* mcxb_sim_detphoton_devptr(mcxb_sim* s) {
+    return s ? s->d_det : nullptr;
+}
+extern "C" void* mcxb_sim_detcount_devptr(mcxb_sim* s) {
+    return s ? s->d_detcount : nullptr;
+}
+extern "C" void* mcxb_sim_seeddata_devptr(mcxb_sim* s) {
+    return s ? s->d_seedout : nullptr;
+}
+extern "C" uint64_t mcxb_sim_fieldlen(mcxb_sim* s) {
+    return s ? s->fieldlen : 0;
+}
+extern "C" uint32_t mcxb_sim_reclen(mcxb_sim* s) {
+    return s ? s->reclen : 0;
+}
+extern "C" uint32_t mcxb_sim_nthread(mcxb_sim* s) {
+    return s ? s->nthread : 0;
+}
+extern "C" const char* mcxb_sim_kernel_name(mcxb_sim* s) {
+    return s ? s->kname : "";
+}
+extern "C" float mcxb_sim_last_kernel_ms(mcxb_sim* s) {
+    if (!s || !s->launched) {
+        return 0.f;
+    }
+
+    float ms = 0.f;
+
+    if (cudaEventSynchronize(s->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) {
+        s->last_ms = ms;
+    }
+
+    return s->last_ms;
+}
+
+extern "C" int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_output* out) {
+    mcxb_sim* s = nullptr;
+    int rc = mcxb_sim_create(cfg, device, &s);
+
+    if (rc == MCXB_OK) {
+        rc = mcxb_sim_reset(s, nullptr);
+    }
+
+    if (rc == MCXB_OK) {
+        rc = mcxb_sim_launch(s, nullptr);
+    }
+
+    if (rc == MCXB_OK) {
+        rc = mcxb_sim_fetch(s, nullptr, out);
+    }
+
+    mcxb_sim_destroy(s);
+    return rc;
+}

@@ -1,0 +1,32 @@
+/*
+ * kernel_registry.h -- table of the ahead-of-time specialisations of photon_kernel.
+ *
+ * The reference JIT-compiles one OpenCL program per run with -D flags for source type, reflection and
+ * detector capture (src/mcx_host.cpp:857-971).  Here the same axes are C++ template parameters and
+ * every combination that is shipped is compiled for sm_100a at build time; kernels_inst.cu is compiled
+ * once per group (-DMCXB_INST_GROUP=k) so the groups build in parallel.
+ */
+#pragma once
+#include "photon_kernel.cuh"
+
+namespace mcxb {
+
+typedef void (*PhotonKernelFn)(const SimParam);
+
+struct KernelEntry {
+    int  src;          /* SrcType or srcAny */
+    bool reflect, savedet, media16, acc64, stats;
+    PhotonKernelFn fn;
+    const char* name;
+};
+
+constexpr int kNumGroups = 6;
+
+} // namespace mcxb
+
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_0(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_1(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_2(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_3(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_4(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_5(int* n);

@@ -1,0 +1,1065 @@
+/*
+ * photon_kernel.cuh -- the persistent photon-transport kernel for sm_100a.
+ *
+ * Work done per photon packet (the work of the reference's mcx_main_loop, src/mcx_core.cl:2307-3307, and
+ * launchnewphoton, :1466-2275 -- see SURVEY.md section 8(a) rows R1-R16): source sampling, scattering-length
+ * draw, Henyey-Greenstein deflection, voxel ray-marching with Beer-Lambert attenuation, time-gated
+ * fluence deposit, boundary handling (Fresnel / mirror / cyclic / absorb), Russian roulette, and
+ * detected-photon capture.
+ *
+ * B200 design:
+ *   - one persistent grid, a multiple of the SM count; threads pull photon batches from a per-GPU
+ *     counter (no static per-thread budget, so long-lived photons do not leave a tail);
+ *   - the media volume is a read-only byte (or 16-bit) volume with the detector flag in the top bit,
+ *     fetched through the non-coherent path; the optical-property table, extra sources and detector
+ *     list live in shared memory;
+ *   - fluence goes out as fire-and-forget RED.ADD into an L2-resident accumulator volume (fp64
+ *     accumulators by default: they make the reference's MAX_ACCUM shadow-buffer spill unnecessary);
+ *   - detected photons are compacted with a warp-aggregated atomic (ballot + popc);
+ *   - source type, reflection, detector capture, media word size and accumulator type are compile-time
+ *     specialisations, the same axes the reference JIT-specialises on (src/mcx_host.cpp:857-971).
+ */
+#pragma once
+#include "photon_device.cuh"
+
+namespace mcxb {
+
+/* same numbering as MCX_SRC_* (src/mcx_const.h:75-92) */
+enum SrcType {
+    srcPencil = 0, srcIsotropic, srcCone, srcGaussian, srcPlanar, srcPattern, srcFourier, srcArcsine, srcDisk,
+    srcFourierX, srcFourierX2D, srcZGaussian, srcLine, srcSlit, srcPencilArray, srcPattern3D, srcHyperboloid, srcRing,
+    srcAny = -1      /* decided at run time from SimParam::srctype */
+};
+
+struct SimParam {
+    /* domain */
+    uint32_t nx, ny, nz;
+    uint32_t dimxy, dimxyz;
+    uint32_t fieldlen;            /* dimxyz * maxgate * number of output volumes */
+    float    fnx, fny, fnz;
+    /* time window */
+    float    twin0, twin1, Rtstep;
+    float    oneoverc0;           /* R_C0 * unitinmm                  (src/mcx_host.cpp:512) */
+    float    minaccumtime;        /* unitinmm * R_C0 * unitinmm       (src/mcx_host.cpp:515) */
+    uint32_t maxgate;
+    /* physics switches */
+    float    minenergy;
+    uint32_t gscatter;
+    uint32_t doreflect, save2pt, outputtype, is2d;
+    uint32_t isspecular, issaveref, issaveseed;
+    int32_t  voidtime;
+    uint32_t maxvoidstep;
+    uint8_t  bc[12];
+    /* sources */
+    int32_t  srctype, srcid;
+    uint32_t extrasrclen, srcnum;
+    /* tables in shared memory: [medianum] media, then 4*(1+extrasrclen) source rows, then detnum detectors */
+    uint32_t medianum, detnum, tablen;
+    const float4* tables;
+    const float*  srcpattern;
+    /* launch-angle / phase-function inverse CDF tables (src/mcx_core.cl:2102-2118, 2475-2482) */
+    uint32_t nphase, nangle, ftablen;   /* ftablen = nphase+nangle rounded up to an even count */
+    const float* invcdf;
+    const float* angleinvcdf;
+    /* detected photons */
+    uint32_t savedetflag, partialdata, reclen, maxdetphoton;
+    float*    detphoton;
+    uint32_t* detcount;
+    unsigned long long* seedout;
+    /* photon budget */
+    unsigned long long  nphoton;
+    unsigned long long* counter;  /* dynamic scheduling: next unclaimed photon */
+    uint32_t chunk;               /* photons claimed per refill */
+    uint32_t threadphoton;        /* static scheduling (src/mcx_host.cpp:1011-1012) */
+    int32_t  oddphoton;
+    int32_t  sched;               /* 0 dynamic, 1 static */
+    /* volumes */
+    const void* media;
+    void*       field;
+    const uint32_t* seeds;        /* 4 words per thread */
+    double*     energy;           /* {escaped, launched} */
+    unsigned long long* stats;    /* optional {segments, deposits, scatters} counters, or NULL */
+};
+
+/* per-photon state that survives across segments */
+struct Photon {
+    float px, py, pz, w;          /* position (voxel units) and packet weight */
+    float vx, vy, vz;             /* direction */
+    int   nscat;                  /* scattering events so far; -1 = freshly launched (the EPS sentinel of :2254) */
+    float slen;                   /* remaining unitless scattering length (f.x) */
+    float tof;                    /* time of flight in seconds (f.y) */
+    int   ix, iy, iz, face;       /* current voxel and the face crossed last (flipdir) */
+    uint32_t idx1d;
+    uint32_t label;               /* media label of the current voxel */
+    uint32_t detflag;             /* detector bit of the current voxel, or the boundary code after leaving the grid */
+    float w0;                     /* weight at the last deposit */
+    float pathlen;                /* path length inside the current voxel */
+    float n1;                     /* refractive index of the medium the packet is coming from */
+};
+
+template <typename MediaT> struct MediaTraits;
+template <> struct MediaTraits<uint8_t> {
+    static constexpr uint32_t det = 0x80u, lab = 0x7Fu;
+};
+template <> struct MediaTraits<uint16_t> {
+    static constexpr uint32_t det = 0x8000u, lab = 0x7FFFu;
+};
+
+template <typename MediaT>
+__device__ __forceinline__ void fetch_voxel(const MediaT* __restrict__ media, uint32_t idx, uint32_t& label, uint32_t& det) {
+    const uint32_t m = __ldg(media + idx);
+    label = m & MediaTraits<MediaT>::lab;
+    det = (m & MediaTraits<MediaT>::det) ? kDetMask : 0u;
+}
+
+__device__ __forceinline__ bool inside(const SimParam& P, float x, float y, float z) {
+    return !(x < 0.f || y < 0.f || z < 0.f || x >= P.fnx || y >= P.fny || z >= P.fnz);
+}
+
+__device__ __forceinline__ uint32_t linear_index(const SimParam& P, int ix, int iy, int iz) {
+    return (uint32_t)(iz * (int)P.dimxy + iy * (int)P.nx + ix);
+}
+
+__device__ __forceinline__ bool voxel_in_grid(const SimParam& P, int ix, int iy, int iz) {
+    /* the reference compares (ushort)id against the float dimension (:2801) */
+    return (uint32_t)(ix & 0xFFFF) < P.nx && (uint32_t)(iy & 0xFFFF) < P.ny && (uint32_t)(iz & 0xFFFF) < P.nz;
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * march a packet launched outside the volume (or inside a zero voxel) up to the first non-zero voxel
+ * (src/mcx_core.cl:1350-1455).  Returns the linear index of the entry voxel or -1.
+ * ------------------------------------------------------------------------------------------------- */
+template <typename MediaT>
+__device__ __noinline__ int enter_volume(const SimParam& P, const float4* __restrict__ tab, Photon& ph) {
+    const MediaT* __restrict__ media = static_cast<const MediaT*>(P.media);
+    int count = 1;
+    ph.ix = (int)(short)floorf(ph.px);
+    ph.iy = (int)(short)floorf(ph.py);
+    ph.iz = (int)(short)floorf(ph.pz);
+    ph.face = -1;
+
+    while (true) {
+        if (voxel_in_grid(P, ph.ix, ph.iy, ph.iz)) {
+            int idx = (int)linear_index(P, ph.ix, ph.iy, ph.iz);
+            uint32_t lab, det;
+            fetch_voxel(media, (uint32_t)idx, lab, det);
+
+            if (lab) {
+                /* step back one unit and walk voxel by voxel to the entry face (:1364-1398) */
+                ph.px -= ph.vx;
+                ph.py -= ph.vy;
+                ph.pz -= ph.vz;
+                ph.ix = (int)(short)floorf(ph.px);
+                ph.iy = (int)(short)floorf(ph.py);
+                ph.iz = (int)(short)floorf(ph.pz);
+                ph.tof -= P.minaccumtime;
+                idx = (int)linear_index(P, ph.ix, ph.iy, ph.iz);
+                count = 0;
+
+                while (true) {
+                    bool in = voxel_in_grid(P, ph.ix, ph.iy, ph.iz);
+
+                    if (in) {
+                        fetch_voxel(media, (uint32_t)idx, lab, det);
+
+                        if (lab) {
+                            break;
+                        }
+                    }
+
+                    const float dist = face_distance(ph.px, ph.py, ph.pz, ph.vx, ph.vy, ph.vz, ph.ix, ph.iy, ph.iz, ph.face);
+                    ph.tof += P.minaccumtime * dist;
+                    ph.px = advance(ph.px, dist, ph.vx);
+                    ph.py = advance(ph.py, dist, ph.vy);
+                    ph.pz = advance(ph.pz, dist, ph.vz);
+
+                    if (ph.face == 0) {
+                        ph.ix += (ph.vx > 0.f ? 1 : -1);
+                    } else if (ph.face == 1) {
+                        ph.iy += (ph.vy > 0.f ? 1 : -1);
+                    } else {
+                        ph.iz += (ph.vz > 0.f ? 1 : -1);
+                    }
+
+                    idx = (int)linear_index(P, ph.ix, ph.iy, ph.iz);
+
+                    if (count++ > 3) {
+                        break;
+                    }
+                }
+
+                ph.tof = P.voidtime ? ph.tof : 0.f;
+
+                /* the reference reads media[idx] again here without a bounds check (:1420-1429); after a
+                 * failed refinement idx may lie outside the grid, so clamp the read instead */
+                uint32_t elab = 0;
+
+                if ((uint32_t)idx < P.dimxyz) {
+                    fetch_voxel(media, (uint32_t)idx, elab, det);
+                }
+
+                const float nin = tab[elab].w, nout = tab[0].w;
+
+                if (P.isspecular && nin != nout) {
+                    ph.w *= 1.f - fresnel(ph.vx, ph.vy, ph.vz, nout, nin, ph.face);
+
+                    if (ph.w > kEps) {
+                        refract(ph.vx, ph.vy, ph.vz, nout, nin, ph.face);
+                    }
+                }
+
+                return idx;
+            }
+        }
+
+        if ((ph.px < 0.f && ph.vx <= 0.f) || (ph.px >= P.fnx && ph.vx >= 0.f) ||
+                (ph.py < 0.f && ph.vy <= 0.f) || (ph.py >= P.fny && ph.vy >= 0.f) ||
+                (ph.pz < 0.f && ph.vz <= 0.f) || (ph.pz >= P.fnz && ph.vz >= 0.f)) {
+            return -1;
+        }
+
+        ph.px += ph.vx;
+        ph.py += ph.vy;
+        ph.pz += ph.vz;
+        ph.ix = (int)(short)floorf(ph.px);
+        ph.iy = (int)(short)floorf(ph.py);
+        ph.iz = (int)(short)floorf(ph.pz);
+        ph.tof += P.minaccumtime;
+
+        if ((uint32_t)count++ > P.maxvoidstep) {
+            return -1;
+        }
+    }
+}
+
+/* launch-time media lookup shared by the area sources (:1752-1758) */
+template <typename MediaT>
+__device__ __forceinline__ void locate(const SimParam& P, Photon& ph, uint32_t& rawlabel, uint32_t& rawdet) {
+    ph.idx1d = (uint32_t)((int)floorf(ph.pz) * (int)P.dimxy + (int)floorf(ph.py) * (int)P.nx + (int)floorf(ph.px));
+
+    if (inside(P, ph.px, ph.py, ph.pz)) {
+        fetch_voxel(static_cast<const MediaT*>(P.media), ph.idx1d, rawlabel, rawdet);
+    } else {
+        rawlabel = 0;
+        rawdet = 0;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * sample one packet from the source description S[0..3] = {pos, dir, param1, param2}
+ * (src/mcx_core.cl:1626-2153).  `focus` receives the point that the focal-length rule of :2140-2151
+ * aims at; `aimed` is false for the sources that set their own direction (Lmove = 0 in the reference).
+ * ------------------------------------------------------------------------------------------------- */
+template <int SRC, typename MediaT>
+__device__ __forceinline__ void sample_source(const SimParam& P, const float4* __restrict__ S, Rng& rng, Photon& ph,
+        uint32_t& rawlabel, uint32_t& rawdet, float& fx, float& fy, float& fz, bool& aimed) {
+    const int st = (SRC == srcAny) ? P.srctype : SRC;
+    const float4 pos = S[0], dir = S[1], p1 = S[2], p2 = S[3];
+    ph.px = pos.x;
+    ph.py = pos.y;
+    ph.pz = pos.z;
+    ph.w = pos.w;
+    ph.vx = dir.x;
+    ph.vy = dir.y;
+    ph.vz = dir.z;
+    ph.idx1d = __float_as_uint(p2.z);
+    rawlabel = __float_as_uint(p2.w) & 0x7FFFFFFFu;
+    rawdet = __float_as_uint(p2.w) & kDetMask;
+    fx = pos.x;
+    fy = pos.y;
+    fz = pos.z;
+    aimed = true;
+
+    if (st == srcPencil) {
+        /* position, direction and launch voxel come straight from the source record */
+    } else if (st == srcPlanar || st == srcPattern || st == srcPattern3D || st == srcFourier || st == srcPencilArray) {
+        const float rx = rng_uniform(rng);
+        const float ry = rng_uniform(rng);
+        float rz = 0.f;
+
+        if (st == srcPattern3D) {
+            rz = rng_uniform(rng);
+            ph.px += rx * p1.x;
+            ph.py += ry * p1.y;
+            ph.pz += rz * p1.z;
+        } else {
+            ph.px += rx * p1.x + ry * p2.x;
+            ph.py += rx * p1.y + ry * p2.y;
+            ph.pz += rx * p1.z + ry * p2.z;
+        }
+
+        if (st == srcPattern) {
+            ph.w = pos.w * __ldg(P.srcpattern + (int)(ry * kJustBelowOne * p2.w) * (int)p1.w + (int)(rx * kJustBelowOne * p1.w));
+        } else if (st == srcPattern3D) {
+            ph.w = pos.w * __ldg(P.srcpattern + (int)(rz * kJustBelowOne * p1.z) * (int)p1.y * (int)p1.x
+                                 + (int)(ry * kJustBelowOne * p1.y) * (int)p1.x + (int)(rx * kJustBelowOne * p1.x));
+        } else if (st == srcFourier) {
+            const float kx = floorf(p1.w), ky = floorf(p2.w);
+            ph.w = pos.w * (__cosf((kx * rx + ky * ry + p1.w - kx) * kTwoPi) * (1.f - p2.w + ky) + 1.f) * 0.5f;
+        } else if (st == srcPencilArray) {
+            const float gx = floorf(rx * p1.w), gy = floorf(ry * p2.w);
+            ph.px = pos.x + gx * p1.x / (p1.w - 1.f) + gy * p2.x / (p2.w - 1.f);
+            ph.py = pos.y + gx * p1.y / (p1.w - 1.f) + gy * p2.y / (p2.w - 1.f);
+            ph.pz = pos.z + gx * p1.z / (p1.w - 1.f) + gy * p2.z / (p2.w - 1.f);
+        }
+
+        locate<MediaT>(P, ph, rawlabel, rawdet);
+        fx += (p1.x + p2.x) * 0.5f;
+        fy += (p1.y + p2.y) * 0.5f;
+        fz += (p1.z + p2.z) * 0.5f;
+    } else if (st == srcFourierX || st == srcFourierX2D) {
+        const float rx = rng_uniform(rng);
+        const float ry = rng_uniform(rng);
+        const float s = p1.w * fast_rsqrt(p1.x * p1.x + p1.y * p1.y + p1.z * p1.z);
+        const float ux = s * (dir.y * p1.z - dir.z * p1.y);
+        const float uy = s * (dir.z * p1.x - dir.x * p1.z);
+        const float uz = s * (dir.x * p1.y - dir.y * p1.x);
+        ph.px += rx * p1.x + ry * ux;
+        ph.py += rx * p1.y + ry * uy;
+        ph.pz += rx * p1.z + ry * uz;
+
+        if (st == srcFourierX2D) {
+            ph.w = pos.w * (__sinf((p2.x * rx + p2.z) * kTwoPi) * __sinf((p2.y * ry + p2.w) * kTwoPi) + 1.f) * 0.5f;
+        } else {
+            ph.w = pos.w * (__cosf((p2.x * rx + p2.y * ry + p2.z) * kTwoPi) * (1.f - p2.w) + 1.f) * 0.5f;
+        }
+
+        locate<MediaT>(P, ph, rawlabel, rawdet);
+        fx += (p1.x + ux) * 0.5f;
+        fy += (p1.y + uy) * 0.5f;
+        fz += (p1.z + uz) * 0.5f;
+    } else if (st == srcHyperboloid) {
+        float sphi, cphi;
+        __sincosf(kTwoPi * rng_uniform(rng), &sphi, &cphi);
+        const float r = fast_sqrt(0.5f * rng_scatlen(rng)) * p1.x;
+        const float k = -p1.y / p1.z;
+        const float q = fast_rsqrt(r * r + p1.z * p1.z);
+        float lx = r * (cphi - k * sphi), ly = r * (sphi + k * cphi), lz = 0.f;   /* local launch point */
+        const float dx = -r * sphi * q, dy = r * cphi * q, dz = p1.z * q;         /* local direction    */
+
+        if (ph.vz > -1.f + kEps && ph.vz < 1.f - kEps) {
+            const float t = 1.f - ph.vz * ph.vz;
+            const float st0 = fast_sqrt(t), rs = fast_rsqrt(t);
+            const float cp = ph.vx * rs, sp = ph.vy * rs;
+            const float gx = lx * cp * ph.vz - ly * sp, gy = lx * sp * ph.vz + ly * cp, gz = -lx * st0;
+            const float nvx = dx * cp * ph.vz - dy * sp + dz * cp * st0;
+            const float nvy = dx * sp * ph.vz + dy * cp + dz * sp * st0;
+            const float nvz = -dx * st0 + dz * ph.vz;
+            lx = gx;
+            ly = gy;
+            lz = gz;
+            ph.vx = nvx;
+            ph.vy = nvy;
+            ph.vz = nvz;
+        } else {
+            const float s = (ph.vz > 0.f) ? dz : -dz;
+            ph.vx = dx;
+            ph.vy = dy;
+            ph.vz = s;
+        }
+
+        ph.px = lx + pos.x;
+        ph.py = ly + pos.y;
+        ph.pz = lz + pos.z;
+        aimed = false;
+    } else if (st == srcDisk || st == srcGaussian || st == srcRing) {
+        float phi;
+
+        if (st != srcGaussian && (p1.z > 0.f || p1.w > 0.f)) {
+            phi = fabsf(p1.z - p1.w) * rng_uniform(rng) + fminf(p1.z, p1.w);
+        } else {
+            phi = kTwoPi * rng_uniform(rng);
+        }
+
+        float sphi, cphi, r;
+        __sincosf(phi, &sphi, &cphi);
+
+        if (st != srcGaussian) {
+            r = fast_sqrt(rng_uniform(rng) * fabsf(p1.x * p1.x - p1.y * p1.y) + p1.y * p1.y);
+        } else if (fabsf(dir.w) < 1e-5f || fabsf(p1.y) < 1e-5f) {
+            r = fast_sqrt(-0.5f * __logf(rng_uniform(rng))) * p1.x;
+        } else {
+            const float z0 = p1.x * p1.x * kOnePi / p1.y;
+            r = fast_sqrt(-0.5f * __logf(rng_uniform(rng)) * (1.f + (dir.w * dir.w / (z0 * z0)))) * p1.x;
+        }
+
+        if (ph.vz > -1.f + kEps && ph.vz < 1.f - kEps) {
+            const float t0 = 1.f - ph.vz * ph.vz;
+            const float t1 = r * fast_rsqrt(t0);
+            ph.px += t1 * (ph.vx * ph.vz * cphi - ph.vy * sphi);
+            ph.py += t1 * (ph.vy * ph.vz * cphi + ph.vx * sphi);
+            ph.pz -= t1 * t0 * cphi;
+        } else {
+            ph.px += r * cphi;
+            ph.py += r * sphi;
+        }
+
+        locate<MediaT>(P, ph, rawlabel, rawdet);
+    } else if (st == srcCone || st == srcIsotropic || st == srcArcsine) {
+        float sphi, cphi, stheta, ctheta, ang;
+        __sincosf(kTwoPi * rng_uniform(rng), &sphi, &cphi);
+
+        if (st == srcCone) {
+            do {
+                ang = (p1.y > 0.f) ? kTwoPi * rng_uniform(rng) : acosf(2.f * rng_uniform(rng) - 1.f);
+            } while (ang > p1.x);
+        } else if (st == srcIsotropic) {
+            ang = acosf(2.f * rng_uniform(rng) - 1.f);
+        } else {
+            ang = kOnePi * rng_uniform(rng);
+        }
+
+        __sincosf(ang, &stheta, &ctheta);
+        rotate_direction(ph.vx, ph.vy, ph.vz, stheta, ctheta, sphi, cphi);
+        aimed = false;
+    } else if (st == srcZGaussian) {
+        float sphi, cphi, stheta, ctheta;
+        __sincosf(kTwoPi * rng_uniform(rng), &sphi, &cphi);
+        const float a = fast_sqrt(-2.f * __logf(rng_uniform(rng)));
+        const float ang = a * (1.f - 2.f * rng_uniform(rng)) * p1.x;
+        __sincosf(ang, &stheta, &ctheta);
+        rotate_direction(ph.vx, ph.vy, ph.vz, stheta, ctheta, sphi, cphi);
+        aimed = false;
+    } else if (st == srcLine || st == srcSlit) {
+        float r = rng_uniform(rng);
+        ph.px += r * p1.x;
+        ph.py += r * p1.y;
+        ph.pz += r * p1.z;
+
+        if (st == srcLine) {
+            float s, c;
+            r = fast_rsqrt(p1.x * p1.x + p1.y * p1.y + p1.z * p1.z);
+
+            if (p2.x > 0.f) {
+                const float ax = p1.x * r, ay = p1.y * r, az = p1.z * r;
+                const float d = ph.vx * ax + ph.vy * ay + ph.vz * az;
+                ph.vx -= d * ax;
+                ph.vy -= d * ay;
+                ph.vz -= d * az;
+                const float nrm = fast_rsqrt(ph.vx * ph.vx + ph.vy * ph.vy + ph.vz * ph.vz);
+                ph.vx *= nrm;
+                ph.vy *= nrm;
+                ph.vz *= nrm;
+                __sincosf(p2.x * (2.f * rng_uniform(rng) - 1.f), &s, &c);
+                rotate_about_axis(ph.vx, ph.vy, ph.vz, ax, ay, az, s, c);
+            } else {
+                ph.vx = p1.x * r;
+                ph.vy = p1.y * r;
+                ph.vz = p1.z * r;
+                __sincosf(kTwoPi * rng_uniform(rng), &s, &c);
+                rotate_direction(ph.vx, ph.vy, ph.vz, 1.f, 0.f, s, c);
+            }
+        } else if (p2.x > 0.f || p2.y > 0.f) {
+            float s, c;
+            __sincosf(kTwoPi * rng_uniform(rng), &s, &c);
+            r = fast_sqrt(2.f * rng_scatlen(rng));
+            c *= p2.x * r;
+            s *= p2.y * r;
+            s *= fast_rsqrt(p1.x * p1.x + p1.y * p1.y + p1.z * p1.z);
+            const float qx = p1.y * ph.vz - p1.z * ph.vy, qy = p1.z * ph.vx - p1.x * ph.vz, qz = p1.x * ph.vy - p1.y * ph.vx;
+            c *= fast_rsqrt(qx * qx + qy * qy + qz * qz);
+            ph.vx += c * qx + s * p1.x;
+            ph.vy += c * qy + s * p1.y;
+            ph.vz += c * qz + s * p1.z;
+            r = fast_rsqrt(ph.vx * ph.vx + ph.vy * ph.vy + ph.vz * ph.vz);
+            ph.vx *= r;
+            ph.vy *= r;
+            ph.vz *= r;
+        }
+
+        locate<MediaT>(P, ph, rawlabel, rawdet);
+        fx = pos.x + p1.x * 0.5f;
+        fy = pos.y + p1.y * 0.5f;
+        fz = pos.z + p1.z * 0.5f;
+        /* both the line and the slit source leave the focal-length rule enabled (:2082) */
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * detected-photon record (src/mcx_core.cl:838-926), compacted with one atomic per converged warp
+ * ------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void save_detected(const SimParam& P, const float4* __restrict__ dets, const float* ppath,
+        uint32_t pstride, const Photon& ph, uint32_t detarg, float w0init, int cursrc,
+        const unsigned long long* photonseed) {
+    int detid = 0;
+
+    if (detarg == kOutsideMin) {
+        detid = -1;
+    } else {
+        for (uint32_t i = 0; i < P.detnum; i++) {
+            const float4 d = dets[i];
+            const float dx = d.x - ph.px, dy = d.y - ph.py, dz = d.z - ph.pz;
+
+            if (dx * dx + dy * dy + dz * dz < d.w * d.w) {
+                detid = (int)i + 1;
+                break;
+            }
+        }
+    }
+
+    const uint32_t active = __activemask();
+    const uint32_t hits = __ballot_sync(active, detid != 0);
+
+    if (detid == 0) {
+        return;
+    }
+
+    const uint32_t leader = __ffs(hits) - 1;
+    uint32_t base = 0;
+
+    if (lane_id() == leader) {
+        base = atomicAdd(P.detcount, (uint32_t)__popc(hits));
+    }
+
+    base = __shfl_sync(hits, base, leader) + __popc(hits & lanemask_lt());
+
+    if (base >= P.maxdetphoton) {
+        return;     /* overflow: counted but not stored, the host warns like src/mcx_host.cpp:1207-1210 */
+    }
+
+    if (P.issaveseed) {
+        P.seedout[2 * (size_t)base] = photonseed[0];
+        P.seedout[2 * (size_t)base + 1] = photonseed[pstride];
+    }
+
+    float* rec = P.detphoton + (size_t)base * P.reclen;
+    const uint32_t flag = P.savedetflag;
+
+    if (flag & 0x01u) {
+        if (P.extrasrclen && P.srcid <= 0) {
+            detid |= cursrc << 16;
+        }
+
+        *rec++ = (float)detid;
+    }
+
+    for (uint32_t i = 0; i < P.partialdata; i++) {
+        *rec++ = ppath[i * pstride];
+    }
+
+    if (flag & 0x10u) {
+        *rec++ = ph.px;
+        *rec++ = ph.py;
+        *rec++ = ph.pz;
+    }
+
+    if (flag & 0x20u) {
+        *rec++ = ph.vx;
+        *rec++ = ph.vy;
+        *rec++ = ph.vz;
+    }
+
+    if (flag & 0x40u) {
+        *rec++ = w0init;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * the kernel
+ * ------------------------------------------------------------------------------------------------- */
+constexpr int kBlock = 256;
+
+template <int SRC, bool REFLECT, bool SAVEDET, typename MediaT, typename AccT, bool STATS>
+__global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant__ SimParam P) {
+    extern __shared__ float4 smem[];
+    float4* tab = smem;                                   /* optical properties, row 0 = background */
+    const float4* srctab = tab + P.medianum;              /* 4 rows per source, main source first  */
+    const float4* dettab = srctab + 4 * (1 + P.extrasrclen);
+    float* ftab = reinterpret_cast<float*>(tab + P.tablen);        /* inverse-CDF tables */
+    float* ppath_base = ftab + P.ftablen;                         /* partialdata x blockDim, thread-minor */
+    unsigned long long* seed_base = reinterpret_cast<unsigned long long*>(ppath_base + (SAVEDET ? P.partialdata * kBlock : 0));
+
+    for (uint32_t i = threadIdx.x; i < P.tablen; i += kBlock) {
+        tab[i] = P.tables[i];
+    }
+
+    for (uint32_t i = threadIdx.x; i < P.nphase; i += kBlock) {
+        ftab[i] = P.invcdf[i];
+    }
+
+    for (uint32_t i = threadIdx.x; i < P.nangle; i += kBlock) {
+        ftab[P.nphase + i] = P.angleinvcdf[i];
+    }
+
+    float* ppath = ppath_base + threadIdx.x;
+    unsigned long long* photonseed = seed_base + threadIdx.x;
+
+    if (SAVEDET) {
+        for (uint32_t i = 0; i < P.partialdata; i++) {
+            ppath[i * kBlock] = 0.f;
+        }
+    }
+
+    __syncthreads();
+
+    const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
+    const MediaT* __restrict__ media = static_cast<const MediaT*>(P.media);
+    AccT* __restrict__ field = static_cast<AccT*>(P.field);
+    const float n0 = tab[0].w;
+
+    Rng rng;
+    rng_seed(rng, P.seeds + 4 * (size_t)tid);
+
+    Photon ph;
+    ph.px = ph.py = ph.pz = 0.f;
+    ph.w = __int_as_float(0x7FC00000);        /* NaN: nothing to retire before the first launch (:2329) */
+    ph.vx = ph.vy = ph.vz = 0.f;
+    ph.nscat = -1;
+    ph.slen = 0.f;
+    ph.tof = 0.f;
+    ph.ix = ph.iy = ph.iz = 0;
+    ph.face = -1;
+    ph.idx1d = 0;
+    ph.label = 0;
+    ph.detflag = 0;
+    ph.w0 = 0.f;
+    ph.pathlen = 0.f;
+    ph.n1 = n0;
+
+    float mua = 0.f, mus = 0.f, g = 0.f, nmed = n0;   /* optical properties of the voxel being traversed */
+    float e_escaped = 0.f, e_launched = 0.f;
+    float w0init = 0.f;                               /* launch weight of the live packet (W flag) */
+    int   cursrc = 0;                                 /* source the live packet came from (1-based; 0 = single source) */
+    uint32_t budget = (P.sched == 1) ? (P.threadphoton + ((int)tid < P.oddphoton ? 1u : 0u)) : 0u;
+    uint32_t detarg = 0;                              /* detector argument handed to the retire step */
+    bool relaunch = true;
+    unsigned long long c_seg = 0, c_dep = 0, c_scat = 0;
+
+    while (true) {
+        if (relaunch) {
+            /* ------------------------------------------------------------------ retire (:1494-1569) */
+            if (!(ph.w != ph.w)) {
+                e_escaped += ph.w;
+
+                if (P.issaveref == 1 && ph.label == 0 && ph.idx1d != kOutsideMin && ph.idx1d != kOutsideMax && ph.w > 0.f) {
+                    int tshift = min((int)P.maxgate - 1, (int)floorf((ph.tof - P.twin0) * P.Rtstep));
+
+                    if (P.extrasrclen && P.srcid < 0) {
+                        tshift += (cursrc - 1) * (int)P.maxgate;
+                    }
+
+                    red_add(field + ph.idx1d + (size_t)tshift * P.dimxyz, -ph.w);
+                }
+
+                if (SAVEDET) {
+                    if ((detarg & kDetMask) && ph.label == 0 && P.issaveref < 2) {
+                        save_detected(P, dettab, ppath, kBlock, ph, detarg, w0init, cursrc, photonseed);
+                    }
+                }
+            }
+
+            if (SAVEDET) {
+                for (uint32_t i = 0; i < P.partialdata; i++) {
+                    ppath[i * kBlock] = 0.f;
+                }
+            }
+
+            /* ------------------------------------------------------------------ photon budget */
+            if (budget == 0) {
+                if (P.sched == 1) {
+                    break;
+                }
+
+                const unsigned long long first = atomicAdd(P.counter, (unsigned long long)P.chunk);
+
+                if (first >= P.nphoton) {
+                    break;
+                }
+
+                budget = (uint32_t)min((unsigned long long)P.chunk, P.nphoton - first);
+            }
+
+            /* ------------------------------------------------------------------ launch (:1598-2255) */
+            if (P.issaveseed) {
+                photonseed[0] = rng.a;
+                photonseed[kBlock] = rng.b;
+            }
+
+            const float4* S = srctab;
+
+            if (P.extrasrclen && P.srcid != 1) {
+                if (P.srcid > 1) {
+                    S = srctab + 4 * (P.srcid - 1);
+                } else {
+                    cursrc = (int)(rng_uniform(rng) * kJustBelowOne * (float)(P.extrasrclen + 1)) + 1;
+                    S = srctab + 4 * (cursrc - 1);
+                }
+            }
+
+            uint32_t rawlabel = 0, rawdet = 0;
+            float attempts = 1.f;
+            bool failed = false;
+
+            do {
+                float fx, fy, fz;
+                bool aimed;
+                ph.slen = 0.f;
+                ph.tof = 0.f;
+                sample_source<SRC, MediaT>(P, S, rng, ph, rawlabel, rawdet, fx, fy, fz, aimed);
+
+                if (fabsf(ph.w) <= P.minenergy) {
+                    continue;
+                }
+
+                const float focal = S[1].w;
+
+                if (P.nangle) {
+                    /* launch zenith angle from a user table (:2102-2124) */
+                    const float* at = ftab + P.nphase;
+                    float ang, c;
+
+                    if (focal > 0.f) {
+                        ang = fminf(rng_uniform(rng) * (float)P.nangle, (float)P.nangle - kEps);
+                        c = at[(int)ang];
+                    } else {
+                        ang = fminf(rng_uniform(rng) * (float)(P.nangle - 1), (float)(P.nangle - 1) - kEps);
+                        const float fr = ang - (float)(int)ang;
+                        const uint32_t i0 = ((uint32_t)ang >= P.nangle - 1) ? P.nangle - 1 : (uint32_t)ang;
+                        const uint32_t i1 = ((uint32_t)ang + 1 >= P.nangle - 1) ? P.nangle - 1 : (uint32_t)ang + 1;
+                        c = (1.f - fr) * at[i0] + fr * at[i1];
+                    }
+
+                    float stheta, ctheta, sphi, cphi;
+                    __sincosf(c * kOnePi, &stheta, &ctheta);
+                    __sincosf(kTwoPi * rng_uniform(rng), &sphi, &cphi);
+
+                    if (focal < 1.5f && focal >= 0.f) {
+                        ph.vx = S[1].x;
+                        ph.vy = S[1].y;
+                        ph.vz = S[1].z;
+                    }
+
+                    rotate_direction(ph.vx, ph.vy, ph.vz, stheta, ctheta, sphi, cphi);
+                } else if (aimed) {
+                    if (focal != focal) {                       /* NaN: isotropic launch (:2126-2132) */
+                        float stheta, ctheta, sphi, cphi;
+                        __sincosf(kTwoPi * rng_uniform(rng), &sphi, &cphi);
+                        __sincosf(acosf(2.f * rng_uniform(rng) - 1.f), &stheta, &ctheta);
+                        rotate_direction(ph.vx, ph.vy, ph.vz, stheta, ctheta, sphi, cphi);
+                    } else if (focal < 0.f && isinf(focal)) {   /* -inf: Lambertian launch (:2133-2139) */
+                        float sphi, cphi;
+                        __sincosf(kTwoPi * rng_uniform(rng), &sphi, &cphi);
+                        const float stheta = fast_sqrt(rng_uniform(rng));
+                        const float ctheta = fast_sqrt(1.f - stheta * stheta);
+                        rotate_direction(ph.vx, ph.vy, ph.vz, stheta, ctheta, sphi, cphi);
+                    } else if (focal != 0.f) {                  /* converge to / diverge from a focal point (:2140-2151) */
+                        const float sgn = (float)((focal > 0.f) - (focal < 0.f));
+                        fx += focal * ph.vx;
+                        fy += focal * ph.vy;
+                        fz += focal * ph.vz;
+                        ph.vx = sgn * (fx - ph.px);
+                        ph.vy = sgn * (fy - ph.py);
+                        ph.vz = sgn * (fz - ph.pz);
+                        const float r = fast_rsqrt(ph.vx * ph.vx + ph.vy * ph.vy + ph.vz * ph.vz);
+                        ph.vx *= r;
+                        ph.vy *= r;
+                        ph.vz *= r;
+                    }
+                }
+
+                if (rawlabel == 0) {
+                    const int idx = enter_volume<MediaT>(P, tab, ph);
+
+                    if (idx >= 0) {
+                        ph.idx1d = (uint32_t)idx;
+                        fetch_voxel(media, ph.idx1d, rawlabel, rawdet);
+                    }
+                }
+
+                ph.ix = (int)(short)floorf(ph.px);
+                ph.iy = (int)(short)floorf(ph.py);
+                ph.iz = (int)(short)floorf(ph.pz);
+                attempts += 1.f;
+
+                if (attempts > (float)P.maxvoidstep) {
+                    failed = true;
+                    break;
+                }
+            } while (rawlabel == 0 || fabsf(ph.w) <= P.minenergy);
+
+            if (failed) {
+                ph.w = __int_as_float(0x7FC00000);
+                break;       /* the source never reaches the volume: this thread gives up (:2204-2206) */
+            }
+
+            budget--;
+            ph.label = rawlabel;
+            ph.detflag = rawdet;
+            {
+                const float4 pr = tab[ph.label];
+                mua = pr.x;
+                mus = pr.y;
+                g = pr.z;
+                nmed = pr.w;
+            }
+            e_launched += ph.w;
+            ph.w0 = ph.w;
+            w0init = ph.w;
+            ph.nscat = -1;
+            ph.pathlen = 0.f;
+            ph.face = -1;
+            relaunch = false;
+        }
+
+        /* ------------------------------------------------------------------ scattering (:2446-2649) */
+        if (ph.slen <= 0.f) {
+            ph.slen = rng_scatlen(rng);
+
+            if (ph.nscat >= 0) {
+                float sphi = 0.f, cphi = 1.f, stheta, ctheta;
+
+                if (!P.is2d) {
+                    __sincosf(kTwoPi * rng_uniform(rng), &sphi, &cphi);
+                }
+
+                if (P.nphase > 2) {
+                    /* tabulated phase function: linear interpolation of the inverse CDF of cos(theta) */
+                    float u = rng_uniform(rng) * (float)(P.nphase - 1);
+                    const float fr = u - (float)(int)u;
+                    const uint32_t i0 = ((uint32_t)u >= P.nphase) ? P.nphase - 1 : (uint32_t)u;
+                    const uint32_t i1 = ((uint32_t)u + 1 >= P.nphase) ? P.nphase - 1 : (uint32_t)u + 1;
+                    ctheta = (1.f - fr) * ftab[i0] + fr * ftab[i1];
+                    stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
+                } else {
+                    const float gg = ((uint32_t)ph.nscat > P.gscatter) ? 0.f : g;
+
+                    if (fabsf(gg) > kEps) {
+                        /* Henyey-Greenstein inverse CDF (:2487-2490); sin(acos(c)) == sqrt(1-c^2) on [0,pi] */
+                        float t = __fdividef(1.f - g * g, 1.f - g + 2.f * g * rng_uniform(rng));
+                        t *= t;
+                        ctheta = __fdividef(1.f + g * g - t, 2.f * g);
+                        ctheta = fmaxf(-1.f, fminf(1.f, ctheta));
+                    } else {
+                        ctheta = 2.f * rng_uniform(rng) - 1.f;
+                    }
+
+                    stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
+                }
+
+                if (SAVEDET) {
+                    const uint32_t flag = P.savedetflag;
+                    const uint32_t M = P.medianum - 1;
+
+                    if (flag & 0x02u) {
+                        uint32_t* cnt = reinterpret_cast<uint32_t*>(ppath + (ph.label - 1) * kBlock);
+                        *cnt += 1u;
+                    }
+
+                    if (flag & 0x08u) {
+                        ppath[(M * ((flag >> 1 & 1u) + (flag >> 2 & 1u)) + ph.label - 1) * kBlock] += 1.f - ctheta;
+                    }
+                }
+
+                if (P.is2d) {
+                    rotate_direction_2d(ph.vx, ph.vy, ph.vz, (rng_uniform(rng) > 0.5f ? stheta : -stheta), ctheta, (int)P.is2d);
+                } else {
+                    rotate_direction(ph.vx, ph.vy, ph.vz, stheta, ctheta, sphi, cphi);
+                }
+
+                ph.nscat++;
+                if (STATS) {
+                    c_scat++;
+                }
+            } else {
+                ph.nscat = 0;
+            }
+        }
+
+        /* ------------------------------------------------------------------ one ray segment (:2652-2765) */
+        ph.n1 = nmed;
+        {
+            const float4 pr = tab[ph.label];
+            mua = pr.x;
+            mus = pr.y;
+            g = pr.z;
+            nmed = pr.w;
+        }
+        const float dist = face_distance(ph.px, ph.py, ph.pz, ph.vx, ph.vy, ph.vz, ph.ix, ph.iy, ph.iz, ph.face);
+        const float musp = __fmul_rn(mus, ((uint32_t)(ph.nscat + 1) > P.gscatter) ? __fsub_rn(1.f, g) : 1.f);
+        float slen;
+        const float len = step_length(dist, musp, ph.slen, slen);
+        ph.pathlen += len;
+        ph.px = advance(ph.px, len, ph.vx);
+        ph.py = advance(ph.py, len, ph.vy);
+        ph.pz = advance(ph.pz, len, ph.vz);
+
+        if (slen != ph.slen) {          /* reached the face before the scattering site */
+            if (ph.face == 0) {
+                ph.ix += (ph.vx > 0.f ? 1 : -1);
+            } else if (ph.face == 1) {
+                ph.iy += (ph.vy > 0.f ? 1 : -1);
+            } else {
+                ph.iz += (ph.vz > 0.f ? 1 : -1);
+            }
+        }
+
+        ph.w *= __expf(-mua * len);
+        ph.slen -= slen;
+        ph.tof += len * nmed * P.oneoverc0;
+        if (STATS) {
+            c_seg++;
+        }
+
+        if (SAVEDET) {
+            if (P.savedetflag & 0x04u) {
+                ppath[(((P.savedetflag >> 1) & 1u) * (P.medianum - 1) + ph.label - 1) * kBlock] += len;
+            }
+        }
+
+        /* ------------------------------------------------------------------ new voxel (:2796-2811) */
+        const uint32_t oldidx = ph.idx1d;
+        const uint32_t olddet = ph.detflag;
+        const uint32_t oldlabel = ph.label;
+        ph.idx1d = linear_index(P, ph.ix, ph.iy, ph.iz);
+
+        if (!voxel_in_grid(P, ph.ix, ph.iy, ph.iz)) {
+            ph.label = 0;
+            ph.idx1d = (ph.ix < 0 || ph.iy < 0 || ph.iz < 0) ? kOutsideMin : kOutsideMax;
+            uint32_t code = P.bc[(ph.idx1d == kOutsideMax) * 3 + ph.face];
+            ph.detflag = ((code & 0xFu) == bcUnknown) ? (P.doreflect ? (uint32_t)bcReflect : (uint32_t)bcAbsorb) : code;
+        } else {
+            fetch_voxel(media, ph.idx1d, ph.label, ph.detflag);
+        }
+
+        /* ------------------------------------------------------------------ deposit (:2816-2929) */
+        if (ph.idx1d != oldidx) {
+            if (P.save2pt && ph.tof >= P.twin0 && ph.tof < P.twin1) {
+                float weight = 0.f;
+                /* clamped: (tof-twin0)*Rtstep can round up to maxgate for tof one ulp below twin1 */
+                int tshift = min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1);
+
+                if (P.outputtype == otEnergy) {
+                    weight = ph.w0 - ph.w;
+                } else if (P.outputtype == otFluence || P.outputtype == otFlux) {
+                    weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : __fdividef(ph.w0 - ph.w, mua);
+                } else if (P.outputtype == otL) {
+                    weight = ph.w0 * ph.pathlen;
+                }
+
+                if (P.extrasrclen && P.srcid < 0) {
+                    tshift += (cursrc - 1) * (int)P.maxgate;
+                }
+
+                if (fabsf(weight) > 0.f) {
+                    red_add(field + oldidx + (size_t)tshift * P.dimxyz, weight);
+                    if (STATS) {
+                        c_dep++;
+                    }
+                }
+            }
+
+            ph.w0 = ph.w;
+            ph.pathlen = 0.f;
+        }
+
+        /* ------------------------------------------------------------------ leave / time out (:2957-3028) */
+        const uint32_t bcode = ph.detflag & 0xFu;
+
+        if ((ph.label == 0 && (bcode == bcAbsorb || bcode == bcCyclic || (bcode == bcReflect && ph.n1 == n0))) || ph.tof > P.twin1) {
+            if (ph.detflag == bcCyclic) {
+                /* re-enter through the opposite face (:2970-2996) */
+                if (ph.face == 0) {
+                    ph.px = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fnx : 0.f), (ph.vx > 0.f) - (ph.vx < 0.f));
+                    ph.ix = (int)(short)floorf(ph.px);
+                } else if (ph.face == 1) {
+                    ph.py = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fny : 0.f), (ph.vy > 0.f) - (ph.vy < 0.f));
+                    ph.iy = (int)(short)floorf(ph.py);
+                } else {
+                    ph.pz = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fnz : 0.f), (ph.vz > 0.f) - (ph.vz < 0.f));
+                    ph.iz = (int)(short)floorf(ph.pz);
+                }
+
+                if (voxel_in_grid(P, ph.ix, ph.iy, ph.iz)) {
+                    ph.idx1d = linear_index(P, ph.ix, ph.iy, ph.iz);
+                    fetch_voxel(media, ph.idx1d, ph.label, ph.detflag);
+                    continue;
+                }
+            }
+
+            detarg = ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face])) ? kOutsideMin : olddet;
+            relaunch = true;
+            continue;
+        }
+
+        /* ------------------------------------------------------------------ Russian roulette (:3031-3061) */
+        if (fabsf(ph.w) < P.minenergy) {
+            if (rng_uniform(rng) * kRouletteSize <= 1.f) {
+                ph.w *= kRouletteSize;
+            } else {
+                detarg = olddet;
+                relaunch = true;
+                continue;
+            }
+        }
+
+        /* ------------------------------------------------------------------ index mismatch (:3063-3297) */
+        if (REFLECT) {
+            const float n2 = tab[ph.label].w;
+            const bool want = (ph.label && P.doreflect) ||
+                              (ph.label == 0 && ((bcode == bcUnknown && P.doreflect) || bcode == bcReflect || bcode == bcMirror));
+
+            if (want && (bcode == bcMirror || ph.n1 != n2)) {
+                float Rtotal = 1.f;
+
+                if (bcode != bcMirror) {
+                    Rtotal = fresnel(ph.vx, ph.vy, ph.vz, ph.n1, n2, ph.face);
+                }
+
+                if (Rtotal < 1.f && !(ph.label == 0 && bcode == bcMirror) && rng_uniform(rng) > Rtotal) {
+                    refract(ph.vx, ph.vy, ph.vz, ph.n1, n2, ph.face);
+
+                    if (ph.label == 0) {
+                        detarg = ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face])) ? kOutsideMin : olddet;
+                        relaunch = true;
+                        continue;
+                    }
+
+                    nmed = n2;     /* now travelling in the new medium */
+                } else {
+                    /* mirror the direction and put the packet back on the face it came through (:3204-3213) */
+                    if (ph.face == 0) {
+                        ph.vx = -ph.vx;
+                        ph.px = nudge(rintf(ph.px), 0);
+                        ph.ix = (int)(short)rintf(ph.px);
+                    } else if (ph.face == 1) {
+                        ph.vy = -ph.vy;
+                        ph.py = nudge(rintf(ph.py), 0);
+                        ph.iy = (int)(short)rintf(ph.py);
+                    } else {
+                        ph.vz = -ph.vz;
+                        ph.pz = nudge(rintf(ph.pz), 0);
+                        ph.iz = (int)(short)rintf(ph.pz);
+                    }
+
+                    ph.idx1d = oldidx;
+                    ph.label = oldlabel;
+                    ph.detflag = olddet;
+                    nmed = ph.n1;
+                }
+            } else {
+                nmed = n2;
+            }
+        }
+    }
+
+    /* ---------------------------------------------------------------------- energy bookkeeping (:3301-3302) */
+    double esc = (double)e_escaped, lau = (double)e_launched;
+
+    for (int o = 16; o > 0; o >>= 1) {
+        esc += __shfl_xor_sync(0xFFFFFFFFu, esc, o);
+        lau += __shfl_xor_sync(0xFFFFFFFFu, lau, o);
+    }
+
+    if (lane_id() == 0) {
+        atomicAdd(P.energy, esc);
+        atomicAdd(P.energy + 1, lau);
+    }
+
+    if (STATS && P.stats) {
+        atomicAdd(P.stats, c_seg);
+        atomicAdd(P.stats + 1, c_dep);
+        atomicAdd(P.stats + 2, c_scat);
+    }
+}
+
+} // namespace mcxb

@@ -243,10 +243,12 @@ def prepare(cfg):
     c.nthread = int(cfg.get("nthread", 0)) if not cfg.get("autopilot", 1) or "nthread" in cfg else 0
     c.nblocksize = int(cfg.get("nblocksize", 0)) if "nblocksize" in cfg else 0
     c.sched = int(cfg.get("sched", 0))
+    acc = cfg.get("accum", 0)
+    c.accum = {"f64": 0, "f32": 1}.get(acc, acc) if isinstance(acc, str) else int(acc)
     dbg = cfg.get("debuglevel", 0)
     if isinstance(dbg, str):
         dbg = sum(1 << "RMPT".find(ch) for ch in dbg.upper() if ch in "RMPT")
-    c.debuglevel = int(dbg)
+    c.debuglevel = int(dbg) | (abi.DEBUG_STATS if cfg.get("stats") else 0)
     ot = cfg.get("outputtype", "flux")
     if isinstance(ot, str):
         if ot.lower() not in OUTPUTTYPES:
@@ -361,11 +363,18 @@ def prepare(cfg):
     c.prop = prop.ctypes.data_as(C.POINTER(abi.F4))
     c.detpos = detpos.ctypes.data_as(C.POINTER(abi.F4)) if c.detnum else None
     c.srcdata = extra.ctypes.data_as(C.POINTER(abi.Source)) if nsrc > 1 else None
+    for key, cnt, ptr in (("invcdf", "nphase", "invcdf"), ("angleinvcdf", "nangle", "angleinvcdf")):
+        if cfg.get(key) is not None:
+            tabv = np.ascontiguousarray(np.asarray(cfg[key], dtype=np.float32).ravel()).copy()
+            p.keep[key] = tabv
+            setattr(c, cnt, tabv.size)
+            setattr(c, ptr, tabv.ctypes.data_as(C.POINTER(C.c_float)))
     if cfg.get("srcpattern") is not None:
         pat = np.asarray(cfg["srcpattern"], dtype=np.float32)
         pat = np.ascontiguousarray(pat.ravel(order="F")).copy()
         p.keep["srcpattern"] = pat
         c.srcpattern = pat.ctypes.data_as(C.POINTER(C.c_float))
+        c.srcpattern_len = pat.size
         if c.srctype == 5 and pat.size < int(srcp1[0, 3]) * int(srcp2[0, 3]):
             raise ConfigError(-4, "srcpattern is smaller than srcparam1.w x srcparam2.w")
     return p
