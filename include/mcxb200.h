@@ -203,6 +203,7 @@ int  mcxb_sim_create(const mcxb_config* cfg, int device, mcxb_sim** sim);   /* H
 int  mcxb_sim_reset(mcxb_sim* sim, void* cuda_stream);                      /* zero field / energy / counters, restore seeds */
 int  mcxb_sim_launch(mcxb_sim* sim, void* cuda_stream);                     /* enqueue the photon kernel; asynchronous */
 int  mcxb_sim_set_photons(mcxb_sim* sim, uint64_t nphoton);                 /* change the photon budget of the next launch */
+int  mcxb_sim_reseed(mcxb_sim* sim, int32_t seed, uint64_t seed_skip);      /* new per-thread seed slice (rank r: skip r*nthread) */
 int  mcxb_sim_finalize(mcxb_sim* sim, void* cuda_stream);                   /* accumulators -> float32 volume on the device; asynchronous */
 int  mcxb_sim_fetch(mcxb_sim* sim, void* cuda_stream, mcxb_output* out);    /* finalize if needed, sync, D2H, add into out->field, normalise */
 /* raw device pointers, valid after mcxb_sim_finalize, so that a host framework (torch.distributed / NCCL)

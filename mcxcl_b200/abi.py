@@ -130,6 +130,7 @@ SYMBOLS = [
     ("mcxb_sim_reset", C.c_int, [_VP, _VP]),
     ("mcxb_sim_launch", C.c_int, [_VP, _VP]),
     ("mcxb_sim_set_photons", C.c_int, [_VP, C.c_uint64]),
+    ("mcxb_sim_reseed", C.c_int, [_VP, C.c_int32, C.c_uint64]),
     ("mcxb_sim_finalize", C.c_int, [_VP, _VP]),
     ("mcxb_sim_fetch", C.c_int, [_VP, _VP, C.POINTER(Output)]),
     ("mcxb_sim_field_devptr", _VP, [_VP]),

@@ -730,6 +730,20 @@ extern "C" int mcxb_sim_set_photons(mcxb_sim* s, uint64_t nphoton) {
     return MCXB_OK;
 }
 
+extern "C" int mcxb_sim_reseed(mcxb_sim* s, int32_t seed, uint64_t seed_skip) {
+    if (!s) {
+        return fail(MCXB_ERR_ARG, "sim is NULL");
+    }
+
+    CU_TRY(cudaSetDevice(s->device));
+    std::vector<uint32_t> seeds((size_t)s->nthread * 4);
+    mcxb_fill_seeds(seed, seed_skip, s->nthread, seeds.data());
+    CU_TRY(cudaMemcpy(s->d_seeds, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice));
+    s->cfg.seed = seed;
+    s->cfg.seed_skip = seed_skip;
+    return MCXB_OK;
+}
+
 extern "C" int mcxb_sim_launch(mcxb_sim* s, void* cuda_stream) {
     if (!s) {
         return fail(MCXB_ERR_ARG, "sim is NULL");

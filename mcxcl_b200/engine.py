@@ -66,6 +66,9 @@ class Simulation:
     def set_photons(self, n):
         abi.check(self.lib.mcxb_sim_set_photons(self.h, int(n)), "mcxb_sim_set_photons")
 
+    def reseed(self, seed, seed_skip=0):
+        abi.check(self.lib.mcxb_sim_reseed(self.h, int(seed), int(seed_skip)), "mcxb_sim_reseed")
+
     def reset(self, stream=None):
         abi.check(self.lib.mcxb_sim_reset(self.h, C.c_void_p(stream or 0)), "mcxb_sim_reset")
 

@@ -1,0 +1,118 @@
+"""Photon sharding over the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+
+The reference splits the photon budget over OpenCL devices by workload weight (``-G`` mask, ``-W`` weights;
+src/mcx_host.cpp:650-662, 1011-1012, 1098-1104), gives device *i* the next slice of ONE rand() stream
+(:759-768), lets every device fill a private fluence volume and sums volumes, energies and detected-photon
+lists on the host (:1218-1232, 1292-1306).  Here every rank runs the persistent kernel on its share with its
+seed slice, then ONE collective step combines the results on the device before normalisation:
+
+    reduce(SUM, float32 volume) -> rank 0      (NCCL over NVLink / NVSwitch)
+    reduce(SUM, float64 {escaped, launched})   -> rank 0
+    all_gather(detected counts) + variable-length send/recv of the detected-photon records -> rank 0
+
+`split_photons` / `gather_plan` are pure host logic (tested with gloo on CPU); `run_distributed` needs GPUs.
+"""
+import numpy as np
+
+from . import engine, hostcfg
+
+
+def split_photons(nphoton, workload):
+    """Per-rank photon counts: nphoton*w_i/sum(w) rounded down, the remainder going to the first ranks
+    (the reference computes threadphoton/oddphoton per device from the same ratio, src/mcx_host.cpp:1011-1012)."""
+    w = np.asarray(workload, dtype=np.float64)
+    if w.ndim != 1 or w.size == 0 or (w < 0).any() or w.sum() <= 0:
+        raise ValueError("workload must be a non-empty list of non-negative weights with a positive sum")
+    share = np.floor(int(nphoton) * (w / w.sum())).astype(np.int64)
+    rem = int(nphoton) - int(share.sum())
+    order = [i for i in range(w.size) if w[i] > 0]
+    for k in range(rem):
+        share[order[k % len(order)]] += 1
+    return [int(x) for x in share]
+
+
+def gather_plan(counts, maxdetphoton):
+    """offsets/lengths of each rank's detected-photon records in rank 0's buffer (exclusive scan, clipped to
+    the buffer size the way the reference clips at maxdetphoton, src/mcx_host.cpp:1207-1216)."""
+    offs, lens, at = [], [], 0
+    for c in counts:
+        n = max(0, min(int(c), int(maxdetphoton) - at))
+        offs.append(at)
+        lens.append(n)
+        at += n
+    return offs, lens, at
+
+
+class _DevArray:
+    """exposes a raw device pointer to torch through __cuda_array_interface__ (zero copy)"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def _as_tensor(ptr, shape, typestr, device):
+    import torch
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
+
+
+def combine(sim, dist, rank, world, device):
+    """the collective step; returns (gathered detected records on rank 0 or None, per-rank counts)"""
+    import torch
+    sim.finalize()
+    ptr = sim.devptrs()
+    field = _as_tensor(ptr["field"], (sim.fieldlen,), "<f4", device)
+    energy = _as_tensor(ptr["energy"], (2,), "<f8", device)
+    dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
+    dist.reduce(energy, dst=0, op=dist.ReduceOp.SUM)
+    c = sim.p.c
+    if not (c.issavedet and ptr["detphoton"]):
+        return None, [0] * world
+    mine = _as_tensor(ptr["detcount"], (1,), "<i4", device).to(torch.int64)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, mine)
+    counts = [int(x) for x in counts.cpu()]
+    reclen = max(1, sim.reclen)
+    stored = [min(x, c.maxdetphoton) for x in counts]
+    offs, lens, total = gather_plan(stored, c.maxdetphoton)
+    local = _as_tensor(ptr["detphoton"], (c.maxdetphoton * reclen,), "<f4", device)
+    ops, out = [], None
+    if rank == 0:
+        out = torch.empty(total * reclen, dtype=torch.float32, device=device)
+        out[:lens[0] * reclen] = local[:lens[0] * reclen]
+        for r in range(1, world):
+            if lens[r]:
+                ops.append(dist.P2POp(dist.irecv, out[offs[r] * reclen:(offs[r] + lens[r]) * reclen], r))
+    elif lens[rank]:
+        ops.append(dist.P2POp(dist.isend, local[:lens[rank] * reclen], 0))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out, counts
+
+
+def run_distributed(cfg, workload=None):
+    """`pmcxcl.run`-style call executed by every rank of an initialised torch.distributed NCCL group; rank 0
+    returns the combined result dictionary, the other ranks return None."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    device = torch.device("cuda", torch.cuda.current_device())
+    shares = split_photons(cfg["nphoton"], workload or [1.0] * world)
+    p = hostcfg.prepare(dict(cfg, nphoton=shares[rank]))
+    with engine.Simulation(p, device.index) as sim:
+        sim.reseed(p.c.seed, rank * sim.nthread)
+        sim.reset()
+        sim.launch()
+        detp, counts = combine(sim, dist, rank, world, device)
+        if rank != 0:
+            torch.cuda.synchronize()
+            return None
+        res = sim.fetch()
+        if detp is not None:
+            res["detp"] = detp.cpu().numpy().reshape(-1, max(1, sim.reclen))
+            res["detected"] = int(sum(counts))
+            res["saved"] = res["detp"].shape[0]
+        res["nphoton"] = int(cfg["nphoton"])
+        res["shares"] = shares
+        res["flux"] = engine.shape_field(p, res["field"])
+        return res

@@ -49,6 +49,11 @@ def _load(path, prefix):
         "transmit": (C.c_int, [_VP, _VP, _VP, _VP, C.c_uint32]),
         "seeds": (None, [C.c_int, C.c_uint64, C.c_uint64, _VP]),
     }
+    size = getattr(lib, prefix + "configsize")
+    size.restype = C.c_uint
+    if size() != C.sizeof(abi.Config):
+        raise RuntimeError("%s was built against another include/mcxb200.h (sizeof(mcxb_config) %d != %d): rebuild it"
+                           % (path, size(), C.sizeof(abi.Config)))
     for name, (res, args) in sig.items():
         fn = getattr(lib, prefix + name)
         fn.restype, fn.argtypes = res, args

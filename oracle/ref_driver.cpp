@@ -89,7 +89,7 @@ extern "C" void mcxref_seeds(int seed, uint64_t skip_records, uint64_t nrecords,
 extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_result* res) {
     using namespace refd;
 
-    if (cfg->srctype < 0 || cfg->srctype >= 18 || nthread == 0) {
+    if (cfg->abi_version != MCXB_ABI_VERSION || cfg->srctype < 0 || cfg->srctype >= 18 || nthread == 0) {
         return -1;
     }
 
@@ -157,6 +157,11 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     param.gscatter = cfg->gscatter;
     param.is2d = is2d;
     param.srcnum = cfg->srcnum ? cfg->srcnum : 1;
+    /* inverse-CDF tables live at the head of the __local scratch (src/mcx_core.cl:2354-2383, src/mcx_host.cpp:1013) */
+    param.nphase = cfg->invcdf ? cfg->nphase : 0;
+    param.nphaselen = param.nphase + (param.nphase & 1);
+    param.nangle = cfg->angleinvcdf ? cfg->nangle : 0;
+    param.nanglelen = param.nangle + (param.nangle & 1);
     memcpy(param.bc, cfg->bc, 12);
 
     /* media table followed by the extra sources (src/mcx_host.cpp:746-751) */
@@ -195,7 +200,7 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     std::vector<unsigned int> tdetcount(hostthreads, 0);
     std::vector<unsigned long long> cnt_seg(hostthreads, 0), cnt_dep(hostthreads, 0), cnt_log(hostthreads, 0);
     std::vector<float> genergy((size_t)nthread * 2, 0.f);
-    const size_t sharedbytes = 4 * (size_t)(w0offset + param.srcnum + 2) + 16 * param.issaveseed + 64;
+    const size_t sharedbytes = 4 * (size_t)(param.nphaselen + param.nanglelen) + 4 * (size_t)(w0offset + param.srcnum + 2) + 16 * param.issaveseed + 64;
 
     auto t0 = std::chrono::steady_clock::now();
     #pragma omp parallel num_threads(hostthreads)
@@ -227,7 +232,7 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
             kern(cfg->vol, tfield[tid].data(), genergy.data(), seeds.data(),
                  cfg->issavedet ? tdet[tid].data() : NULL, gproperty.data(), (float*)cfg->srcpattern,
                  gdetpos.data(), &progress, &tdetcount[tid],
-                 cfg->issaveseed ? tseed[tid].data() : NULL, NULL, NULL, shared.data(), &param);
+                 cfg->issaveseed ? tseed[tid].data() : NULL, (float*)cfg->invcdf, (float*)cfg->angleinvcdf, shared.data(), &param);
         }
 
         cnt_seg[tid] = clshim_cnt_isgreater;
@@ -430,6 +435,10 @@ extern "C" int mcxref_transmit(mcxb_f4* v, const float* n1, const float* n2, con
     }
 
     return 0;
+}
+
+extern "C" unsigned int mcxref_configsize(void) {
+    return (unsigned int)sizeof(mcxb_config);
 }
 
 extern "C" unsigned int mcxref_paramsize(void) {

@@ -1,0 +1,75 @@
+"""Generate tests/golden/*.npz from the reference's own kernel source (oracle/_ref/libmcxref.so).
+
+    python tests/golden/make_golden.py
+
+Needs /root/reference (to build oracle/_ref); the outputs are committed so the GPU box, which has no
+reference tree, can still test against reference statistics.
+
+ref_stats_<deck>.npz:  per-voxel mean and seed-to-seed standard deviation of the RAW (un-normalised)
+fluence deposits of R independent reference runs (seeds s0 .. s0+R-1, N photons, W work-items), kept for
+the voxels whose mean exceeds 1e-4 of the peak (the criterion of BASELINE.json), plus the absorbed
+fraction, detected count and per-photon work counters of every run.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from mcxcl_b200 import benchmarks, hostcfg  # noqa: E402
+from oracle import loader  # noqa: E402
+
+DECKS = {
+    # name: (deck kwargs, photons per run, work-items, runs)
+    "cube60": (dict(name="cube60"), 200000, 4096, 12),
+    "cube60b": (dict(name="cube60b"), 200000, 4096, 12),
+    # 200^3 volume: statistics are kept on 8x8x8-voxel blocks (25^3 bins) to keep the fixture small
+    "skinvessel": (dict(name="skinvessel", bin=8), 20000, 2048, 8),
+}
+SEED0 = 1648335518
+
+
+def bin_field(field, dims, b):
+    """sum an x-fastest flat volume over b x b x b blocks"""
+    nx, ny, nz = dims
+    v = field.reshape(nz, ny, nx)
+    return v.reshape(nz // b, b, ny // b, b, nx // b, b).sum(axis=(1, 3, 5)).ravel()
+
+
+def main():
+    ref = loader.ref()
+    only = sys.argv[1:]
+    for key, (kw, nph, work, runs) in DECKS.items():
+        if only and key not in only:
+            continue
+        cfg = benchmarks.get(kw["name"], nph)
+        fields, absorbed, detected, seg, dep, sca = [], [], [], [], [], []
+        for r in range(runs):
+            cfg["seed"] = SEED0 + r
+            p = hostcfg.prepare(cfg)
+            o = ref.run(p, work, hostthreads=0)
+            fld = o["field"].astype(np.float64)
+            if kw.get("bin"):
+                fld = bin_field(fld, p.dims, kw["bin"])
+            fields.append(fld)
+            absorbed.append(o["absorbed"])
+            detected.append(o["detected"])
+            seg.append(o["n_segment"] / nph)
+            dep.append(o["n_deposit"] / nph)
+            sca.append(o["n_scatter"] / nph)
+            print(key, r, o["absorbed"], o["detected"], flush=True)
+        f = np.stack(fields)
+        mean, std = f.mean(0), f.std(0, ddof=1)
+        keep = np.nonzero(mean > 1e-4 * mean.max())[0]
+        np.savez_compressed(os.path.join(HERE, "ref_stats_%s.npz" % key),
+                            idx=keep.astype(np.uint32), mean=mean[keep].astype(np.float32), std=std[keep].astype(np.float32),
+                            total=f.sum(1), absorbed=np.array(absorbed), detected=np.array(detected),
+                            seg=np.array(seg), dep=np.array(dep), sca=np.array(sca),
+                            nphoton=nph, work=work, runs=runs, seed0=SEED0, bin=kw.get("bin", 1))
+        print(key, "voxels kept", keep.size, "absorbed", np.mean(absorbed), "+-", np.std(absorbed, ddof=1))
+
+
+if __name__ == "__main__":
+    main()

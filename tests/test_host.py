@@ -1,0 +1,166 @@
+"""CPU-side checks: the C ABI library loads and exports every symbol of include/mcxb200.h, the ctypes
+mirror has the C layout, the seed table is glibc-rand() compatible, and the host configuration layer
+(mcxcl_b200.hostcfg, mirror of mcx_initcfg/mcx_validatecfg/mcx_preprocess/mcx_maskdet) behaves like the
+reference's.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from mcxcl_b200 import abi, benchmarks, hostcfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mcxb200.h")
+
+
+def test_library_exports_every_declared_symbol(lib):
+    text = open(HEADER).read()
+    declared = set(re.findall(r"\b(mcxb_[a-z0-9_]+)\s*\(", text))
+    assert declared, "no prototypes found"
+    bound = {name for name, _, _ in abi.SYMBOLS}
+    assert declared == bound, (declared - bound, bound - declared)
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_ctypes_layout_matches_c_header():
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "mcxb200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu\n", sizeof(mcxb_config), sizeof(mcxb_output), sizeof(mcxb_gpuinfo), sizeof(mcxb_trace_step), sizeof(mcxb_source));
+    printf("%zu %zu %zu %zu %zu %zu\n", offsetof(mcxb_config, vol), offsetof(mcxb_config, src), offsetof(mcxb_config, nphoton),
+           offsetof(mcxb_config, bc), offsetof(mcxb_config, sched), offsetof(mcxb_config, accum));
+    printf("%zu %zu %zu\n", offsetof(mcxb_output, energytot), offsetof(mcxb_output, kernel_launches), offsetof(mcxb_output, stats));
+    return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        cfile = os.path.join(d, "t.c")
+        open(cfile, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), cfile, "-o", exe])
+        lines = subprocess.check_output([exe]).decode().split("\n")
+    sizes = [int(x) for x in lines[0].split()]
+    assert sizes == [C.sizeof(abi.Config), C.sizeof(abi.Output), C.sizeof(abi.GPUInfo), C.sizeof(abi.TraceStep), C.sizeof(abi.Source)]
+    offs = [int(x) for x in lines[1].split()]
+    assert offs == [getattr(abi.Config, f).offset for f in ("vol", "src", "nphoton", "bc", "sched", "accum")]
+    offs = [int(x) for x in lines[2].split()]
+    assert offs == [getattr(abi.Output, f).offset for f in ("energytot", "kernel_launches", "stats")]
+
+
+def test_seed_table_is_glibc_rand(lib):
+    """src/mcx_host.cpp:696-700, 759-768: srand(seed); seeds[i] = rand().  Compared with the C library itself."""
+    libc = C.CDLL("libc.so.6")
+    libc.rand.restype = C.c_int
+    for seed, skip, n in ((1648335518, 0, 64), (29012392, 17, 33), (1, 0, 8), (2147483647, 3, 5)):
+        libc.srand(C.c_uint(seed))
+        want = np.array([libc.rand() for _ in range(4 * (skip + n))], dtype=np.uint32)[4 * skip:]
+        got = np.zeros(4 * n, dtype=np.uint32)
+        lib.mcxb_fill_seeds(seed, skip, n, got.ctypes.data)
+        assert (got == want).all(), seed
+
+
+def test_seed_slices_concatenate(lib):
+    """rank r of a multi-GPU job skips r*nthread records of ONE stream (src/mcx_host.cpp:759-768)."""
+    whole = np.zeros(4 * 96, dtype=np.uint32)
+    lib.mcxb_fill_seeds(12345, 0, 96, whole.ctypes.data)
+    parts = []
+    for r in range(3):
+        part = np.zeros(4 * 32, dtype=np.uint32)
+        lib.mcxb_fill_seeds(12345, 32 * r, 32, part.ctypes.data)
+        parts.append(part)
+    assert (np.concatenate(parts) == whole).all()
+
+
+def test_prepare_cube60_matches_reference_preprocessing():
+    p = hostcfg.prepare(benchmarks.get("cube60b", 1e6))
+    c = p.c
+    assert (c.dimx, c.dimy, c.dimz, c.medianum) == (60, 60, 60, 3)
+    assert p.maxgate == 1 and p.fieldlen == 216000
+    assert c.savedetflag == 5 and p.partialdata == 2 and p.reclen == 3
+    # launch voxel index / label stored as uint bits in param2.z/.w (src/mcx_utils.c:1718-1749)
+    z, w = np.array([c.src.param2.z, c.src.param2.w], dtype=np.float32).view(np.uint32)
+    assert (z, w) == (29 * 60 + 29, 1)
+    vol = p.keep["vol"]
+    assert int((vol >> 31).sum()) == 48          # mcxcl --bench cube60 --dumpmask flags 48 voxels
+    assert set(np.unique(vol & 0x7FFFFFFF)) == {1}
+    assert c.isreflect == 1 and hostcfg.prepare(benchmarks.get("cube60", 1e3)).c.isreflect == 0
+
+
+def test_prepare_unitinmm_and_zero_mus():
+    p = hostcfg.prepare(benchmarks.get("skinvessel", 1e3))
+    prop = p.keep["prop"]
+    assert prop[0, 1] == np.float32(1e-10)                       # mus==0 -> EPS (src/mcx_utils.c:1647-1653)
+    np.testing.assert_allclose(prop[2, 0], np.float32(23.05426549) * np.float32(0.005), rtol=1e-7)
+    assert p.c.issavedet == 0 and p.c.savedetflag == 0 and p.c.srctype == 8
+    assert sorted(np.unique(p.keep["vol"]).tolist()) == [1, 2, 3, 4]
+    counts = np.bincount(p.keep["vol"])
+    assert counts[1] == 800000 and counts[4] == 480000 and counts[2] == 251400
+
+
+def test_prepare_one_based_coordinates():
+    p = hostcfg.prepare(benchmarks.get("qtest", 1e3))
+    assert (p.c.src.pos.x, p.c.src.pos.y, p.c.src.pos.z) == (29.0, 29.0, 0.0)
+    np.testing.assert_array_equal(p.keep["detpos"][0], np.array([29, 19, 0, 1], dtype=np.float32))
+
+
+def test_prepare_direction_normalised():
+    cfg = benchmarks.get("cube60", 10)
+    cfg["srcdir"] = [0.1636, 0.4569, -0.8743]
+    p = hostcfg.prepare(cfg)
+    d = np.array([p.c.src.dir.x, p.c.src.dir.y, p.c.src.dir.z], dtype=np.float64)
+    assert abs(np.linalg.norm(d) - 1) < 1e-6
+
+
+@pytest.mark.parametrize("mutate,code", [
+    (lambda c: c.pop("prop"), -4),
+    (lambda c: c.update(vol=np.ones((4, 4), np.uint8)), -4),
+    (lambda c: c.update(srcdir=[0, 0, 0]), -4),
+    (lambda c: c.update(prop=[[0, 0, 1, 1]]), -4),
+    (lambda c: c.update(tend=0.0), -6),
+    (lambda c: c.update(srctype="laser"), -6),
+    (lambda c: c.update(bc="xyzabc"), -4),
+    (lambda c: c.update(respin=2), -1),
+])
+def test_prepare_rejects_like_reference(mutate, code):
+    cfg = benchmarks.get("cube60", 10)
+    mutate(cfg)
+    with pytest.raises(hostcfg.ConfigError) as e:
+        hostcfg.prepare(cfg)
+    assert e.value.code == code and "MCXCL ERROR(%d)" % code in str(e.value)
+
+
+def test_boundary_condition_parsing():
+    codes = hostcfg.parse_bc("aarraa")
+    assert codes[:6].tolist() == [2, 2, 1, 1, 2, 2] and not codes[6:].any()
+    codes = hostcfg.parse_bc("______111111")
+    assert codes[:6].tolist() == [0] * 6 and codes[6:].tolist() == [1] * 6
+    assert hostcfg.parse_savedetflag("dspxvw") == 0x77 and hostcfg.parse_savedetflag("DP") == 5
+
+
+def test_multisource_rows():
+    cfg = benchmarks.get("cube60", 10)
+    cfg.update(srcpos=[[29, 29, 0], [10, 10, 0], [50, 50, 0]], srcdir=[[0, 0, 1]] * 3, srcid=-1)
+    p = hostcfg.prepare(cfg)
+    assert p.c.extrasrclen == 2 and p.nsrcvol == 3 and p.fieldlen == 3 * 216000
+    assert p.keep["extra"].shape == (2, 16)
+    z = p.keep["extra"][:, 14].view(np.uint32)
+    assert z.tolist() == [10 * 60 + 10, 50 * 60 + 50]
+
+
+def test_engine_refuses_to_run_without_a_gpu(lib):
+    """no CPU fallback: on a box without CUDA devices the product path fails loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mcxcl_b200 import engine
+    with pytest.raises(RuntimeError) as e:
+        engine.run(benchmarks.get("cube60", 100))
+    assert "failed" in str(e.value)
+    assert engine.gpuinfo() == []

@@ -1,0 +1,111 @@
+"""Pin the CPU oracle (oracle/_ref: the reference's own kernel source compiled for the host) against every
+known answer the reference's tests and the survey hold for the photon-transport path
+(tests/golden/kat_survey.json; reference test/testmcx.sh:60-132, mcxlabcl/examples/mcx_gpu_benchmarks.m)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from mcxcl_b200 import benchmarks, hostcfg
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "kat_survey.json")))
+
+
+def bits(x):
+    return np.asarray(x, dtype=np.float32).view(np.uint32)
+
+
+def test_seed_table_matches_glibc_rand(ref):
+    seeds = ref.seeds(KAT["seed"], len(KAT["rng"])).reshape(-1, 4)
+    for row in KAT["rng"]:
+        assert seeds[row["thread"]].tolist() == row["seed"]
+
+
+def test_rng_known_answers(ref):
+    seeds = ref.seeds(KAT["seed"], len(KAT["rng"]))
+    u, _ = ref.rng(seeds, 3)
+    for row in KAT["rng"]:
+        np.testing.assert_allclose(u[row["thread"]], np.array(row["u"], dtype=np.float32), rtol=2e-7, atol=0)
+
+
+def test_rng_state_words(ref):
+    # t[0] = seed[0]<<32 | seed[1] (src/mcx_core.cl:709-712): check through zero draws
+    seeds = ref.seeds(KAT["seed"], len(KAT["rng"]))
+    _, st = ref.rng(seeds, 0)
+    for row in KAT["rng"]:
+        assert [hex(int(x)) for x in st[row["thread"]]] == [hex(int(t, 16)) for t in row["t"]]
+
+
+def test_traversal_known_answers(ref):
+    t = KAT["trace"]
+    v0 = np.array([int(b, 16) for b in t["v0_bits"]], dtype=np.uint32).view(np.float32)
+    p0 = np.array(t["p0"] + [1.0], dtype=np.float32)
+    out = ref.trace(p0, np.append(v0, 0).astype(np.float32), len(t["steps"]), t["dims"], t["musp"])[0]
+    for k, s in enumerate(t["steps"]):
+        assert int(out["face"][k]) == s["face"], k
+        assert "%08x" % bits(out["dist"][k]) == s["dist"], k
+        assert ["%08x" % bits(out[c][k]) for c in ("px", "py", "pz")] == s["p"], k
+        assert [int(out[c][k]) for c in ("ix", "iy", "iz")] == s["voxel"], k
+        assert int(out["idx1d"][k]) == s["idx1d"], k
+
+
+def test_scalar_known_answers(ref):
+    sc = KAT["scalar"]
+    a = [r[0] for r in sc["nextafter"]]
+    d = [r[1] for r in sc["nextafter"]]
+    rc = sc["reflectcoeff"]
+    na, r = ref.scalar(a, d, [x["v"] + [0] for x in rc], [x["n1"] for x in rc], [x["n2"] for x in rc], [x["face"] for x in rc])
+    assert ["%08x" % b for b in bits(na)] == [r_[2] for r_ in sc["nextafter"]]
+    assert ["%08x" % b for b in bits(r)] == [x["bits"] for x in rc]
+
+
+@pytest.mark.parametrize("deck,prefix", [("cube60", "17."), ("cube60b", "27.")])
+def test_absorbed_fraction_pins(ref, deck, prefix):
+    """test/testmcx.sh:60-66: `--bench cube60` prints absorbed 17.x%, cube60b 27.x%."""
+    p = hostcfg.prepare(benchmarks.get(deck, 1e5))
+    o = ref.run(p, 1024, hostthreads=0)
+    assert ("%.5f" % (100 * o["absorbed"])).startswith(prefix)
+    assert abs(o["energytot"] - 1e5) <= 10           # mcx_gpu_benchmarks.m: |energytot - nphoton| <= 10
+    if deck == "cube60":
+        lo, tol = KAT["statistical"]["cube60_absorbed"]
+        assert abs(o["absorbed"] - lo) <= tol
+
+
+def test_detected_count_pin(ref):
+    """cube60b, 1e5 photons over 1024 work-items -> 489 detected (test/testmcx.sh:80-82: 4xx)."""
+    p = hostcfg.prepare(benchmarks.get("cube60b", 1e5))
+    o = ref.run(p, 1024, hostthreads=0)
+    assert o["detected"] == KAT["statistical"]["cube60b_detected_1e5_w1024"]
+    assert o["reclen"] == 3 and o["detp"].shape == (489, 3)
+    assert set(np.unique(o["detp"][:, 0]).astype(int)) == {1, 2, 3, 4}
+    # energy conservation: sum(field)*mua == absorbed energy (fluence deposits are (w0-w)/mua)
+    mua = p.keep["prop"][1, 0]
+    np.testing.assert_allclose(o["field"].astype(np.float64).sum() * mua, o["energytot"] - o["energyesc"], rtol=2e-4)
+
+
+def test_work_counters(ref):
+    """cube60b 322.7 segments / 193.4 deposits / 130.0 scatters per photon."""
+    p = hostcfg.prepare(benchmarks.get("cube60b", 1e5))
+    o = ref.run(p, 1024, hostthreads=0)
+    assert abs(o["n_segment"] / 1e5 - 322.7) < 0.1
+    assert abs(o["n_deposit"] / 1e5 - 193.4) < 0.1
+    assert abs(o["n_scatter"] / 1e5 - 130.0) < 0.1
+
+
+def test_oracle_deterministic_across_host_threads(ref):
+    p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
+    a = ref.run(p, 512, hostthreads=1)
+    b = ref.run(p, 512, hostthreads=0)
+    assert a["energyesc"] == b["energyesc"] and a["detected"] == b["detected"]
+
+
+def test_golden_fixture_consistency(ref):
+    """the committed reference statistics reproduce from the oracle (first seed of the series)."""
+    g = np.load(os.path.join(HERE, "golden", "ref_stats_cube60b.npz"))
+    cfg = benchmarks.get("cube60b", int(g["nphoton"]))
+    cfg["seed"] = int(g["seed0"])
+    o = ref.run(hostcfg.prepare(cfg), int(g["work"]), hostthreads=0)
+    assert o["absorbed"] == pytest.approx(float(g["absorbed"][0]), abs=1e-12)
+    assert o["detected"] == int(g["detected"][0])
