@@ -219,22 +219,23 @@ struct mcxb_sim {
     float last_ms = 0.f;
 };
 
-static const KernelEntry* find_kernel(int src, bool refl, bool det, bool m16, bool acc64, bool stats) {
+static const KernelEntry* find_kernel(int src, bool refl, bool det, bool m16, bool acc64, bool stats, bool common) {
     typedef const KernelEntry* (*GroupFn)(int*);
-    static const GroupFn groups[kNumGroups] = { mcxb_kernel_group_0, mcxb_kernel_group_1, mcxb_kernel_group_2,
-                                                mcxb_kernel_group_3, mcxb_kernel_group_4, mcxb_kernel_group_5
+    static const GroupFn groups[kNumGroups] = { mcxb_kernel_group_0, mcxb_kernel_group_1, mcxb_kernel_group_2, mcxb_kernel_group_3,
+                                                mcxb_kernel_group_4, mcxb_kernel_group_5, mcxb_kernel_group_6
                                               };
+    /* most specialised first: {source, common} -> {any source, common} -> {any source, generic} */
+    const int wantsrc[3] = { src, (int)srcAny, (int)srcAny };
+    const bool wantgen[3] = { false, false, true };
 
-    for (int pass = 0; pass < 2; pass++) {
-        const int want = pass == 0 ? src : (int)srcAny;
-
+    for (int pass = common ? 0 : 2; pass < 3; pass++) {
         for (int g = 0; g < kNumGroups; g++) {
             int n = 0;
             const KernelEntry* e = groups[g](&n);
 
             for (int i = 0; i < n; i++) {
-                if (e[i].src == want && e[i].reflect == refl && e[i].savedet == det && e[i].media16 == m16 &&
-                        e[i].acc64 == acc64 && e[i].stats == stats) {
+                if (e[i].src == wantsrc[pass] && e[i].generic == wantgen[pass] && e[i].reflect == refl && e[i].savedet == det &&
+                        e[i].media16 == m16 && e[i].acc64 == acc64 && e[i].stats == stats) {
                     return e + i;
                 }
             }
@@ -242,6 +243,20 @@ static const KernelEntry* find_kernel(int src, bool refl, bool det, bool m16, bo
     }
 
     return nullptr;
+}
+
+/* true when the configuration fits the compile-time assumptions of the GEN=false kernels (photon_kernel.cuh) */
+static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t nphase) {
+    for (int i = 0; i < 12; i++) {
+        if (cfg->bc[i] != 0) {
+            return false;
+        }
+    }
+
+    const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
+    return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->extrasrclen == 0 && cfg->issaveref == 0 &&
+           !(savedet && cfg->issaveseed > 0) && cfg->issave2pt != 0 &&
+           (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE);
 }
 
 /* the reference's rule for compiling the reflection code in (src/mcx_host.cpp:945-956) */
@@ -533,8 +548,9 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->acc64 = cfg->accum != MCXB_ACCUM_F32;
     const bool refl = needs_reflection(cfg);
     const bool stats = (cfg->debuglevel & MCXB_DEBUG_STATS) != 0;
-    const KernelEntry* ke = stats ? find_kernel(srcAny, true, true, s->media16, true, true)
-                            : find_kernel(cfg->srctype, refl, savedet, s->media16, s->acc64, false);
+    const bool common = is_common_config(cfg, savedet, nphase);
+    const KernelEntry* ke = stats ? find_kernel(srcAny, true, true, s->media16, true, true, false)
+                            : find_kernel(cfg->srctype, refl, savedet, s->media16, s->acc64, false, common);
 
     if (!ke) {
         return fail(MCXB_ERR_ARG, "no kernel specialisation for this configuration");
@@ -857,7 +873,7 @@ extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) 
         const float* src = s->h_field;
         const uint64_t n = s->fieldlen;
 
-        if (s->cfg.isnormalized && !s->rngdebug) {
+        if (s->cfg.isnormalized && !s->rngdebug && out->energytot > 0.0) {     /* nothing launched: leave the zeros alone */
             const float scale = mcxb_normalizer(&s->cfg, out->energytot);
             out->normalizer = scale;
 

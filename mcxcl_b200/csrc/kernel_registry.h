@@ -15,12 +15,12 @@ typedef void (*PhotonKernelFn)(const SimParam);
 
 struct KernelEntry {
     int  src;          /* SrcType or srcAny */
-    bool reflect, savedet, media16, acc64, stats;
+    bool reflect, savedet, media16, acc64, stats, generic;
     PhotonKernelFn fn;
     const char* name;
 };
 
-constexpr int kNumGroups = 6;
+constexpr int kNumGroups = 7;
 
 } // namespace mcxb
 
@@ -30,3 +30,4 @@ extern "C" const mcxb::KernelEntry* mcxb_kernel_group_2(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_3(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_4(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_5(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_6(int* n);

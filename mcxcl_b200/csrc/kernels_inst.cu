@@ -2,38 +2,42 @@
  * kernels_inst.cu -- explicit instantiations of photon_kernel, one group per compilation
  * (nvcc ... -DMCXB_INST_GROUP=k).  See kernel_registry.h.
  *
- *   group 0: pencil beam,           8-bit media
- *   group 1: disk / ring source,    8-bit media
- *   group 2: planar + fourier,      8-bit media
- *   group 3: isotropic + cone,      8-bit media
- *   group 4: any source (run time), 8-bit media  (+ the instrumented variant that counts segments/deposits/scatters)
- *   group 5: any source (run time), 16-bit media (volumes with more than 127 labels)
+ *   "common" = the GEN=false form of the kernel (photon_kernel.cuh), "generic" = every option at run time
+ *   group 0: pencil beam,           8-bit media, common
+ *   group 1: disk source,           8-bit media, common
+ *   group 2: planar + fourier,      8-bit media, common
+ *   group 3: isotropic + cone,      8-bit media, common
+ *   group 4: any source (run time), 8-bit media, common
+ *   group 5: any source (run time), 8-bit media, generic  (+ the instrumented variant that counts segments/deposits/scatters)
+ *   group 6: any source (run time), 16-bit media, generic (volumes with more than 127 labels)
  */
 #include "kernel_registry.h"
 
 #ifndef MCXB_INST_GROUP
-    #error "compile with -DMCXB_INST_GROUP=<0..5>"
+    #error "compile with -DMCXB_INST_GROUP=<0..6>"
 #endif
 
 namespace mcxb {
 
-#define MCXB_K(SRC, R, D, M, A, S) { SRC, R, D, sizeof(M) == 2, sizeof(A) == 8, S, photon_kernel<SRC, R, D, M, A, S>, #SRC "/" #R #D "/" #M "/" #A }
-#define MCXB_RD(SRC, M, A) MCXB_K(SRC, false, false, M, A, false), MCXB_K(SRC, true, false, M, A, false), \
-                           MCXB_K(SRC, false, true, M, A, false), MCXB_K(SRC, true, true, M, A, false)
+#define MCXB_K(SRC, R, D, M, A, S, G) { SRC, R, D, sizeof(M) == 2, sizeof(A) == 8, S, G, photon_kernel<SRC, R, D, M, A, S, G>, #SRC "/" #R #D "/" #M "/" #A "/" #G }
+#define MCXB_RD(SRC, M, A, G) MCXB_K(SRC, false, false, M, A, false, G), MCXB_K(SRC, true, false, M, A, false, G), \
+                              MCXB_K(SRC, false, true, M, A, false, G), MCXB_K(SRC, true, true, M, A, false, G)
 
 static const KernelEntry entries[] = {
 #if MCXB_INST_GROUP == 0
-    MCXB_RD(srcPencil, uint8_t, double), MCXB_RD(srcPencil, uint8_t, float)
+    MCXB_RD(srcPencil, uint8_t, double, false), MCXB_RD(srcPencil, uint8_t, float, false)
 #elif MCXB_INST_GROUP == 1
-    MCXB_RD(srcDisk, uint8_t, double), MCXB_RD(srcDisk, uint8_t, float)
+    MCXB_RD(srcDisk, uint8_t, double, false), MCXB_RD(srcDisk, uint8_t, float, false)
 #elif MCXB_INST_GROUP == 2
-    MCXB_RD(srcPlanar, uint8_t, double), MCXB_RD(srcFourier, uint8_t, double)
+    MCXB_RD(srcPlanar, uint8_t, double, false), MCXB_RD(srcFourier, uint8_t, double, false)
 #elif MCXB_INST_GROUP == 3
-    MCXB_RD(srcIsotropic, uint8_t, double), MCXB_RD(srcCone, uint8_t, double)
+    MCXB_RD(srcIsotropic, uint8_t, double, false), MCXB_RD(srcCone, uint8_t, double, false)
 #elif MCXB_INST_GROUP == 4
-    MCXB_RD(srcAny, uint8_t, double), MCXB_RD(srcAny, uint8_t, float), MCXB_K(srcAny, true, true, uint8_t, double, true)
+    MCXB_RD(srcAny, uint8_t, double, false), MCXB_RD(srcAny, uint8_t, float, false)
 #elif MCXB_INST_GROUP == 5
-    MCXB_RD(srcAny, uint16_t, double), MCXB_RD(srcAny, uint16_t, float), MCXB_K(srcAny, true, true, uint16_t, double, true)
+    MCXB_RD(srcAny, uint8_t, double, true), MCXB_RD(srcAny, uint8_t, float, true), MCXB_K(srcAny, true, true, uint8_t, double, true, true)
+#elif MCXB_INST_GROUP == 6
+    MCXB_RD(srcAny, uint16_t, double, true), MCXB_RD(srcAny, uint16_t, float, true), MCXB_K(srcAny, true, true, uint16_t, double, true, true)
 #endif
 };
 

@@ -282,11 +282,14 @@ __device__ __forceinline__ void sample_source(const SimParam& P, const float4* _
             ph.px += rx * p1.x;
             ph.py += ry * p1.y;
             ph.pz += rz * p1.z;
-        } else {
-            ph.px += rx * p1.x + ry * p2.x;
-            ph.py += rx * p1.y + ry * p2.y;
-            ph.pz += rx * p1.z + ry * p2.z;
         }
+
+        /* reference quirk, kept for parity: in the OpenCL build the `else` that separates the pattern3d offset
+         * from the planar one is compiled only for __NVCC__ (:1675-1678), so a pattern3d packet receives the
+         * planar offset rx*param1 + ry*param2 on top of its own ("reference quirks") */
+        ph.px += rx * p1.x + ry * p2.x;
+        ph.py += rx * p1.y + ry * p2.y;
+        ph.pz += rx * p1.z + ry * p2.z;
 
         if (st == srcPattern) {
             ph.w = pos.w * __ldg(P.srcpattern + (int)(ry * kJustBelowOne * p2.w) * (int)p1.w + (int)(rx * kJustBelowOne * p1.w));
@@ -556,11 +559,27 @@ __device__ __forceinline__ void save_detected(const SimParam& P, const float4* _
 
 /* ---------------------------------------------------------------------------------------------------
  * the kernel
+ *
+ * Compile-time axes (the reference JIT-specialises on the same ones, src/mcx_host.cpp:857-971):
+ *   SRC      source type, or srcAny = decided at run time
+ *   REFLECT  index-mismatch handling compiled in (MCX_DO_REFLECTION)
+ *   SAVEDET  detected-photon capture compiled in (MCX_SAVE_DETECTORS)
+ *   MediaT   uint8_t (<=127 labels) or uint16_t media words
+ *   AccT     double or float fluence accumulators
+ *   STATS    count segments / deposits / scattering events (instrumented build, used to measure SURVEY 8(d))
+ *   GEN      false = the common configuration, with everything below decided at compile time:
+ *              3-D domain, Henyey-Greenstein phase function, no gscatter switch, one source, flux or fluence
+ *              output with save2pt on, no diffuse-reflectance / seed saving, all six boundary codes "unknown"
+ *              (i.e. governed by isreflect alone) and no detect-on-face flags;
+ *            true  = every option read from SimParam at run time.
  * ------------------------------------------------------------------------------------------------- */
 constexpr int kBlock = 256;
+#ifndef MCXB_MINBLOCKS
+    #define MCXB_MINBLOCKS 3
+#endif
 
-template <int SRC, bool REFLECT, bool SAVEDET, typename MediaT, typename AccT, bool STATS>
-__global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant__ SimParam P) {
+template <int SRC, bool REFLECT, bool SAVEDET, typename MediaT, typename AccT, bool STATS, bool GEN>
+__global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __grid_constant__ SimParam P) {
     extern __shared__ float4 smem[];
     float4* tab = smem;                                   /* optical properties, row 0 = background */
     const float4* srctab = tab + P.medianum;              /* 4 rows per source, main source first  */
@@ -596,6 +615,8 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
     const MediaT* __restrict__ media = static_cast<const MediaT*>(P.media);
     AccT* __restrict__ field = static_cast<AccT*>(P.field);
     const float n0 = tab[0].w;
+    /* partial-path rows of this thread, biased so that the row of label L is ppath_len[L * kBlock] */
+    float* const ppath_len = ppath + ((int)(((P.savedetflag >> 1) & 1u) * (P.medianum - 1)) - 1) * kBlock;
 
     Rng rng;
     rng_seed(rng, P.seeds + 4 * (size_t)tid);
@@ -631,7 +652,7 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
             if (!(ph.w != ph.w)) {
                 e_escaped += ph.w;
 
-                if (P.issaveref == 1 && ph.label == 0 && ph.idx1d != kOutsideMin && ph.idx1d != kOutsideMax && ph.w > 0.f) {
+                if (GEN && P.issaveref == 1 && ph.label == 0 && ph.idx1d != kOutsideMin && ph.idx1d != kOutsideMax && ph.w > 0.f) {
                     int tshift = min((int)P.maxgate - 1, (int)floorf((ph.tof - P.twin0) * P.Rtstep));
 
                     if (P.extrasrclen && P.srcid < 0) {
@@ -642,7 +663,7 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
                 }
 
                 if (SAVEDET) {
-                    if ((detarg & kDetMask) && ph.label == 0 && P.issaveref < 2) {
+                    if ((detarg & kDetMask) && ph.label == 0 && (!GEN || P.issaveref < 2)) {
                         save_detected(P, dettab, ppath, kBlock, ph, detarg, w0init, cursrc, photonseed);
                     }
                 }
@@ -670,14 +691,14 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
             }
 
             /* ------------------------------------------------------------------ launch (:1598-2255) */
-            if (P.issaveseed) {
+            if (GEN && P.issaveseed) {
                 photonseed[0] = rng.a;
                 photonseed[kBlock] = rng.b;
             }
 
             const float4* S = srctab;
 
-            if (P.extrasrclen && P.srcid != 1) {
+            if (GEN && P.extrasrclen && P.srcid != 1) {
                 if (P.srcid > 1) {
                     S = srctab + 4 * (P.srcid - 1);
                 } else {
@@ -758,7 +779,11 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
                 }
 
                 if (rawlabel == 0) {
-                    const int idx = enter_volume<MediaT>(P, tab, ph);
+                    /* the marcher takes the packet by reference and is not inlined: hand it a copy so that the
+                     * live packet state never has its address taken and stays in registers */
+                    Photon tmp = ph;
+                    const int idx = enter_volume<MediaT>(P, tab, tmp);
+                    ph = tmp;
 
                     if (idx >= 0) {
                         ph.idx1d = (uint32_t)idx;
@@ -785,13 +810,7 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
             budget--;
             ph.label = rawlabel;
             ph.detflag = rawdet;
-            {
-                const float4 pr = tab[ph.label];
-                mua = pr.x;
-                mus = pr.y;
-                g = pr.z;
-                nmed = pr.w;
-            }
+            nmed = tab[ph.label].w;
             e_launched += ph.w;
             ph.w0 = ph.w;
             w0init = ph.w;
@@ -807,34 +826,34 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
 
             if (ph.nscat >= 0) {
                 float sphi = 0.f, cphi = 1.f, stheta, ctheta;
+                const bool flat = GEN && P.is2d;
 
-                if (!P.is2d) {
-                    __sincosf(kTwoPi * rng_uniform(rng), &sphi, &cphi);
+                if (!flat) {
+                    mufu_sincos(kTwoPi * rng_uniform(rng), sphi, cphi);
                 }
 
-                if (P.nphase > 2) {
+                if (GEN && P.nphase > 2) {
                     /* tabulated phase function: linear interpolation of the inverse CDF of cos(theta) */
                     float u = rng_uniform(rng) * (float)(P.nphase - 1);
                     const float fr = u - (float)(int)u;
                     const uint32_t i0 = ((uint32_t)u >= P.nphase) ? P.nphase - 1 : (uint32_t)u;
                     const uint32_t i1 = ((uint32_t)u + 1 >= P.nphase) ? P.nphase - 1 : (uint32_t)u + 1;
                     ctheta = (1.f - fr) * ftab[i0] + fr * ftab[i1];
-                    stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
                 } else {
-                    const float gg = ((uint32_t)ph.nscat > P.gscatter) ? 0.f : g;
+                    const float gg = (GEN && (uint32_t)ph.nscat > P.gscatter) ? 0.f : g;
 
                     if (fabsf(gg) > kEps) {
                         /* Henyey-Greenstein inverse CDF (:2487-2490); sin(acos(c)) == sqrt(1-c^2) on [0,pi] */
-                        float t = __fdividef(1.f - g * g, 1.f - g + 2.f * g * rng_uniform(rng));
+                        float t = (1.f - g * g) * mufu_rcp(1.f - g + 2.f * g * rng_uniform(rng));
                         t *= t;
-                        ctheta = __fdividef(1.f + g * g - t, 2.f * g);
+                        ctheta = (1.f + g * g - t) * mufu_rcp(2.f * g);
                         ctheta = fmaxf(-1.f, fminf(1.f, ctheta));
                     } else {
                         ctheta = 2.f * rng_uniform(rng) - 1.f;
                     }
-
-                    stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
                 }
+
+                stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
 
                 if (SAVEDET) {
                     const uint32_t flag = P.savedetflag;
@@ -850,13 +869,14 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
                     }
                 }
 
-                if (P.is2d) {
+                if (flat) {
                     rotate_direction_2d(ph.vx, ph.vy, ph.vz, (rng_uniform(rng) > 0.5f ? stheta : -stheta), ctheta, (int)P.is2d);
                 } else {
                     rotate_direction(ph.vx, ph.vy, ph.vz, stheta, ctheta, sphi, cphi);
                 }
 
                 ph.nscat++;
+
                 if (STATS) {
                     c_scat++;
                 }
@@ -875,34 +895,32 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
             nmed = pr.w;
         }
         const float dist = face_distance(ph.px, ph.py, ph.pz, ph.vx, ph.vy, ph.vz, ph.ix, ph.iy, ph.iz, ph.face);
-        const float musp = __fmul_rn(mus, ((uint32_t)(ph.nscat + 1) > P.gscatter) ? __fsub_rn(1.f, g) : 1.f);
+        const float musp = (GEN && (uint32_t)(ph.nscat + 1) > P.gscatter) ? __fmul_rn(mus, __fsub_rn(1.f, g)) : mus;
         float slen;
         const float len = step_length(dist, musp, ph.slen, slen);
         ph.pathlen += len;
         ph.px = advance(ph.px, len, ph.vx);
         ph.py = advance(ph.py, len, ph.vy);
         ph.pz = advance(ph.pz, len, ph.vz);
-
-        if (slen != ph.slen) {          /* reached the face before the scattering site */
-            if (ph.face == 0) {
-                ph.ix += (ph.vx > 0.f ? 1 : -1);
-            } else if (ph.face == 1) {
-                ph.iy += (ph.vy > 0.f ? 1 : -1);
-            } else {
-                ph.iz += (ph.vz > 0.f ? 1 : -1);
-            }
+        {
+            /* reached the face before the scattering site: step into the neighbour across that face */
+            const float vf = (ph.face == 0) ? ph.vx : ((ph.face == 1) ? ph.vy : ph.vz);
+            const int d = (slen != ph.slen) ? ((vf > 0.f) ? 1 : -1) : 0;
+            ph.ix += (ph.face == 0) ? d : 0;
+            ph.iy += (ph.face == 1) ? d : 0;
+            ph.iz += (ph.face == 2) ? d : 0;
         }
-
-        ph.w *= __expf(-mua * len);
+        ph.w *= mufu_ex2(mua * len * -1.4426950408889634f);
         ph.slen -= slen;
         ph.tof += len * nmed * P.oneoverc0;
+
         if (STATS) {
             c_seg++;
         }
 
         if (SAVEDET) {
             if (P.savedetflag & 0x04u) {
-                ppath[(((P.savedetflag >> 1) & 1u) * (P.medianum - 1) + ph.label - 1) * kBlock] += len;
+                ppath_len[ph.label * kBlock] += len;
             }
         }
 
@@ -910,38 +928,50 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
         const uint32_t oldidx = ph.idx1d;
         const uint32_t olddet = ph.detflag;
         const uint32_t oldlabel = ph.label;
-        ph.idx1d = linear_index(P, ph.ix, ph.iy, ph.iz);
 
-        if (!voxel_in_grid(P, ph.ix, ph.iy, ph.iz)) {
+        /* the reference compares (ushort)id against the dimension (:2801); ids stay within [-32768, 32767] */
+        if ((uint32_t)ph.ix < P.nx && (uint32_t)ph.iy < P.ny && (uint32_t)ph.iz < P.nz) {
+            ph.idx1d = linear_index(P, ph.ix, ph.iy, ph.iz);
+            fetch_voxel(media, ph.idx1d, ph.label, ph.detflag);
+        } else {
             ph.label = 0;
             ph.idx1d = (ph.ix < 0 || ph.iy < 0 || ph.iz < 0) ? kOutsideMin : kOutsideMax;
-            uint32_t code = P.bc[(ph.idx1d == kOutsideMax) * 3 + ph.face];
-            ph.detflag = ((code & 0xFu) == bcUnknown) ? (P.doreflect ? (uint32_t)bcReflect : (uint32_t)bcAbsorb) : code;
-        } else {
-            fetch_voxel(media, ph.idx1d, ph.label, ph.detflag);
+
+            if (GEN) {
+                const uint32_t code = P.bc[(ph.idx1d == kOutsideMax) * 3 + ph.face];
+                ph.detflag = ((code & 0xFu) == bcUnknown) ? (P.doreflect ? (uint32_t)bcReflect : (uint32_t)bcAbsorb) : code;
+            } else {
+                ph.detflag = REFLECT ? (uint32_t)bcReflect : (uint32_t)bcAbsorb;
+            }
         }
 
         /* ------------------------------------------------------------------ deposit (:2816-2929) */
         if (ph.idx1d != oldidx) {
-            if (P.save2pt && ph.tof >= P.twin0 && ph.tof < P.twin1) {
-                float weight = 0.f;
-                /* clamped: (tof-twin0)*Rtstep can round up to maxgate for tof one ulp below twin1 */
-                int tshift = min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1);
+            if ((!GEN || P.save2pt) && ph.tof >= P.twin0 && ph.tof < P.twin1) {
+                float weight;
 
-                if (P.outputtype == otEnergy) {
+                if (GEN && P.outputtype == otEnergy) {
                     weight = ph.w0 - ph.w;
-                } else if (P.outputtype == otFluence || P.outputtype == otFlux) {
-                    weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : __fdividef(ph.w0 - ph.w, mua);
-                } else if (P.outputtype == otL) {
+                } else if (GEN && P.outputtype == otL) {
                     weight = ph.w0 * ph.pathlen;
+                } else {
+                    weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * mufu_rcp(mua));
                 }
 
-                if (P.extrasrclen && P.srcid < 0) {
-                    tshift += (cursrc - 1) * (int)P.maxgate;
+                uint32_t tshift = 0;
+
+                if (P.maxgate > 1) {
+                    /* clamped: (tof-twin0)*Rtstep can round up to maxgate for tof one ulp below twin1 */
+                    tshift = (uint32_t)min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1);
+                }
+
+                if (GEN && P.extrasrclen && P.srcid < 0) {
+                    tshift += (uint32_t)(cursrc - 1) * P.maxgate;
                 }
 
                 if (fabsf(weight) > 0.f) {
-                    red_add(field + oldidx + (size_t)tshift * P.dimxyz, weight);
+                    red_add(field + ((size_t)tshift * P.dimxyz + oldidx), weight);
+
                     if (STATS) {
                         c_dep++;
                     }
@@ -955,8 +985,8 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
         /* ------------------------------------------------------------------ leave / time out (:2957-3028) */
         const uint32_t bcode = ph.detflag & 0xFu;
 
-        if ((ph.label == 0 && (bcode == bcAbsorb || bcode == bcCyclic || (bcode == bcReflect && ph.n1 == n0))) || ph.tof > P.twin1) {
-            if (ph.detflag == bcCyclic) {
+        if ((ph.label == 0 && (bcode == bcAbsorb || (GEN && bcode == bcCyclic) || (bcode == bcReflect && ph.n1 == n0))) || ph.tof > P.twin1) {
+            if (GEN && ph.detflag == bcCyclic) {
                 /* re-enter through the opposite face (:2970-2996) */
                 if (ph.face == 0) {
                     ph.px = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fnx : 0.f), (ph.vx > 0.f) - (ph.vx < 0.f));
@@ -976,7 +1006,7 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
                 }
             }
 
-            detarg = ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face])) ? kOutsideMin : olddet;
+            detarg = (GEN && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
             relaunch = true;
             continue;
         }
@@ -994,22 +1024,28 @@ __global__ void __launch_bounds__(kBlock, 3) photon_kernel(const __grid_constant
 
         /* ------------------------------------------------------------------ index mismatch (:3063-3297) */
         if (REFLECT) {
-            const float n2 = tab[ph.label].w;
-            const bool want = (ph.label && P.doreflect) ||
-                              (ph.label == 0 && ((bcode == bcUnknown && P.doreflect) || bcode == bcReflect || bcode == bcMirror));
+            const float n2 = (ph.label == oldlabel) ? nmed : tab[ph.label].w;
+            const bool mirror = GEN && bcode == bcMirror;
+            bool handle = false;
 
-            if (want && (bcode == bcMirror || ph.n1 != n2)) {
+            if (mirror || ph.n1 != n2) {
+                handle = ph.label ? (!GEN || P.doreflect)
+                         : (GEN ? ((bcode == bcUnknown && P.doreflect) || bcode == bcReflect || bcode == bcMirror)
+                                : (bcode == bcUnknown || bcode == bcReflect));
+            }
+
+            if (handle) {
                 float Rtotal = 1.f;
 
-                if (bcode != bcMirror) {
+                if (!mirror) {
                     Rtotal = fresnel(ph.vx, ph.vy, ph.vz, ph.n1, n2, ph.face);
                 }
 
-                if (Rtotal < 1.f && !(ph.label == 0 && bcode == bcMirror) && rng_uniform(rng) > Rtotal) {
+                if (Rtotal < 1.f && !(ph.label == 0 && mirror) && rng_uniform(rng) > Rtotal) {
                     refract(ph.vx, ph.vy, ph.vz, ph.n1, n2, ph.face);
 
                     if (ph.label == 0) {
-                        detarg = ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face])) ? kOutsideMin : olddet;
+                        detarg = (GEN && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
                         relaunch = true;
                         continue;
                     }

@@ -51,7 +51,9 @@ def test_voxelwise_fluence_within_reference_spread(deck):
     z, ok = zscores(raw_field(p, r), g)
     # keep voxels where the reference spread is resolved (at least a few deposits per run)
     assert ok.mean() > 0.99
-    assert abs(np.mean(z)) < 0.05
+    # voxels crossed by the same packets are correlated, so the mean z of one run scatters by ~0.05-0.1 (the
+    # held-out reference run below shows the same)
+    assert abs(np.mean(z)) < 0.2
     assert 0.85 < np.std(z) < 1.25
     # Student-t with runs-1 = 11 degrees of freedom: P(|t|>3) = 1.2 %
     assert np.mean(np.abs(z) > 3) < 0.03
@@ -68,7 +70,7 @@ def test_voxelwise_heldout_reference_run_calibrates_the_test(ref):
     cfg["seed"] = int(g["seed0"]) + 100
     p, o = run_ref(ref, cfg, work=int(g["work"]))
     z, _ = zscores(o["field"], g)
-    assert abs(np.mean(z)) < 0.05 and 0.85 < np.std(z) < 1.25 and np.mean(np.abs(z) > 3) < 0.03
+    assert abs(np.mean(z)) < 0.2 and 0.85 < np.std(z) < 1.25 and np.mean(np.abs(z) > 3) < 0.03
 
 
 def test_detected_photons_cube60b():
@@ -234,7 +236,19 @@ def test_russian_roulette_matches_reference(ref):
     p, r = run_gpu(cfg)
     _, o = run_ref(ref, cfg)
     assert abs(r["absorbed"] - o["absorbed"]) < 0.012
-    np.testing.assert_allclose(raw_field(p, r).sum(), o["field"].astype(np.float64).sum(), rtol=0.03)
+    # compared as deposited ENERGY per medium (field * mua).  The raw field sum is not a usable statistic here: a
+    # packet that survives the roulette has its weight multiplied by 10 without w0 being touched (reference
+    # :3032-3034), so its next deposit is (w0 - 10 w)/mua < 0; when that happens inside the nearly transparent gel
+    # layer (mua = 1.8e-7 per voxel) ONE such event contributes -5e5 to a sum of 6.8e5, about once per 1e5 photons,
+    # in the reference and here alike.
+    lab = (p.keep["vol"] & 0x7FFFFFFF).ravel()
+    gf, of = raw_field(p, r), o["field"].astype(np.float64)
+    for m in (2, 3, 4):
+        mua = float(p.keep["prop"][m, 0])
+        np.testing.assert_allclose(gf[lab == m].sum() * mua, of[lab == m].sum() * mua, rtol=0.05)
+    tot_g = sum(gf[lab == m].sum() * float(p.keep["prop"][m, 0]) for m in (1, 2, 3, 4))
+    tot_o = sum(of[lab == m].sum() * float(p.keep["prop"][m, 0]) for m in (1, 2, 3, 4))
+    np.testing.assert_allclose(tot_g, tot_o, rtol=0.03)
 
 
 def test_gscatter_similarity_switch(ref):
@@ -247,12 +261,15 @@ def test_gscatter_similarity_switch(ref):
 
 def test_two_dimensional_domain(ref):
     """test/testmcx.sh:108-110: 1 x 100 x 100 domain"""
-    cfg = dict(nphoton=50000, vol=np.ones((1, 100, 100), np.uint8), prop=[[0, 0, 1, 1], [0.005, 1.0, 0.01, 1.37]],
-               tstart=0, tend=5e-9, tstep=5e-9, seed=1648335518, issrcfrom0=1, srcpos=[0.5, 50.0, 0.0], srcdir=[0, 0, 1],
-               isreflect=0, issavedet=0)
+    vol = np.ones((1, 100, 100), np.uint8)
+    vol[0, 30:70, 10:50] = 2                                      # Box Tag 2, O [0,30,10], Size [1,40,40]
+    cfg = dict(nphoton=100000, vol=vol, prop=[[0, 0, 1, 1], [0.02, 0.1, 0.9, 1.37], [0.02, 10, 0.9, 6.85]],
+               tstart=0, tend=5e-9, tstep=5e-9, seed=1648335518, issrcfrom0=1, srcpos=[0.0, 50.0, 0.0], srcdir=[0, 0, 1],
+               isreflect=1, issavedet=0)
     p, r = run_gpu(cfg)
     _, o = run_ref(ref, cfg)
     assert abs(r["absorbed"] - o["absorbed"]) < 0.012
+    assert ("%.1f" % (100 * o["absorbed"]))[0] == "6"               # the reference's pin: absorbed 6x.x%
     assert ("%.1f" % (100 * r["absorbed"]))[0] == "6"
 
 
@@ -365,7 +382,9 @@ def test_full_size_properties_cube60b_1e8():
     assert raw.sum() * mua == pytest.approx(r["energyabs"], rel=1e-4)
     v = raw.reshape(60, 60, 60)
     # the source sits at x=y=29 (voxel 29, lower edge): mirror images about the source column agree
-    left, right = v[:, :, 9:29].sum(), v[:, :, 30:50].sum()
+    # (voxel i <-> 57-i; columns 28/29 are skipped: the unscattered beam runs along the x=29.0 face and
+    # deposits in voxel 29 only)
+    left, right = v[:, :, 9:28].sum(), v[:, :, 30:49].sum()
     assert abs(left - right) / left < 3e-3
     # the hottest voxel holds ~1e8 deposits of order one: fp32 accumulation would have stalled near 2^25
     assert v[0, 29, 29] > 6e7
