@@ -168,11 +168,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("MCXB200_LIB", LIB_PATH)      # tuning experiments only (mcxcl_b200.build --variant)
+    if not os.path.exists(path):
         raise EngineMissing(
             "CUDA engine %s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(there is no CPU fallback)" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+            "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
     for name, restype, argtypes in SYMBOLS:
         fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = restype

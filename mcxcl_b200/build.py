@@ -46,32 +46,38 @@ def _run(job):
     return log
 
 
-def build(force=False, jobs=None, verbose=True):
-    stamp = os.path.join(OBJDIR, "build.stamp")
-    digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+def build(force=False, jobs=None, verbose=True, defines=(), variant=None):
+    """Build the engine.  `variant` + `defines` build an experimental copy (tuning knobs such as
+    -DMCXB_BLOCK=128 -DMCXB_MINBLOCKS=8) into build/variants/<variant>/libmcxb200.so; load it by setting
+    MCXB200_LIB (mcxcl_b200.abi).  The shipped library is always the default build."""
+    objdir = OBJDIR if variant is None else os.path.join(OBJDIR, "variants", variant)
+    lib = LIB if variant is None else os.path.join(objdir, "libmcxb200.so")
+    stamp = os.path.join(objdir, "build.stamp")
+    digest = _digest() + " " + " ".join(defines)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == digest:
         if verbose:
             print("mcxcl_b200.build: up to date")
-        return LIB
-    os.makedirs(OBJDIR, exist_ok=True)
+        return lib
+    os.makedirs(objdir, exist_ok=True)
+    flags = FLAGS + ["-D" + d for d in defines]
     work, objs = [], []
     for g in range(NGROUPS):
-        obj = os.path.join(OBJDIR, "kernels_g%d.o" % g)
-        work.append(([NVCC] + FLAGS + ["-DMCXB_INST_GROUP=%d" % g, "-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", obj],
-                     os.path.join(OBJDIR, "kernels_g%d.log" % g)))
+        obj = os.path.join(objdir, "kernels_g%d.o" % g)
+        work.append(([NVCC] + flags + ["-DMCXB_INST_GROUP=%d" % g, "-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", obj],
+                     os.path.join(objdir, "kernels_g%d.log" % g)))
         objs.append(obj)
     for name in ("engine", "testhooks"):
-        obj = os.path.join(OBJDIR, name + ".o")
-        work.append(([NVCC] + FLAGS + ["-c", os.path.join(CSRC, name + ".cu"), "-o", obj], os.path.join(OBJDIR, name + ".log")))
+        obj = os.path.join(objdir, name + ".o")
+        work.append(([NVCC] + flags + ["-c", os.path.join(CSRC, name + ".cu"), "-o", obj], os.path.join(objdir, name + ".log")))
         objs.append(obj)
     with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as ex:
         list(ex.map(_run, work))
-    _run(([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"], os.path.join(OBJDIR, "link.log")))
+    _run(([NVCC, "-shared", "-o", lib] + objs + ["-lcudart"], os.path.join(objdir, "link.log")))
     with open(stamp, "w") as f:
         f.write(digest)
     if verbose:
-        print("mcxcl_b200.build: built", LIB)
-    return LIB
+        print("mcxcl_b200.build: built", lib)
+    return lib
 
 
 def ptxas_summary():
@@ -95,5 +101,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--jobs", type=int, default=None)
+    ap.add_argument("--variant", default=None)
+    ap.add_argument("-D", dest="defines", action="append", default=[])
     a = ap.parse_args()
-    build(force=a.force, jobs=a.jobs)
+    build(force=a.force, jobs=a.jobs, defines=tuple(a.defines), variant=a.variant)

@@ -177,7 +177,7 @@ extern "C" int mcxb_list_gpu(mcxb_gpuinfo* info, int maxinfo) {
         g->core = p.multiProcessorCount * cores_per_sm(p.major, p.minor);
         g->maxmpthread = p.maxThreadsPerMultiProcessor;
         g->autoblock = kBlock;
-        g->autothread = (uint64_t)kBlock * 3 * p.multiProcessorCount;
+        g->autothread = (uint64_t)kBlock * MCXB_MINBLOCKS * p.multiProcessorCount;
         g->l2cache = (uint64_t)p.l2CacheSize;
     }
 
