@@ -27,6 +27,10 @@ DECKS = {
     "cube60b": (dict(name="cube60b"), 200000, 4096, 12),
     # 200^3 volume: statistics are kept on 8x8x8-voxel blocks (25^3 bins) to keep the fixture small
     "skinvessel": (dict(name="skinvessel", bin=8), 20000, 2048, 8),
+    # the two atlases (no pins in the reference's own tests: the reference series IS the pin); dimensions are
+    # zero-padded up to a multiple of the block size before binning
+    "colin27": (dict(name="colin27", bin=8), 100000, 4096, 8),
+    "digimouse": (dict(name="digimouse", bin=8), 100000, 4096, 8),
 }
 SEED0 = 1648335518
 
@@ -35,7 +39,10 @@ def bin_field(field, dims, b):
     """sum an x-fastest flat volume over b x b x b blocks"""
     nx, ny, nz = dims
     v = field.reshape(nz, ny, nx)
-    return v.reshape(nz // b, b, ny // b, b, nx // b, b).sum(axis=(1, 3, 5)).ravel()
+    pz, py, px = (-nz) % b, (-ny) % b, (-nx) % b
+    if pz or py or px:
+        v = np.pad(v, ((0, pz), (0, py), (0, px)))
+    return v.reshape((nz + pz) // b, b, (ny + py) // b, b, (nx + px) // b, b).sum(axis=(1, 3, 5)).ravel()
 
 
 def main():
@@ -45,7 +52,7 @@ def main():
         if only and key not in only:
             continue
         cfg = benchmarks.get(kw["name"], nph)
-        fields, absorbed, detected, seg, dep, sca = [], [], [], [], [], []
+        fields, absorbed, detected, seg, dep, sca, etot = [], [], [], [], [], [], []
         for r in range(runs):
             cfg["seed"] = SEED0 + r
             p = hostcfg.prepare(cfg)
@@ -56,6 +63,7 @@ def main():
             fields.append(fld)
             absorbed.append(o["absorbed"])
             detected.append(o["detected"])
+            etot.append(o["energytot"])
             seg.append(o["n_segment"] / nph)
             dep.append(o["n_deposit"] / nph)
             sca.append(o["n_scatter"] / nph)
@@ -66,7 +74,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, "ref_stats_%s.npz" % key),
                             idx=keep.astype(np.uint32), mean=mean[keep].astype(np.float32), std=std[keep].astype(np.float32),
                             total=f.sum(1), absorbed=np.array(absorbed), detected=np.array(detected),
-                            seg=np.array(seg), dep=np.array(dep), sca=np.array(sca),
+                            seg=np.array(seg), dep=np.array(dep), sca=np.array(sca), energytot=np.array(etot),
                             nphoton=nph, work=work, runs=runs, seed0=SEED0, bin=kw.get("bin", 1))
         print(key, "voxels kept", keep.size, "absorbed", np.mean(absorbed), "+-", np.std(absorbed, ddof=1))
 

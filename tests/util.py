@@ -73,4 +73,7 @@ def zscores(field_raw, golden, scale=1.0):
 def bin_field(field, dims, b):
     nx, ny, nz = dims
     v = np.asarray(field, dtype=np.float64).reshape(nz, ny, nx)
-    return v.reshape(nz // b, b, ny // b, b, nx // b, b).sum(axis=(1, 3, 5)).ravel()
+    pz, py, px = (-nz) % b, (-ny) % b, (-nx) % b
+    if pz or py or px:
+        v = np.pad(v, ((0, pz), (0, py), (0, px)))
+    return v.reshape((nz + pz) // b, b, (ny + py) // b, b, (nx + px) // b, b).sum(axis=(1, 3, 5)).ravel()
