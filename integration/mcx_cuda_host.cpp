@@ -1,0 +1,472 @@
+/*
+ * mcx_cuda_host.cpp -- the reference-side binding: exports the reference's own boundary symbols
+ *
+ *     void           mcx_run_simulation(Config* cfg, float* fluence, float* totalenergy);
+ *     cl_platform_id mcx_list_gpu(Config* cfg, unsigned int* activedev, cl_device_id* activedevlist, GPUInfo** info);
+ *     void           ocl_assess(int err, const char* file, const int linenum);
+ *
+ * (reference src/mcx_host.h:168-170) on top of the C ABI of include/mcxb200.h, so that the reference's
+ * unchanged front-ends (src/mcxcl.c:35, src/pmcxcl.cpp:1147/1244/1609, src/mcxlabcl.cpp:139/264/345) and
+ * its unchanged configuration / output code (src/mcx_utils.c) link against the B200 engine instead of
+ * src/mcx_host.cpp + libOpenCL.  This file replaces src/mcx_host.cpp for the photon-transport path;
+ * it is compiled against the reference's own headers where they lie (integration/build_cli.py), with
+ * integration/clstub/CL/cl.h standing in for the OpenCL SDK header.
+ *
+ * Contract kept from the reference:
+ *   inputs   everything is read from Config AFTER mcx_preprocess/mcx_validatecfg ran (the front-ends call
+ *            them before reaching the boundary);
+ *   outputs  cfg->exportfield (calloc'd if NULL, accumulated with +=, then normalised in place:
+ *            src/mcx_host.cpp:1048-1054, 1292-1296, 1382-1465), cfg->exportdetected / seeddata (malloc /
+ *            realloc: :1056-1058, 1218-1232), detectedcount, energytot/esc/abs, runtime, normalizer,
+ *            his.*, maxgate; files through mcx_savedata / mcx_savedetphoton when parentid == mpStandalone
+ *            (:1646-1664); the "simulated ... photon/ms" and "absorbed: ...%" report lines (:1677-1693);
+ *   errors   mcx_error(id, msg, file, line): exit(id) standalone, exception under Python/MATLAB;
+ *   devices  cfg->deviceid[] '1' flags select CUDA devices, cfg->workload[] weights split the photons
+ *            (:650-662, 1011-1012); every device gets the next slice of ONE rand() stream (:759-768).
+ *
+ * Several selected GPUs are driven from this one host thread, like the reference drives several OpenCL
+ * devices: the kernels are enqueued on all devices first and collected afterwards; results are summed on
+ * the host.  (The one-process-per-GPU NCCL path lives in mcxcl_b200/multigpu.py.)
+ */
+#include "mcx_host.h"
+#include "mcx_tictoc.h"
+#include "mcx_const.h"
+#include "mcxb200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+namespace {
+
+const char* const kEngineName = "B200-native CUDA engine (libmcxb200)";
+
+void raise(int code, const char* file, int line) {
+    const char* msg = mcxb_last_error();
+    /* same convention as ocl_assess (src/mcx_host.cpp:213-217): the id handed to mcx_error is positive */
+    mcx_error(code < 0 ? -code : code, (msg && msg[0]) ? msg : "CUDA engine error", file, line);
+}
+
+#define MCXB_TRY(call)                          \
+    do {                                        \
+        int rc__ = (call);                      \
+        if (rc__ != MCXB_OK) {                  \
+            raise(rc__, __FILE__, __LINE__);    \
+        }                                       \
+    } while (0)
+
+mcxb_f4 f4(const float4& v) {
+    mcxb_f4 r = {v.x, v.y, v.z, v.w};
+    return r;
+}
+
+/* Config -> mcxb_config: field-by-field, no arithmetic (the reference's preprocessing already ran) */
+void fill_config(const Config* cfg, mcxb_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->abi_version = MCXB_ABI_VERSION;
+    c->dimx = cfg->dim.x;
+    c->dimy = cfg->dim.y;
+    c->dimz = cfg->dim.z;
+    c->vol = cfg->vol;
+    c->unitinmm = cfg->unitinmm;
+    c->medianum = cfg->medianum;
+    c->prop = reinterpret_cast<const mcxb_f4*>(cfg->prop);          /* Medium {mua,mus,g,n}, 16 bytes */
+    c->srctype = cfg->srctype;
+    c->src.pos = f4(cfg->srcpos);
+    c->src.dir = f4(cfg->srcdir);
+    c->src.param1 = f4(cfg->srcparam1);
+    c->src.param2 = f4(cfg->srcparam2);
+    c->extrasrclen = cfg->extrasrclen;
+    c->srcdata = reinterpret_cast<const mcxb_source*>(cfg->srcdata);   /* ExtraSrc == 4 x float4 */
+    c->srcid = cfg->srcid;
+    c->srcnum = cfg->srcnum;
+    c->srcpattern = cfg->srcpattern;
+
+    if (cfg->srcpattern) {
+        if (cfg->srctype == MCX_SRC_PATTERN3D) {
+            c->srcpattern_len = (uint64_t)cfg->srcparam1.x * (uint64_t)cfg->srcparam1.y * (uint64_t)cfg->srcparam1.z * cfg->srcnum;
+        } else {
+            c->srcpattern_len = (uint64_t)cfg->srcparam1.w * (uint64_t)cfg->srcparam2.w * cfg->srcnum;
+        }
+    }
+
+    c->nphase = cfg->nphase;
+    c->nangle = cfg->nangle;
+    c->invcdf = cfg->invcdf;
+    c->angleinvcdf = cfg->angleinvcdf;
+    c->detnum = cfg->detnum;
+    c->detpos = reinterpret_cast<const mcxb_f4*>(cfg->detpos);
+    c->issavedet = cfg->issavedet;
+    c->savedetflag = cfg->savedetflag;
+    c->maxdetphoton = cfg->maxdetphoton;
+    c->issaveseed = cfg->issaveseed;
+    c->issaveref = cfg->issaveref;
+    c->tstart = cfg->tstart;
+    c->tstep = cfg->tstep;
+    c->tend = cfg->tend;
+    c->nphoton = cfg->nphoton;
+    c->seed = cfg->seed;
+    c->isreflect = cfg->isreflect;
+    memcpy(c->bc, cfg->bc, 12);
+    c->isspecular = cfg->isspecular;
+    c->minenergy = cfg->minenergy;
+    c->gscatter = cfg->gscatter;
+    c->maxvoidstep = cfg->maxvoidstep;
+    c->voidtime = cfg->voidtime;
+    c->outputtype = cfg->outputtype;
+    c->isnormalized = 0;               /* normalised once, after every device has been summed */
+    c->issave2pt = cfg->issave2pt;
+    c->debuglevel = cfg->debuglevel & MCX_DEBUG_RNG;
+    c->nthread = cfg->autopilot ? 0 : cfg->nthread;
+    c->nblocksize = cfg->autopilot ? 0 : cfg->nblocksize;
+    c->sched = MCXB_SCHED_DYNAMIC;
+    c->accum = MCXB_ACCUM_F64;
+}
+
+/* what this build's hot path does not cover is refused loudly, never approximated */
+void check_supported(const Config* cfg) {
+    if (cfg->mediabyte > 4) {
+        mcx_error(-1, "continuous / SVMC media formats are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
+    }
+
+    if (cfg->seed == SEED_FROM_FILE) {
+        mcx_error(-1, "photon replay is outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
+    }
+
+    if (cfg->respin != 1) {
+        mcx_error(-1, "respin != 1 is not supported by the CUDA engine", __FILE__, __LINE__);
+    }
+
+    if (cfg->polmedianum || cfg->omega > 0.f || (cfg->debuglevel & (MCX_DEBUG_MOVE | MCX_DEBUG_MOVE_ONLY))) {
+        mcx_error(-1, "polarised, RF and trajectory-saving modes are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
+    }
+}
+
+}  // namespace
+
+extern "C" void ocl_assess(int err, const char* file, const int linenum) {
+    if (err != 0) {
+        mcx_error(-err, "CUDA engine error", file, linenum);
+    }
+}
+
+extern "C" cl_platform_id mcx_list_gpu(Config* cfg, unsigned int* activedev, cl_device_id* activedevlist, GPUInfo** info) {
+    mcxb_gpuinfo dev[MAX_DEVICE];
+    const int n = mcxb_list_gpu(dev, MAX_DEVICE);
+
+    if (n < 0) {
+        raise(n, __FILE__, __LINE__);
+    }
+
+    if (activedev) {
+        *activedev = 0;
+    }
+
+    *info = (GPUInfo*)calloc(MAX_DEVICE, sizeof(GPUInfo));
+    unsigned int active = 0;
+
+    if (cfg->isgpuinfo && n > 0) {
+        MCX_FPRINTF(stdout, S_YELLOW "Platform [0] Name %s\n" S_RESET, kEngineName);
+    }
+
+    for (int i = 0; i < n && i < MAX_DEVICE; i++) {
+        GPUInfo g;
+        memset(&g, 0, sizeof(g));
+        strncpy(g.name, dev[i].name, sizeof(g.name) - 1);
+        g.id = i + 1;
+        g.devcount = n;
+        g.platformid = 0;
+        g.major = dev[i].major;
+        g.minor = dev[i].minor;
+        g.globalmem = dev[i].globalmem;
+        g.constmem = dev[i].constmem;
+        g.sharedmem = dev[i].sharedmem;
+        g.regcount = dev[i].regcount;
+        g.clock = dev[i].clock_khz / 1000;       /* the reference reports MHz (CL_DEVICE_MAX_CLOCK_FREQUENCY) */
+        g.sm = dev[i].sm;
+        g.core = dev[i].core;
+        g.autoblock = dev[i].autoblock;
+        g.autothread = dev[i].autothread;
+        g.maxgate = cfg->maxgate;
+        g.maxmpthread = dev[i].maxmpthread;
+        g.iscpu = 0;
+        g.vendor = dvNVIDIA;
+
+        if (cfg->isgpuinfo) {
+            MCX_FPRINTF(stdout, S_BLUE "============ GPU device ID %d [%d of %d]: %s  ============\n" S_RESET, i, i + 1, n, g.name);
+            MCX_FPRINTF(stdout, " Device %d of %d:\t\t%s\n", i + 1, n, g.name);
+            MCX_FPRINTF(stdout, " Compute units   :\t%d core(s)\n", g.sm);
+            MCX_FPRINTF(stdout, " Global memory   :\t%.0f B\n", (double)g.globalmem);
+            MCX_FPRINTF(stdout, " Local memory    :\t%.0f B\n", (double)g.sharedmem);
+            MCX_FPRINTF(stdout, " Constant memory :\t%.0f B\n", (double)g.constmem);
+            MCX_FPRINTF(stdout, " Clock speed     :\t%d MHz\n", g.clock);
+            MCX_FPRINTF(stdout, " Compute Capacity:\t%d.%d\n", g.major, g.minor);
+            MCX_FPRINTF(stdout, " Stream Processor:\t%d\n", g.core);
+            MCX_FPRINTF(stdout, " Vendor name    :\t%s\n", "NVIDIA");
+            MCX_FPRINTF(stdout, " Auto-thread    :\t%zu\n", g.autothread);
+            MCX_FPRINTF(stdout, " Auto-block     :\t%zu\n", g.autoblock);
+        }
+
+        if (activedevlist != NULL) {
+            if (cfg->deviceid[i] == '1') {
+                memcpy((*info) + active, &g, sizeof(GPUInfo));
+                activedevlist[active++] = (cl_device_id)(intptr_t)(i + 1);
+            }
+        } else {
+            memcpy((*info) + active, &g, sizeof(GPUInfo));
+            active++;
+        }
+    }
+
+    if (activedev) {
+        *activedev = active;
+    }
+
+    *info = (GPUInfo*)realloc(*info, std::max(1u, active) * sizeof(GPUInfo));
+
+    if (cfg->isgpuinfo == 2 && cfg->parentid == mpStandalone) {
+        exit(0);
+    }
+
+    return active ? (cl_platform_id)(intptr_t)1 : NULL;
+}
+
+extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalenergy) {
+    (void)fluence;        /* never referenced by the reference either (callers pass NULL, src/mcxlabcl.cpp:345) */
+    (void)totalenergy;
+
+    cl_device_id devices[MAX_DEVICE];
+    unsigned int workdev = 0;
+    GPUInfo* gpu = NULL;
+    mcx_list_gpu(cfg, &workdev, devices, &gpu);
+
+    if (workdev == 0) {
+        free(gpu);
+        mcx_error(-99, "Specified GPU does not exist", __FILE__, __LINE__);
+    }
+
+    check_supported(cfg);
+
+    cfg->maxgate = (unsigned int)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);
+    const size_t dimxyz = (size_t)cfg->dim.x * cfg->dim.y * cfg->dim.z;
+    const unsigned int nsrcvol = (cfg->extrasrclen && cfg->srcid < 0) ? cfg->extrasrclen + 1 : 1;
+    const size_t fieldlen = dimxyz * cfg->maxgate * nsrcvol;
+
+    /* workload split (src/mcx_host.cpp:650-662, 1011-1012); the remainder goes to the first devices so
+     * that exactly nphoton packets are launched */
+    float fullload = 0.f;
+
+    for (unsigned int i = 0; i < workdev; i++) {
+        fullload += cfg->workload[i];
+    }
+
+    if (fullload < EPS) {
+        for (unsigned int i = 0; i < workdev; i++) {
+            cfg->workload[i] = (float)gpu[i].core;
+            fullload += cfg->workload[i];
+        }
+    }
+
+    std::vector<uint64_t> share(workdev);
+    uint64_t assigned = 0;
+
+    for (unsigned int i = 0; i < workdev; i++) {
+        share[i] = (uint64_t)((double)cfg->nphoton * cfg->workload[i] / fullload);
+        assigned += share[i];
+    }
+
+    for (unsigned int i = 0; assigned < cfg->nphoton; i = (i + 1) % workdev) {
+        if (cfg->workload[i] > 0.f) {
+            share[i]++;
+            assigned++;
+        }
+    }
+
+    /* ---- create one resident simulation per device; seed slices follow each other in ONE stream ---- */
+    std::vector<mcxb_sim*> sims(workdev, (mcxb_sim*)NULL);
+    uint64_t seedskip = 0;
+    int rc = MCXB_OK;
+
+    for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+        mcxb_config c;
+        fill_config(cfg, &c);
+        c.nphoton = share[i];
+        c.seed_skip = seedskip;
+        rc = mcxb_sim_create(&c, (int)(intptr_t)devices[i] - 1, &sims[i]);
+
+        if (rc == MCXB_OK) {
+            seedskip += mcxb_sim_nthread(sims[i]);
+            rc = mcxb_sim_reset(sims[i], NULL);
+        }
+    }
+
+    if (rc == MCXB_OK) {
+        if (cfg->exportfield == NULL && cfg->issave2pt) {
+            cfg->exportfield = (float*)calloc(fieldlen, sizeof(float));
+        }
+
+        const unsigned int reclen = mcxb_sim_reclen(sims[0]);
+
+        if (cfg->issavedet && cfg->exportdetected == NULL) {
+            cfg->exportdetected = (float*)malloc(std::max<size_t>(1, (size_t)reclen * cfg->maxdetphoton) * sizeof(float));
+        }
+
+        if (cfg->issavedet && cfg->issaveseed && cfg->seeddata == NULL) {
+            cfg->seeddata = malloc(std::max<size_t>(1, (size_t)cfg->maxdetphoton) * 16);
+        }
+
+        cfg->his.colcount = reclen;
+        cfg->his.maxmedia = cfg->medianum - 1;
+        cfg->his.detnum = cfg->detnum;
+        cfg->his.srcnum = cfg->srcnum;
+        cfg->his.savedetflag = cfg->savedetflag;
+        cfg->his.totalsource = cfg->extrasrclen + 1;
+        cfg->his.detected = 0;
+        cfg->his.respin = 1;
+        cfg->detectedcount = 0;
+        cfg->energytot = cfg->energyesc = cfg->energyabs = 0.0;
+        cfg->runtime = 0;
+
+        mcx_printheader(cfg);
+        MCX_FPRINTF(cfg->flog, "- code name: [%s] compiled for sm_100a\n", kEngineName);
+        MCX_FPRINTF(cfg->flog, "- RNG: %s, photon scheduling: persistent threads with a per-GPU photon counter\n", MCX_RNG_NAME);
+        MCX_FPRINTF(cfg->flog, "initializing streams ...\t");
+        mcx_flush(cfg);
+
+        /* ---- the reference's timing window: first enqueue ... all devices finished (:1078-1168) ---- */
+        const unsigned int tic0 = GetTimeMillis();
+        MCX_FPRINTF(cfg->flog, "lauching mcx_main_loop for time window [%.1fns %.1fns] ...\n", cfg->tstart * 1e9, cfg->tend * 1e9);
+
+        for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+            MCX_FPRINTF(cfg->flog, "- [device %d(%d): %s] threadph=%d extra=%d np=%.1f nthread=%u nblock=%d repetition=%d\n",
+                        i, gpu[i].id, gpu[i].name, (int)(share[i] / mcxb_sim_nthread(sims[i])), (int)(share[i] % mcxb_sim_nthread(sims[i])),
+                        (double)share[i], mcxb_sim_nthread(sims[i]), (int)gpu[i].autoblock, 1);
+            rc = mcxb_sim_launch(sims[i], NULL);
+        }
+
+        float kernelms = 0.f;
+
+        for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+            kernelms = std::max(kernelms, mcxb_sim_last_kernel_ms(sims[i]));     /* waits for device i */
+        }
+
+        const unsigned int toc = GetTimeMillis() - tic0;
+        cfg->runtime = std::max(1u, std::max(toc, (unsigned int)(kernelms + 0.5f)));
+        MCX_FPRINTF(cfg->flog, "kernel complete:  \t%d ms\nretrieving flux ... \t", toc);
+        mcx_flush(cfg);
+
+        /* ---- read back, sum over devices (:1172-1306) ---- */
+        std::vector<float> detbuf;
+        std::vector<uint64_t> seedbuf;
+
+        for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+            mcxb_output out;
+            memset(&out, 0, sizeof(out));
+            out.field = cfg->issave2pt ? cfg->exportfield : NULL;      /* accumulated with += by the engine */
+            out.fieldlen = fieldlen;
+
+            if (cfg->issavedet) {
+                detbuf.resize(std::max<size_t>(1, (size_t)reclen * cfg->maxdetphoton));
+                out.detphoton = detbuf.data();
+
+                if (cfg->issaveseed) {
+                    seedbuf.resize(std::max<size_t>(1, (size_t)cfg->maxdetphoton * 2));
+                    out.seeddata = seedbuf.data();
+                }
+            }
+
+            rc = mcxb_sim_fetch(sims[i], NULL, &out);
+
+            if (rc != MCXB_OK) {
+                break;
+            }
+
+            if (cfg->issavedet) {
+                if (out.detected > cfg->maxdetphoton) {
+                    MCX_FPRINTF(cfg->flog, S_RED "WARNING: the detected photon number is more than what your have specified (%u > %d), please use the -H option to specify a greater number\t" S_RESET,
+                                out.detected, cfg->maxdetphoton);
+                } else {
+                    MCX_FPRINTF(cfg->flog, "detected " S_BOLD S_BLUE "%d photons" S_RESET ", total: " S_BOLD S_BLUE "%d" S_RESET "\t", out.detected, cfg->detectedcount + out.detected);
+                }
+
+                cfg->his.detected += out.detected;
+
+                if (cfg->exportdetected && out.saved) {
+                    cfg->exportdetected = (float*)realloc(cfg->exportdetected, (size_t)(cfg->detectedcount + out.saved) * reclen * sizeof(float));
+                    memcpy(cfg->exportdetected + (size_t)cfg->detectedcount * reclen, detbuf.data(), (size_t)out.saved * reclen * sizeof(float));
+
+                    if (cfg->issaveseed && cfg->seeddata) {
+                        cfg->seeddata = realloc(cfg->seeddata, (size_t)(cfg->detectedcount + out.saved) * 16);
+                        memcpy((char*)cfg->seeddata + (size_t)cfg->detectedcount * 16, seedbuf.data(), (size_t)out.saved * 16);
+                    }
+
+                    cfg->detectedcount += out.saved;
+                }
+            }
+
+            cfg->energytot += out.energytot;
+            cfg->energyesc += out.energyesc;
+        }
+
+        MCX_FPRINTF(cfg->flog, "transfer complete:        %d ms\n", GetTimeMillis() - tic0);
+        mcx_flush(cfg);
+    }
+
+    for (unsigned int i = 0; i < workdev; i++) {
+        mcxb_sim_destroy(sims[i]);      /* full teardown before any error is raised (:35-49, 1846-1848) */
+    }
+
+    if (rc != MCXB_OK) {
+        free(gpu);
+        raise(rc, __FILE__, __LINE__);
+        return;
+    }
+
+    /* ---- normalise once with the global launched energy (:1382-1465) ---- */
+    if (cfg->issave2pt && cfg->isnormalized && !(cfg->debuglevel & MCX_DEBUG_RNG) && cfg->energytot > 0.0) {
+        mcxb_config c;
+        fill_config(cfg, &c);
+        MCX_FPRINTF(cfg->flog, "normalizing raw data ...\t");
+        cfg->energyabs += cfg->energytot - cfg->energyesc;
+        const float scale = mcxb_normalizer(&c, cfg->energytot);
+        cfg->normalizer = scale;
+        cfg->his.normalizer = scale;
+        MCX_FPRINTF(cfg->flog, "source 1, normalization factor alpha=%f\n", scale);
+        mcx_normalize(cfg->exportfield, scale, (int)fieldlen, cfg->isnormalized, 0, 1);
+    } else {
+        cfg->energyabs += cfg->energytot - cfg->energyesc;
+    }
+
+#ifndef MCX_CONTAINER
+
+    if (cfg->issave2pt && cfg->parentid == mpStandalone) {
+        MCX_FPRINTF(cfg->flog, "saving data to file ... %zu %d\t", fieldlen, cfg->maxgate);
+        mcx_savedata(cfg->exportfield, fieldlen, cfg);
+        MCX_FPRINTF(cfg->flog, "saving data complete\n\n");
+        mcx_flush(cfg);
+    }
+
+    if (cfg->issavedet && cfg->parentid == mpStandalone && cfg->exportdetected) {
+        cfg->his.unitinmm = cfg->unitinmm;
+        cfg->his.savedphoton = cfg->detectedcount;
+        cfg->his.totalphoton = cfg->nphoton;
+
+        if (cfg->issaveseed) {
+            cfg->his.seedbyte = 16;
+        }
+
+        cfg->his.detected = cfg->detectedcount;
+        mcx_savedetphoton(cfg->exportdetected, cfg->seeddata, cfg->detectedcount, 0, cfg);
+    }
+
+#endif
+
+    MCX_FPRINTF(cfg->flog, "simulated %zu photons (%zu) with %d devices (repeat x%d)\nMCX simulation speed: " S_BOLD S_BLUE "%.2f photon/ms" S_RESET "\n",
+                cfg->nphoton, cfg->nphoton, workdev, cfg->respin, (double)cfg->nphoton / std::max(1u, cfg->runtime));
+    MCX_FPRINTF(cfg->flog, "total simulated energy: %.2f\tabsorbed: " S_BOLD S_BLUE "%5.5f%%" S_RESET "\n(loss due to initial specular reflection is excluded in the total)\n",
+                cfg->energytot, (cfg->energytot - cfg->energyesc) / cfg->energytot * 100.f);
+    mcx_flush(cfg);
+    free(gpu);
+}
