@@ -55,39 +55,66 @@ def _as_tensor(ptr, shape, typestr, device):
     return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
 
 
-def combine(sim, dist, rank, world, device):
-    """the collective step; returns (gathered detected records on rank 0 or None, per-rank counts)"""
+def combine_tensors(dist, rank, world, field, energy, detcount, records, reclen, maxdetphoton, seeds=None):
+    """The collective step on plain torch tensors (CUDA tensors over NCCL in production, CPU tensors over gloo
+    in tests/test_multigpu_host.py):
+
+        field    float32[fieldlen]   raw deposits of this rank          -> summed in place on rank 0
+        energy   float64[2]          {escaped, launched}                -> summed in place on rank 0
+        detcount int                 photons this rank detected (may exceed maxdetphoton)
+        records  float32[>= stored*reclen]  this rank's detected-photon records
+        seeds    int64[>= stored*2] or None  RNG states of the detected photons (issaveseed)
+
+    Returns (records on rank 0 or None, seeds on rank 0 or None, per-rank detected counts)."""
     import torch
+    dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
+    dist.reduce(energy, dst=0, op=dist.ReduceOp.SUM)
+    if records is None:
+        return None, None, [0] * world
+    mine = torch.tensor([int(detcount)], dtype=torch.int64, device=field.device)
+    gathered = [torch.zeros(1, dtype=torch.int64, device=field.device) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    counts = [int(x.item()) for x in gathered]
+    reclen = max(1, int(reclen))
+    stored = [min(x, int(maxdetphoton)) for x in counts]
+    offs, lens, total = gather_plan(stored, maxdetphoton)
+    ops, out, out_seeds = [], None, None
+    if rank == 0:
+        out = torch.empty(total * reclen, dtype=torch.float32, device=field.device)
+        out[:lens[0] * reclen] = records[:lens[0] * reclen]
+        if seeds is not None:
+            out_seeds = torch.empty(total * 2, dtype=torch.int64, device=field.device)
+            out_seeds[:lens[0] * 2] = seeds[:lens[0] * 2]
+        for r in range(1, world):
+            if lens[r]:
+                ops.append(dist.P2POp(dist.irecv, out[offs[r] * reclen:(offs[r] + lens[r]) * reclen], r))
+                if seeds is not None:
+                    ops.append(dist.P2POp(dist.irecv, out_seeds[offs[r] * 2:(offs[r] + lens[r]) * 2], r))
+    elif lens[rank]:
+        ops.append(dist.P2POp(dist.isend, records[:lens[rank] * reclen].contiguous(), 0))
+        if seeds is not None:
+            ops.append(dist.P2POp(dist.isend, seeds[:lens[rank] * 2].contiguous(), 0))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out, out_seeds, counts
+
+
+def combine(sim, dist, rank, world, device):
+    """finalize this rank's accumulators and run the collective step on the engine's device buffers (zero copy);
+    returns (gathered detected records on rank 0 or None, gathered seeds or None, per-rank counts)"""
     sim.finalize()
     ptr = sim.devptrs()
     field = _as_tensor(ptr["field"], (sim.fieldlen,), "<f4", device)
     energy = _as_tensor(ptr["energy"], (2,), "<f8", device)
-    dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
-    dist.reduce(energy, dst=0, op=dist.ReduceOp.SUM)
     c = sim.p.c
     if not (c.issavedet and ptr["detphoton"]):
-        return None, [0] * world
-    mine = _as_tensor(ptr["detcount"], (1,), "<i4", device).to(torch.int64)
-    counts = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(counts, mine)
-    counts = [int(x) for x in counts.cpu()]
+        return combine_tensors(dist, rank, world, field, energy, 0, None, 0, 0)
     reclen = max(1, sim.reclen)
-    stored = [min(x, c.maxdetphoton) for x in counts]
-    offs, lens, total = gather_plan(stored, c.maxdetphoton)
+    mine = int(_as_tensor(ptr["detcount"], (1,), "<i4", device).item())
     local = _as_tensor(ptr["detphoton"], (c.maxdetphoton * reclen,), "<f4", device)
-    ops, out = [], None
-    if rank == 0:
-        out = torch.empty(total * reclen, dtype=torch.float32, device=device)
-        out[:lens[0] * reclen] = local[:lens[0] * reclen]
-        for r in range(1, world):
-            if lens[r]:
-                ops.append(dist.P2POp(dist.irecv, out[offs[r] * reclen:(offs[r] + lens[r]) * reclen], r))
-    elif lens[rank]:
-        ops.append(dist.P2POp(dist.isend, local[:lens[rank] * reclen], 0))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    return out, counts
+    seeds = _as_tensor(ptr["seeddata"], (c.maxdetphoton * 2,), "<i8", device) if (c.issaveseed and ptr["seeddata"]) else None
+    return combine_tensors(dist, rank, world, field, energy, mine, local, reclen, c.maxdetphoton, seeds)
 
 
 def run_distributed(cfg, workload=None):
@@ -103,7 +130,7 @@ def run_distributed(cfg, workload=None):
         sim.reseed(p.c.seed, rank * sim.nthread)
         sim.reset()
         sim.launch()
-        detp, counts = combine(sim, dist, rank, world, device)
+        detp, seeds, counts = combine(sim, dist, rank, world, device)
         if rank != 0:
             torch.cuda.synchronize()
             return None
@@ -112,6 +139,8 @@ def run_distributed(cfg, workload=None):
             res["detp"] = detp.cpu().numpy().reshape(-1, max(1, sim.reclen))
             res["detected"] = int(sum(counts))
             res["saved"] = res["detp"].shape[0]
+            if seeds is not None:
+                res["seeds"] = seeds.cpu().numpy().view(np.uint64).reshape(-1, 2)
         res["nphoton"] = int(cfg["nphoton"])
         res["shares"] = shares
         res["flux"] = engine.shape_field(p, res["field"])

@@ -88,7 +88,7 @@ def test_mc2_and_mch_files_match_the_engine(tmp_path):
     r = engine.run(benchmarks.get("cube60b", n))
     # same deck, same seed, same scheduler: the two runs are statistically equivalent (dynamic scheduling is not
     # stream-reproducible), compare integrals and the depth profile
-    a, b = mc2.astype(np.float64).reshape(60, 60, 60), r["flux"].astype(np.float64).transpose(2, 1, 0)
+    a, b = mc2.astype(np.float64).reshape(60, 60, 60), r["flux"][..., 0].astype(np.float64).transpose(2, 1, 0)
     np.testing.assert_allclose(a.sum(), b.sum(), rtol=0.01)
     np.testing.assert_allclose(a.sum(axis=(1, 2))[:30], b.sum(axis=(1, 2))[:30], rtol=0.05)
     raw = open(os.path.join(tmp_path, "cli60b.mch"), "rb").read()
