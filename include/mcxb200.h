@@ -196,6 +196,11 @@ int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_output* out);
 /* last error message of the calling thread ("" if none) */
 const char* mcxb_last_error(void);
 
+/* Device and pinned buffers of finished simulations are kept per size and reused by the next call (front-ends
+ * call mcx_run_simulation in loops; cudaFree / cudaFreeHost cost more than the rest of the host work).  This
+ * returns every cached buffer to the driver, e.g. before handing the GPU to another library. */
+void mcxb_release_cached_buffers(void);
+
 /* ---- staged API: the same path with inputs resident in HBM (bench `value`, multi-GPU plumbing) */
 typedef struct mcxb_sim mcxb_sim;
 

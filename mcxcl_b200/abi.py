@@ -126,6 +126,7 @@ SYMBOLS = [
     ("mcxb_list_gpu", C.c_int, [C.POINTER(GPUInfo), C.c_int]),
     ("mcxb_run_simulation", C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(Output)]),
     ("mcxb_last_error", C.c_char_p, []),
+    ("mcxb_release_cached_buffers", None, []),
     ("mcxb_sim_create", C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(_VP)]),
     ("mcxb_sim_reset", C.c_int, [_VP, _VP]),
     ("mcxb_sim_launch", C.c_int, [_VP, _VP]),

@@ -21,6 +21,8 @@
 #include <ctime>
 #include <string>
 #include <vector>
+#include <map>
+#include <mutex>
 #include <algorithm>
 
 using namespace mcxb;
@@ -107,6 +109,116 @@ extern "C" void mcxb_fill_seeds(int32_t seed, uint64_t skip_records, uint64_t nr
     for (uint64_t i = 0; i < nrecords * 4; i++) {
         out4[i] = g.next();
     }
+}
+
+/* -------------------------------------------------------------------------------------------------
+ * Buffer pool.  cudaFree / cudaFreeHost synchronise the device and unpin pages: measured on a B200 box the
+ * teardown of one simulation cost 12 ms to more than a second, several times the rest of the host work of a call.
+ * Front-ends call mcx_run_simulation in loops (wavelengths, sources, repetitions), always with the same buffer
+ * sizes, so released buffers are kept by exact size per device and handed out again.  Cached bytes are bounded;
+ * mcxb_release_cached_buffers() returns everything to the driver.
+ * ------------------------------------------------------------------------------------------------- */
+namespace {
+struct BufferPool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> freedev, freehost;     /* (device, bytes) -> pointer; host: device = -1 */
+    std::map<void*, std::pair<int, size_t> > live;
+    size_t cacheddev = 0, cachedhost = 0;
+    static constexpr size_t kMaxDev = (size_t)16 << 30, kMaxHost = (size_t)2 << 30;
+
+    cudaError_t get(void** out, int device, size_t bytes, bool host) {
+        bytes = std::max<size_t>(bytes, 16);
+        std::lock_guard<std::mutex> lk(mu);
+        auto& fl = host ? freehost : freedev;
+        auto it = fl.find(std::make_pair(host ? -1 : device, bytes));
+
+        if (it != fl.end()) {
+            *out = it->second;
+            fl.erase(it);
+            (host ? cachedhost : cacheddev) -= bytes;
+        } else {
+            cudaError_t e = host ? cudaMallocHost(out, bytes) : cudaMalloc(out, bytes);
+
+            if (e != cudaSuccess) {
+                /* make room and try once more */
+                cudaGetLastError();
+                drop_locked();
+                e = host ? cudaMallocHost(out, bytes) : cudaMalloc(out, bytes);
+
+                if (e != cudaSuccess) {
+                    *out = nullptr;
+                    return e;
+                }
+            }
+        }
+
+        live[*out] = std::make_pair(host ? -1 : device, bytes);
+        return cudaSuccess;
+    }
+    void put(void* ptr) {
+        if (!ptr) {
+            return;
+        }
+
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = live.find(ptr);
+
+        if (it == live.end()) {
+            return;
+        }
+
+        const std::pair<int, size_t> key = it->second;
+        live.erase(it);
+        const bool host = key.first < 0;
+        size_t& cached = host ? cachedhost : cacheddev;
+
+        if (cached + key.second > (host ? kMaxHost : kMaxDev)) {
+            if (host) {
+                cudaFreeHost(ptr);
+            } else {
+                cudaSetDevice(key.first);
+                cudaFree(ptr);
+            }
+
+            return;
+        }
+
+        cached += key.second;
+        (host ? freehost : freedev).insert(std::make_pair(key, ptr));
+    }
+    void drop_locked() {
+        for (auto& kv : freedev) {
+            cudaSetDevice(kv.first.first);
+            cudaFree(kv.second);
+        }
+
+        for (auto& kv : freehost) {
+            cudaFreeHost(kv.second);
+        }
+
+        freedev.clear();
+        freehost.clear();
+        cacheddev = cachedhost = 0;
+    }
+    void drop() {
+        std::lock_guard<std::mutex> lk(mu);
+        drop_locked();
+    }
+};
+BufferPool& pool() {
+    static BufferPool* p = new BufferPool();      /* intentionally leaked: no CUDA calls during static destruction */
+    return *p;
+}
+template <typename T> cudaError_t dev_alloc(T** out, int device, size_t bytes) {
+    return pool().get(reinterpret_cast<void**>(out), device, bytes, false);
+}
+template <typename T> cudaError_t host_alloc(T** out, size_t bytes) {
+    return pool().get(reinterpret_cast<void**>(out), -1, bytes, true);
+}
+} // namespace
+
+extern "C" void mcxb_release_cached_buffers(void) {
+    pool().drop();
 }
 
 /* ------------------------------------------------------------------------------------------------- */
@@ -338,21 +450,14 @@ static void sim_free(mcxb_sim* s) {
     }
 
     cudaSetDevice(s->device);
-    cudaFree(s->d_media);
-    cudaFree(s->d_field);
-    cudaFree(s->d_field32);
-    cudaFree(s->d_tables);
-    cudaFree(s->d_seeds);
-    cudaFree(s->d_det);
-    cudaFree(s->d_detcount);
-    cudaFree(s->d_seedout);
-    cudaFree(s->d_counter);
-    cudaFree(s->d_energy);
-    cudaFree(s->d_pattern);
-    cudaFree(s->d_invcdf);
-    cudaFree(s->d_stats);
-    cudaFreeHost(s->h_field);
-    cudaFreeHost(s->h_small);
+    cudaDeviceSynchronize();        /* pooled buffers may be handed out again at once: nothing may still be using them */
+    void* bufs[] = { s->d_media, s->d_field, s->d_field32, s->d_tables, s->d_seeds, s->d_det, s->d_detcount, s->d_seedout,
+                     s->d_counter, s->d_energy, s->d_pattern, s->d_invcdf, s->d_stats, s->h_field, s->h_small
+                   };
+
+    for (void* b : bufs) {
+        pool().put(b);
+    }
 
     if (s->ev0) {
         cudaEventDestroy(s->ev0);
@@ -489,7 +594,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
             }
         }
 
-        CU_TRY(cudaMalloc(&s->d_media, packed.size()));
+        CU_TRY(dev_alloc(&s->d_media, device, packed.size()));
         CU_TRY(cudaMemcpy(s->d_media, packed.data(), packed.size(), cudaMemcpyHostToDevice));
     }
 
@@ -518,12 +623,12 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
             tab[cfg->medianum + 4 * (1 + cfg->extrasrclen) + i] = make_float4(cfg->detpos[i].x, cfg->detpos[i].y, cfg->detpos[i].z, cfg->detpos[i].w);
         }
 
-        CU_TRY(cudaMalloc(&s->d_tables, sizeof(float4) * tablen));
+        CU_TRY(dev_alloc(&s->d_tables, device, sizeof(float4) * tablen));
         CU_TRY(cudaMemcpy(s->d_tables, tab.data(), sizeof(float4) * tablen, cudaMemcpyHostToDevice));
     }
 
     if (cfg->srcpattern && cfg->srcpattern_len) {
-        CU_TRY(cudaMalloc(&s->d_pattern, sizeof(float) * cfg->srcpattern_len));
+        CU_TRY(dev_alloc(&s->d_pattern, device, sizeof(float) * cfg->srcpattern_len));
         CU_TRY(cudaMemcpy(s->d_pattern, cfg->srcpattern, sizeof(float) * cfg->srcpattern_len, cudaMemcpyHostToDevice));
     }
 
@@ -540,7 +645,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
             memcpy(t.data() + nphase, cfg->angleinvcdf, sizeof(float) * nangle);
         }
 
-        CU_TRY(cudaMalloc(&s->d_invcdf, sizeof(float) * t.size()));
+        CU_TRY(dev_alloc(&s->d_invcdf, device, sizeof(float) * t.size()));
         CU_TRY(cudaMemcpy(s->d_invcdf, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
     }
 
@@ -593,28 +698,28 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     {
         std::vector<uint32_t> seeds((size_t)s->nthread * 4);
         mcxb_fill_seeds(cfg->seed, cfg->seed_skip, s->nthread, seeds.data());
-        CU_TRY(cudaMalloc(&s->d_seeds, seeds.size() * 4));
+        CU_TRY(dev_alloc(&s->d_seeds, device, seeds.size() * 4));
         CU_TRY(cudaMemcpy(s->d_seeds, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice));
     }
 
     /* ---- outputs ---- */
-    CU_TRY(cudaMalloc(&s->d_field, (s->acc64 ? 8 : 4) * s->fieldlen));
-    CU_TRY(cudaMalloc(&s->d_field32, 4 * s->fieldlen));
-    CU_TRY(cudaMalloc(&s->d_energy, 2 * sizeof(double)));
-    CU_TRY(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
-    CU_TRY(cudaMalloc(&s->d_detcount, sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&s->d_stats, 3 * sizeof(unsigned long long)));
+    CU_TRY(dev_alloc(&s->d_field, device, (s->acc64 ? 8 : 4) * s->fieldlen));
+    CU_TRY(dev_alloc(&s->d_field32, device, 4 * s->fieldlen));
+    CU_TRY(dev_alloc(&s->d_energy, device, 2 * sizeof(double)));
+    CU_TRY(dev_alloc(&s->d_counter, device, sizeof(unsigned long long)));
+    CU_TRY(dev_alloc(&s->d_detcount, device, sizeof(uint32_t)));
+    CU_TRY(dev_alloc(&s->d_stats, device, 3 * sizeof(unsigned long long)));
 
     if (savedet) {
-        CU_TRY(cudaMalloc(&s->d_det, sizeof(float) * std::max<size_t>(1, (size_t)cfg->maxdetphoton * std::max(1u, s->reclen))));
+        CU_TRY(dev_alloc(&s->d_det, device, sizeof(float) * std::max<size_t>(1, (size_t)cfg->maxdetphoton * std::max(1u, s->reclen))));
 
         if (cfg->issaveseed) {
-            CU_TRY(cudaMalloc(&s->d_seedout, 2 * sizeof(unsigned long long) * std::max<size_t>(1, cfg->maxdetphoton)));
+            CU_TRY(dev_alloc(&s->d_seedout, device, 2 * sizeof(unsigned long long) * std::max<size_t>(1, cfg->maxdetphoton)));
         }
     }
 
-    CU_TRY(cudaMallocHost(&s->h_field, 4 * s->fieldlen));
-    CU_TRY(cudaMallocHost(&s->h_small, 8 * sizeof(double)));
+    CU_TRY(host_alloc(&s->h_field, 4 * s->fieldlen));
+    CU_TRY(host_alloc(&s->h_small, 8 * sizeof(double)));
     CU_TRY(cudaEventCreate(&s->ev0));
     CU_TRY(cudaEventCreate(&s->ev1));
 

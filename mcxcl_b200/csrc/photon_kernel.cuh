@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
     float mua = 0.f, mus = 0.f, g = 0.f, nmed = n0;   /* optical properties of the voxel being traversed */
     float e_escaped = 0.f, e_launched = 0.f;
     float w0init = 0.f;                               /* launch weight of the live packet (W flag) */
+    float pacc = 0.f;                                 /* path length travelled in the current medium, not yet added to its ppath row */
     int   cursrc = 0;                                 /* source the live packet came from (1-based; 0 = single source) */
     uint32_t budget = (P.sched == 1) ? (P.threadphoton + ((int)tid < P.oddphoton ? 1u : 0u)) : 0u;
     uint32_t detarg = 0;                              /* detector argument handed to the retire step */
@@ -820,6 +821,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             ph.nscat = -1;
             ph.pathlen = 0.f;
             ph.face = -1;
+            pacc = 0.f;
             relaunch = false;
         }
 
@@ -922,9 +924,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
         }
 
         if (SAVEDET) {
-            if (P.savedetflag & 0x04u) {
-                ppath_len[ph.label * kBlock] += len;
-            }
+            pacc += len;     /* moved to the partial-path row of this medium when the packet leaves it (below) */
         }
 
         /* ------------------------------------------------------------------ new voxel (:2796-2811) */
@@ -985,98 +985,114 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             ph.pathlen = 0.f;
         }
 
-        /* ------------------------------------------------------------------ leave / time out (:2957-3028) */
-        const uint32_t bcode = ph.detflag & 0xFu;
+        /* Everything below only has work to do for the few packets that changed medium (which includes leaving the
+         * grid), ran out of time or fell below the roulette threshold: one test keeps the other lanes out of it.
+         * (With the label unchanged n1 == n of the current medium, so the index-mismatch block is a no-op, and
+         * boundary codes are only ever attached to a label-0 step out of the grid.) */
+        if (ph.label != oldlabel || ph.tof > P.twin1 || fabsf(ph.w) < P.minenergy) {
+            if (SAVEDET) {
+                if (ph.label != oldlabel) {
+                    if ((P.savedetflag & 0x04u) && oldlabel) {
+                        ppath_len[oldlabel * kBlock] += pacc;
+                    }
 
-        if ((ph.label == 0 && (bcode == bcAbsorb || (GEN && bcode == bcCyclic) || (bcode == bcReflect && ph.n1 == n0))) || ph.tof > P.twin1) {
-            bool reentered = false;
-
-            if (GEN && ph.detflag == bcCyclic) {
-                /* re-enter through the opposite face (:2970-2996) */
-                if (ph.face == 0) {
-                    ph.px = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fnx : 0.f), (ph.vx > 0.f) - (ph.vx < 0.f));
-                    ph.ix = (int)(short)floorf(ph.px);
-                } else if (ph.face == 1) {
-                    ph.py = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fny : 0.f), (ph.vy > 0.f) - (ph.vy < 0.f));
-                    ph.iy = (int)(short)floorf(ph.py);
-                } else {
-                    ph.pz = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fnz : 0.f), (ph.vz > 0.f) - (ph.vz < 0.f));
-                    ph.iz = (int)(short)floorf(ph.pz);
-                }
-
-                if (voxel_in_grid(P, ph.ix, ph.iy, ph.iz)) {
-                    ph.idx1d = linear_index(P, ph.ix, ph.iy, ph.iz);
-                    fetch_voxel(media, ph.idx1d, ph.label, ph.detflag);
-                    reentered = true;
+                    pacc = 0.f;
                 }
             }
 
-            if (!reentered) {
-                detarg = (GEN && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
-                relaunch = true;
-            }
-        } else {
-            /* -------------------------------------------------------------- Russian roulette (:3031-3061) */
-            if (fabsf(ph.w) < P.minenergy) {
-                if (rng_uniform(rng) * kRouletteSize <= 1.f) {
-                    ph.w *= kRouletteSize;
-                } else {
-                    detarg = olddet;
+            /* ------------------------------------------------------------------ leave / time out (:2957-3028) */
+            const uint32_t bcode = ph.detflag & 0xFu;
+
+            if ((ph.label == 0 && (bcode == bcAbsorb || (GEN && bcode == bcCyclic) || (bcode == bcReflect && ph.n1 == n0))) || ph.tof > P.twin1) {
+                bool reentered = false;
+
+                if (GEN && ph.detflag == bcCyclic) {
+                    /* re-enter through the opposite face (:2970-2996) */
+                    if (ph.face == 0) {
+                        ph.px = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fnx : 0.f), (ph.vx > 0.f) - (ph.vx < 0.f));
+                        ph.ix = (int)(short)floorf(ph.px);
+                    } else if (ph.face == 1) {
+                        ph.py = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fny : 0.f), (ph.vy > 0.f) - (ph.vy < 0.f));
+                        ph.iy = (int)(short)floorf(ph.py);
+                    } else {
+                        ph.pz = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fnz : 0.f), (ph.vz > 0.f) - (ph.vz < 0.f));
+                        ph.iz = (int)(short)floorf(ph.pz);
+                    }
+
+                    if (voxel_in_grid(P, ph.ix, ph.iy, ph.iz)) {
+                        ph.idx1d = linear_index(P, ph.ix, ph.iy, ph.iz);
+                        fetch_voxel(media, ph.idx1d, ph.label, ph.detflag);
+                        reentered = true;
+                    }
+                }
+
+                if (!reentered) {
+                    detarg = (GEN && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
                     relaunch = true;
                 }
-            }
-
-            /* -------------------------------------------------------------- index mismatch (:3063-3297) */
-            if (REFLECT && !relaunch) {
-                const float n2 = (ph.label == oldlabel) ? nmed : tab[ph.label].w;
-                const bool mirror = GEN && bcode == bcMirror;
-                bool handle = false;
-
-                if (mirror || ph.n1 != n2) {
-                    handle = ph.label ? (!GEN || P.doreflect)
-                             : (GEN ? ((bcode == bcUnknown && P.doreflect) || bcode == bcReflect || bcode == bcMirror)
-                                    : (bcode == bcUnknown || bcode == bcReflect));
+            } else {
+                /* -------------------------------------------------------------- Russian roulette (:3031-3061) */
+                if (fabsf(ph.w) < P.minenergy) {
+                    if (rng_uniform(rng) * kRouletteSize <= 1.f) {
+                        ph.w *= kRouletteSize;
+                    } else {
+                        detarg = olddet;
+                        relaunch = true;
+                    }
                 }
 
-                if (handle) {
-                    float Rtotal = 1.f;
+                /* -------------------------------------------------------------- index mismatch (:3063-3297) */
+                if (REFLECT && !relaunch) {
+                    const float n2 = (ph.label == oldlabel) ? nmed : tab[ph.label].w;
+                    const bool mirror = GEN && bcode == bcMirror;
+                    bool handle = false;
 
-                    if (!mirror) {
-                        Rtotal = fresnel(ph.vx, ph.vy, ph.vz, ph.n1, n2, ph.face);
+                    if (mirror || ph.n1 != n2) {
+                        handle = ph.label ? (!GEN || P.doreflect)
+                                 : (GEN ? ((bcode == bcUnknown && P.doreflect) || bcode == bcReflect || bcode == bcMirror)
+                                        : (bcode == bcUnknown || bcode == bcReflect));
                     }
 
-                    if (Rtotal < 1.f && !(ph.label == 0 && mirror) && rng_uniform(rng) > Rtotal) {
-                        refract(ph.vx, ph.vy, ph.vz, ph.n1, n2, ph.face);
+                    if (handle) {
+                        float Rtotal = 1.f;
 
-                        if (ph.label == 0) {
-                            detarg = (GEN && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
-                            relaunch = true;
+                        if (!mirror) {
+                            Rtotal = fresnel(ph.vx, ph.vy, ph.vz, ph.n1, n2, ph.face);
                         }
 
-                        nmed = n2;     /* now travelling in the new medium */
-                    } else {
-                        /* mirror the direction and put the packet back on the face it came through (:3204-3213) */
-                        if (ph.face == 0) {
-                            ph.vx = -ph.vx;
-                            ph.px = nudge(rintf(ph.px), 0);
-                            ph.ix = (int)(short)rintf(ph.px);
-                        } else if (ph.face == 1) {
-                            ph.vy = -ph.vy;
-                            ph.py = nudge(rintf(ph.py), 0);
-                            ph.iy = (int)(short)rintf(ph.py);
+                        if (Rtotal < 1.f && !(ph.label == 0 && mirror) && rng_uniform(rng) > Rtotal) {
+                            refract(ph.vx, ph.vy, ph.vz, ph.n1, n2, ph.face);
+
+                            if (ph.label == 0) {
+                                detarg = (GEN && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
+                                relaunch = true;
+                            }
+
+                            nmed = n2;     /* now travelling in the new medium */
                         } else {
-                            ph.vz = -ph.vz;
-                            ph.pz = nudge(rintf(ph.pz), 0);
-                            ph.iz = (int)(short)rintf(ph.pz);
-                        }
+                            /* mirror the direction and put the packet back on the face it came through (:3204-3213) */
+                            if (ph.face == 0) {
+                                ph.vx = -ph.vx;
+                                ph.px = nudge(rintf(ph.px), 0);
+                                ph.ix = (int)(short)rintf(ph.px);
+                            } else if (ph.face == 1) {
+                                ph.vy = -ph.vy;
+                                ph.py = nudge(rintf(ph.py), 0);
+                                ph.iy = (int)(short)rintf(ph.py);
+                            } else {
+                                ph.vz = -ph.vz;
+                                ph.pz = nudge(rintf(ph.pz), 0);
+                                ph.iz = (int)(short)rintf(ph.pz);
+                            }
 
-                        ph.idx1d = oldidx;
-                        ph.label = oldlabel;
-                        ph.detflag = olddet;
-                        nmed = ph.n1;
+                            ph.idx1d = oldidx;
+                            ph.label = oldlabel;
+                            ph.detflag = olddet;
+                            nmed = ph.n1;
+                        }
+                    } else {
+                        nmed = n2;
                     }
-                } else {
-                    nmed = n2;
                 }
             }
         }

@@ -98,16 +98,21 @@ def test_scalar_helpers_bit_exact(lib, ref):
     rs = np.random.RandomState(11)
     a = np.concatenate([rs.uniform(-5, 65, 5000), np.arange(0, 61), [0.0, -0.0, 1000.0, -1000.0]]).astype(np.float32)
     d = rs.randint(-1, 2, a.size).astype(np.int32)
-    v = rs.normal(size=(6000, 4)).astype(np.float32)
+    m = 300000
+    v = rs.normal(size=(m, 4)).astype(np.float32)
     v[:, :3] /= np.linalg.norm(v[:, :3], axis=1, keepdims=True)
-    n1 = rs.choice([1.0, 1.33, 1.37, 1.45, 1.55], 6000).astype(np.float32)
-    n2 = rs.choice([1.0, 1.33, 1.37, 1.45, 1.55], 6000).astype(np.float32)
-    face = rs.randint(0, 3, 6000).astype(np.int32)
+    v[:1000, 2] = rs.uniform(-1e-3, 1e-3, 1000)                  # grazing incidence on z faces
+    v[1000:2000, :3] = [0, 0, 1]                                 # normal incidence
+    n1 = rs.choice([1.0, 1.33, 1.37, 1.45, 1.55, 6.85], m).astype(np.float32)
+    n2 = rs.choice([1.0, 1.33, 1.37, 1.45, 1.55, 6.85], m).astype(np.float32)
+    n1[2000:3000] = rs.uniform(1.0, 2.5, 1000)
+    n2[2000:3000] = rs.uniform(1.0, 2.5, 1000)
+    face = rs.randint(0, 3, m).astype(np.int32)
     wna, wrc = ref.scalar(a, d, v, n1, n2, face)
     gna = np.zeros_like(wna)
     grc = np.zeros_like(wrc)
     abi.check(lib.mcxb_test_scalar(0, a.ctypes.data, d.ctypes.data, a.size, gna.ctypes.data, v.ctypes.data, n1.ctypes.data,
-                                   n2.ctypes.data, face.ctypes.data, 6000, grc.ctypes.data), "mcxb_test_scalar")
+                                   n2.ctypes.data, face.ctypes.data, m, grc.ctypes.data), "mcxb_test_scalar")
     assert (f32bits(gna) == f32bits(wna)).all()
     assert (f32bits(grc) == f32bits(wrc)).all()
     sc = KAT["scalar"]
