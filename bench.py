@@ -39,6 +39,17 @@ PUBLISHED_PHOTONS_PER_MS = 12953.37     # reference README.md:618 (cube60b-like 
 WORK = {"cube60": dict(seg=196.7, dep=117.8, sca=79.7), "cube60b": dict(seg=322.7, dep=193.4, sca=130.0),
         "skinvessel": dict(seg=343.9, dep=307.2, sca=35.7), "colin27": dict(seg=1880.5, dep=233.4, sca=1647.4)}
 FALLBACK_HBM_GBS = 6650.0
+N_SM, SCHEDULERS_PER_SM = 148, 4
+
+
+def kernel_counters(workload):
+    """per-photon instruction counts and DRAM traffic of the photon kernel from the committed ncu capture
+    (profiles/kernel_counters.json, written by tools/ncu_counters.py from the .ncu-rep of the same kernel version)"""
+    path = os.path.join(ROOT, "profiles", "kernel_counters.json")
+    try:
+        return json.load(open(path)).get(workload)
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -241,12 +252,24 @@ def main():
             abi.check(lib.mcxb_bench_red(local, 8, max(p.fieldlen, 1 << 16), 148 * 8, 2000, 0, 3, C.byref(ms_), C.byref(ops_)))
             red_peak = ops_.value / ms_.value / 1e6
             red_ach = w["dep"] * nph / (kern_ms * 1e-3) / 1e9
-            roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
+            kc = kernel_counters(args.workload)
+            issue = None
+            traffic = None
+            if kc:
+                f_sm = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                issue_peak = N_SM * SCHEDULERS_PER_SM * f_sm                       # warp instructions per second
+                issue_ach = kc["warp_inst_per_photon"] * nph / (kern_ms * 1e-3)
+                issue = dict(achieved=issue_ach / 1e12, peak=issue_peak / 1e12, unit="T warp-instructions/s", frac=issue_ach / issue_peak,
+                             warp_inst_per_photon=kc["warp_inst_per_photon"], lanes_per_warp_inst=kc["lanes_per_warp_inst"],
+                             peak_source="148 SMs x 4 schedulers x SM clock sampled during this run (%.0f MHz)" % (f_sm / 1e6),
+                             counter_source=kc["source"])
+                traffic = kc["dram_bytes_per_photon"] * nph
+            roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                         kernel="photon_kernel<%s>" % kname, kernel_ms=kern_ms,
                         algorithmic_bytes_per_photon=w["seg"] + w["dep"] * acc_bytes,
-                        note="working set (media %.2f MB + fp64 accumulators %.2f MB) is L2-resident, so HBM is not the binding ceiling; see l2_red and issue" % (p.dimxyz / 1e6, 8 * p.fieldlen / 1e6),
-                        l2_red=dict(achieved=red_ach, peak=red_peak, unit="G reductions/s", frac=red_ach / red_peak, peak_source="mcxb_bench_red: uniform random fp64 RED over a buffer of the volume's size, measured in this run"),
-                        issue=dict(segments_per_s=w["seg"] * nph / (kern_ms * 1e-3), source="issue-slot utilisation: profiles/ (ncu sm__inst_executed / sm__cycles_active)"))
+                        note="working set (media %.2f MB + fp64 accumulators %.2f MB) is L2-resident: DRAM traffic is a small fraction of the algorithmic bytes and HBM is not the binding ceiling; the kernel is bound by SM issue slots (issue) and, behind that, by L2 reductions (l2_red)" % (p.dimxyz / 1e6, 8 * p.fieldlen / 1e6),
+                        issue=issue,
+                        l2_red=dict(achieved=red_ach, peak=red_peak, unit="G reductions/s", frac=red_ach / red_peak, peak_source="mcxb_bench_red: uniform random fp64 RED over a buffer of the volume's size, measured in this run"))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             info = bounded_cpu_run(args.workload, args.cpu_photons)
