@@ -1,0 +1,197 @@
+"""The plain-C restatement (oracle/mcx_oracle.c) against the reference's own kernel source (oracle/_ref) and against
+the known answers of tests/golden/kat_survey.json.
+
+Both checkers run under the same numeric contract (IEEE binary32, no contraction, libm float functions), so with
+one host thread -- work-items executed in index order into one private field -- every output must agree BIT FOR BIT:
+field, per-work-item energies, detected-photon records, saved seeds and the work counters."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import decks
+from mcxcl_b200 import benchmarks, hostcfg
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "kat_survey.json")))
+
+
+def bits(x):
+    return np.asarray(x, dtype=np.float32).view(np.uint32)
+
+
+def both(ref, port, cfg, work=64):
+    p = hostcfg.prepare(cfg)
+    a = ref.run(p, work, hostthreads=1, want_energy=True)
+    b = port.run(p, work, hostthreads=1, want_energy=True)
+    return p, a, b
+
+
+def assert_identical(a, b):
+    assert a["energytot"] == b["energytot"] and a["energyesc"] == b["energyesc"]
+    assert (bits(a["energy"]) == bits(b["energy"])).all()
+    assert (bits(a["field"]) == bits(b["field"])).all()
+    assert a["detected"] == b["detected"] and a["reclen"] == b["reclen"]
+    if a["detp"] is not None:
+        assert (bits(a["detp"]) == bits(b["detp"])).all()
+    if a["seeds"] is not None:
+        assert (a["seeds"] == b["seeds"]).all()
+    assert (a["n_segment"], a["n_deposit"], a["n_scatter"]) == (b["n_segment"], b["n_deposit"], b["n_scatter"])
+
+
+# ---------------------------------------------------------------------------------------- unit level
+
+def test_port_rng_kat(port):
+    seeds = port.seeds(KAT["seed"], len(KAT["rng"]))
+    for row in KAT["rng"]:
+        assert seeds.reshape(-1, 4)[row["thread"]].tolist() == row["seed"]
+    u, _ = port.rng(seeds, 3)
+    _, st = port.rng(seeds, 0)
+    for row in KAT["rng"]:
+        np.testing.assert_allclose(u[row["thread"]], np.array(row["u"], dtype=np.float32), rtol=2e-7, atol=0)
+        assert [int(x) for x in st[row["thread"]]] == [int(t, 16) for t in row["t"]]
+
+
+def test_port_traversal_and_scalar_kat(port):
+    t = KAT["trace"]
+    v0 = np.array([int(b, 16) for b in t["v0_bits"]], dtype=np.uint32).view(np.float32)
+    out = port.trace(np.array(t["p0"] + [1.0], dtype=np.float32), np.append(v0, 0).astype(np.float32), len(t["steps"]), t["dims"], t["musp"])[0]
+    for k, s in enumerate(t["steps"]):
+        assert int(out["face"][k]) == s["face"] and int(out["idx1d"][k]) == s["idx1d"]
+        assert "%08x" % bits(out["dist"][k]) == s["dist"]
+        assert ["%08x" % bits(out[c][k]) for c in ("px", "py", "pz")] == s["p"]
+    sc = KAT["scalar"]
+    rc = sc["reflectcoeff"]
+    na, r = port.scalar([x[0] for x in sc["nextafter"]], [x[1] for x in sc["nextafter"]], [x["v"] + [0] for x in rc],
+                        [x["n1"] for x in rc], [x["n2"] for x in rc], [x["face"] for x in rc])
+    assert ["%08x" % b for b in bits(na)] == [x[2] for x in sc["nextafter"]]
+    assert ["%08x" % b for b in bits(r)] == [x["bits"] for x in rc]
+
+
+def test_port_unit_hooks_match_reference_source(ref, port):
+    rs = np.random.RandomState(5)
+    seeds = rs.randint(0, 2 ** 31, 4 * 300).astype(np.uint32)
+    ua, sa = ref.rng(seeds, 40)
+    ub, sb = port.rng(seeds, 40)
+    assert (bits(ua) == bits(ub)).all() and (sa == sb).all()
+    n = 400
+    p0 = np.zeros((n, 4), np.float32)
+    p0[:, :3] = rs.uniform(0, 1, (n, 3)) * [31, 17, 23]
+    v0 = np.zeros((n, 4), np.float32)
+    d = rs.normal(size=(n, 3))
+    d[:40, 0] = 0          # axis-parallel rays: the division by zero of hitgrid
+    d[40:80, 1:] = 0
+    v0[:, :3] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    ta = ref.trace(p0, v0, 48, (31, 17, 23), 2.5)
+    tb = port.trace(p0, v0, 48, (31, 17, 23), 2.5)
+    assert all(ta[f].tobytes() == tb[f].tobytes() for f in ta.dtype.names)
+    a = rs.uniform(-5, 70, 500).astype(np.float32)
+    dr = rs.randint(-1, 2, 500).astype(np.int32)
+    n1 = rs.choice([1.0, 1.33, 1.37, 1.5], n).astype(np.float32)
+    n2 = rs.choice([1.0, 1.33, 1.37, 1.5], n).astype(np.float32)
+    face = rs.randint(0, 3, n).astype(np.int32)
+    ra = ref.scalar(a, dr, v0, n1, n2, face)
+    rb = port.scalar(a, dr, v0, n1, n2, face)
+    assert (bits(ra[0]) == bits(rb[0])).all() and (bits(ra[1]) == bits(rb[1])).all()
+    th, ph = rs.uniform(0, np.pi, n), rs.uniform(0, 2 * np.pi, n)
+    v1 = v0.copy()
+    v1[:10, :3] = [0, 0, 1]
+    v1[10:20, :3] = [0, 0, -1]
+    args = [np.sin(th), np.cos(th), np.sin(ph), np.cos(ph)]
+    assert (bits(ref.rotate(v1, *args)) == bits(port.rotate(v1, *args))).all()
+    ok = n1 <= n2          # transmission always defined
+    assert (bits(ref.transmit(v0[ok], n1[ok], n2[ok], face[ok])) == bits(port.transmit(v0[ok], n1[ok], n2[ok], face[ok]))).all()
+
+
+# ----------------------------------------------------------------------------------- whole simulations
+
+@pytest.mark.parametrize("name", sorted(decks.SOURCES))
+def test_port_bit_identical_sources(ref, port, name):
+    cfg = decks.cube(3000, **decks.SOURCES[name])
+    _, a, b = both(ref, port, cfg)
+    assert a["energytot"] > 0
+    assert_identical(a, b)
+
+
+@pytest.mark.parametrize("name", sorted(decks.BOUNDARIES))
+def test_port_bit_identical_boundaries(ref, port, name):
+    over = dict(decks.BOUNDARIES[name])
+    over["nphoton"] = min(int(over.get("nphoton", 3000)), 3000)
+    _, a, b = both(ref, port, decks.cube(**over))
+    assert_identical(a, b)
+
+
+@pytest.mark.parametrize("case", ["two_layer", "two_layer_gates", "roulette", "savedet_all", "saveseed", "energy", "length",
+                                  "multisrc_pick", "multisrc_volumes", "multisrc_fixed", "gscatter", "saveref", "flat2d",
+                                  "skinvessel", "phase_table", "angle_table", "angle_table_discrete", "rngdebug", "odd_split"])
+def test_port_bit_identical_features(ref, port, case):
+    multi = dict(srcpos=[[29.0, 29.0, 0.0, 1.0], [10.0, 40.0, 0.0, 1.0], [45.0, 15.0, 0.0, 0.5]])    # N x 4: extra sources
+    work = 64
+    if case == "two_layer":
+        cfg = decks.two_layer(3000)
+    elif case == "two_layer_gates":
+        cfg = decks.two_layer(3000, tend=2e-9, tstep=2e-10)
+    elif case == "roulette":
+        cfg = decks.two_layer(3000, minenergy=0.05)
+    elif case == "savedet_all":
+        cfg = decks.two_layer(6000, savedetflag=0x7F)
+    elif case == "saveseed":
+        cfg = decks.cube(6000, issaveseed=1)
+    elif case == "energy":
+        cfg = decks.two_layer(3000, outputtype="energy")
+    elif case == "length":
+        cfg = decks.two_layer(2000, outputtype="length")
+    elif case == "multisrc_pick":
+        cfg = decks.cube(4000, srcid=0, savedetflag=0x7F, **multi)
+    elif case == "multisrc_volumes":
+        cfg = decks.cube(4000, srcid=-1, **multi)
+    elif case == "multisrc_fixed":
+        cfg = decks.cube(3000, srcid=3, **multi)
+    elif case == "gscatter":
+        cfg = decks.two_layer(3000, gscatter=5)
+    elif case == "saveref":
+        cfg = decks.two_layer(3000, issaveref=1)
+    elif case == "flat2d":
+        cfg = decks.cube(3000)
+        cfg.update(vol=np.ones((1, 60, 60), dtype=np.uint8), srcpos=[0.0, 29.0, 0.0], detpos=[[0, 19, 0, 2]])
+    elif case == "skinvessel":
+        cfg = benchmarks.get("skinvessel", 300)
+    elif case == "phase_table":
+        cfg = decks.cube(3000, invcdf=np.cos(np.linspace(np.pi, 0, 200)).astype(np.float32))
+    elif case == "angle_table":
+        cfg = decks.cube(3000, srcdir=[0, 0, 1, 0], angleinvcdf=np.linspace(0, 0.3, 16).astype(np.float32))
+    elif case == "angle_table_discrete":
+        cfg = decks.cube(3000, srcdir=[0, 0, 1, 1], angleinvcdf=np.array([0, 0.1, 0.2], dtype=np.float32))
+    elif case == "rngdebug":
+        cfg = decks.cube(100, debuglevel=1)
+    else:
+        cfg = decks.cube(3037)
+        work = 100
+    try:
+        p, a, b = both(ref, port, cfg, work)
+    except (KeyError, ValueError, TypeError) as e:
+        pytest.skip("host config mirror does not take this option: %s" % e)
+    assert_identical(a, b)
+    if case.startswith("multisrc"):
+        assert p.c.extrasrclen == 2
+        if case == "multisrc_volumes":
+            assert a["field"].size == 3 * 216000 and all(a["field"].reshape(3, -1).sum(axis=1) > 0)
+
+
+def test_port_parallel_run_matches_serial_totals(port):
+    p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
+    a = port.run(p, 512, hostthreads=1)
+    b = port.run(p, 512, hostthreads=0)
+    assert a["energyesc"] == b["energyesc"] and a["detected"] == b["detected"]
+    np.testing.assert_allclose(a["field"], b["field"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("deck,prefix", [("cube60", "17."), ("cube60b", "27.")])
+def test_port_absorbed_fraction_pins(port, deck, prefix):
+    """reference test/testmcx.sh:60-66"""
+    o = port.run(hostcfg.prepare(benchmarks.get(deck, 1e5)), 1024, hostthreads=0)
+    assert ("%.5f" % (100 * o["absorbed"])).startswith(prefix)
+    assert abs(o["energytot"] - 1e5) <= 10
+    if deck == "cube60b":
+        assert o["detected"] == KAT["statistical"]["cube60b_detected_1e5_w1024"]
