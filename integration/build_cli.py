@@ -63,7 +63,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     h = hashlib.sha256()
     for f in [os.path.join(HERE, "mcx_cuda_host.cpp"), os.path.join(HERE, "clstub", "CL", "cl.h"), os.path.abspath(__file__),
-              os.path.join(ROOT, "include", "mcxb200.h")] + [os.path.join(SRC, f) for f in C_FILES + CXX_FILES]:
+              os.path.join(ROOT, "include", "mcxb200.h")] + [os.path.join(SRC, f) for f in C_FILES + CXX_FILES + ["pmcxcl.cpp"]]:
         h.update(open(f, "rb").read())
     stamp = os.path.join(OUT, "build.stamp")
     if not args.force and os.path.exists(exe) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
@@ -91,10 +91,45 @@ def main():
                                     "-lm", "-pthread"])
     for o in objs:
         os.remove(o)
+    print("build_cli: built", exe)
+    mod = build_pmcxcl()
+    print("build_cli: built", mod)
     with open(stamp, "w") as f:
         f.write(h.hexdigest())
-    print("build_cli: built", exe)
     return 0
+
+
+def build_pmcxcl():
+    """The reference's UNCHANGED Python front-end (src/pmcxcl.cpp, a pybind11 module) against the B200 engine:
+    the `_pmcxcl` target of src/CMakeLists.txt:116-144 with mcx_host.cpp -> integration/mcx_cuda_host.cpp and
+    OpenCL::OpenCL -> libmcxb200.so.  -DMCX_CONTAINER makes mcx_error raise instead of exit (src/mcx_utils.c:1298-1305)."""
+    import sysconfig
+
+    import pybind11
+    defs = DEFS + ["-DMCX_CONTAINER", "-DPYBIND11_VERSION_MAJOR"]
+    inc = INC + ["-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"]]
+    mod = os.path.join(OUT, "_pmcxcl" + sysconfig.get_config_var("EXT_SUFFIX"))
+    jobs, objs = [], []
+
+    def add(cmd, src, tag="py_"):
+        obj = os.path.join(OUT, tag + os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        jobs.append(cmd + ["-c", os.path.join(SRC, src) if not os.path.isabs(src) else src, "-o", obj])
+        objs.append(obj)
+
+    for f in ["mcx_utils.c", "mcx_shapes.c", "mcx_lang.c", "mcx_tictoc.c", "cjson/cJSON.c", "ubj/ubjw.c"]:
+        add(["gcc", "-std=c99", "-O2", "-w", "-m64", "-fPIC"] + defs + inc, f)
+    for f in ["mcx_mie.cpp", "mcx_neurojson.cpp", "pmcxcl.cpp"]:
+        add(["g++", "-O2", "-w", "-m64", "-fPIC", "-fvisibility=hidden"] + defs + inc, f)
+    for f in ZMAT_FILES:
+        add(["gcc", "-O2", "-w", "-fPIC"] + ZMAT_DEFS + ZMAT_INC, f, tag="pyz_")
+    add(["g++", "-std=c++17", "-O2", "-Wall", "-m64", "-fPIC"] + defs + inc, os.path.join(HERE, "mcx_cuda_host.cpp"))
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        list(ex.map(run, jobs))
+    run(["g++", "-shared", "-o", mod] + objs + ["-L" + os.path.join(ROOT, "mcxcl_b200"), "-lmcxb200", "-Wl,-rpath,$ORIGIN/../../mcxcl_b200",
+                                               "-lm", "-pthread"])
+    for o in objs:
+        os.remove(o)
+    return mod
 
 
 if __name__ == "__main__":

@@ -20,6 +20,7 @@
 #include <cmath>
 #include <ctime>
 #include <string>
+#include <chrono>
 #include <vector>
 #include <map>
 #include <mutex>
@@ -221,6 +222,47 @@ extern "C" void mcxb_release_cached_buffers(void) {
     pool().drop();
 }
 
+/* cudaGetDeviceProperties costs milliseconds (measured: up to 200 ms on a busy host) and the answer never changes:
+ * one query per device per process */
+static cudaError_t device_properties(int device, const cudaDeviceProp** out) {
+    static std::mutex mu;
+    static std::map<int, cudaDeviceProp> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(device);
+
+    if (it == cache.end()) {
+        cudaDeviceProp p;
+        const cudaError_t e = cudaGetDeviceProperties(&p, device);
+
+        if (e != cudaSuccess) {
+            return e;
+        }
+
+        it = cache.insert(std::make_pair(device, p)).first;
+    }
+
+    *out = &it->second;
+    return cudaSuccess;
+}
+
+/* the seed table of the last call: front-ends repeat runs with the same seed and launch shape */
+static void cached_seeds(int32_t seed, uint64_t skip, uint64_t nrecords, std::vector<uint32_t>& out) {
+    static std::mutex mu;
+    static int32_t cseed = 0;
+    static uint64_t cskip = 0;
+    static std::vector<uint32_t> cache;
+    std::lock_guard<std::mutex> lk(mu);
+
+    if (seed <= 0 || seed != cseed || skip != cskip || cache.size() != nrecords * 4) {
+        cache.resize(nrecords * 4);
+        mcxb_fill_seeds(seed, skip, nrecords, cache.data());
+        cseed = seed;
+        cskip = skip;
+    }
+
+    out = cache;
+}
+
 /* ------------------------------------------------------------------------------------------------- */
 static int cores_per_sm(int major, int minor) {
     /* same table idea as mcx_nv_corecount (src/mcx_host.cpp:224-240), extended to Hopper/Blackwell */
@@ -269,8 +311,9 @@ extern "C" int mcxb_list_gpu(mcxb_gpuinfo* info, int maxinfo) {
     }
 
     for (int i = 0; i < n && i < maxinfo && info; i++) {
-        cudaDeviceProp p;
-        CU_TRY(cudaGetDeviceProperties(&p, i));
+        const cudaDeviceProp* pp = nullptr;
+        CU_TRY(device_properties(i, &pp));
+        const cudaDeviceProp& p = *pp;
         mcxb_gpuinfo* g = info + i;
         memset(g, 0, sizeof(*g));
         strncpy(g->name, p.name, sizeof(g->name) - 1);
@@ -527,8 +570,9 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     }
 
     CU_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    const cudaDeviceProp* propp = nullptr;
+    CU_TRY(device_properties(device, &propp));
+    const cudaDeviceProp& prop = *propp;
 
     if (prop.major < 10) {
         return fail(MCXB_ERR_NODEVICE, "this engine is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
@@ -696,8 +740,8 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
 
     /* ---- seeds ---- */
     {
-        std::vector<uint32_t> seeds((size_t)s->nthread * 4);
-        mcxb_fill_seeds(cfg->seed, cfg->seed_skip, s->nthread, seeds.data());
+        std::vector<uint32_t> seeds;
+        cached_seeds(cfg->seed, cfg->seed_skip, s->nthread, seeds);
         CU_TRY(dev_alloc(&s->d_seeds, device, seeds.size() * 4));
         CU_TRY(cudaMemcpy(s->d_seeds, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -857,8 +901,8 @@ extern "C" int mcxb_sim_reseed(mcxb_sim* s, int32_t seed, uint64_t seed_skip) {
     }
 
     CU_TRY(cudaSetDevice(s->device));
-    std::vector<uint32_t> seeds((size_t)s->nthread * 4);
-    mcxb_fill_seeds(seed, seed_skip, s->nthread, seeds.data());
+    std::vector<uint32_t> seeds;
+    cached_seeds(seed, seed_skip, s->nthread, seeds);
     CU_TRY(cudaMemcpy(s->d_seeds, seeds.data(), seeds.size() * 4, cudaMemcpyHostToDevice));
     s->cfg.seed = seed;
     s->cfg.seed_skip = seed_skip;
@@ -1037,8 +1081,14 @@ extern "C" float mcxb_sim_last_kernel_ms(mcxb_sim* s) {
 }
 
 extern "C" int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_output* out) {
+    /* MCXB_TIMING=1 prints where the host time of one call goes (create / reset+launch / fetch / destroy) */
+    static const bool timing = getenv("MCXB_TIMING") != nullptr;
+    typedef std::chrono::steady_clock clk;
+    clk::time_point t[5];
     mcxb_sim* s = nullptr;
+    t[0] = clk::now();
     int rc = mcxb_sim_create(cfg, device, &s);
+    t[1] = clk::now();
 
     if (rc == MCXB_OK) {
         rc = mcxb_sim_reset(s, nullptr);
@@ -1048,10 +1098,23 @@ extern "C" int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_outp
         rc = mcxb_sim_launch(s, nullptr);
     }
 
+    t[2] = clk::now();
+
     if (rc == MCXB_OK) {
         rc = mcxb_sim_fetch(s, nullptr, out);
     }
 
+    t[3] = clk::now();
     mcxb_sim_destroy(s);
+    t[4] = clk::now();
+
+    if (timing) {
+        auto ms = [&](int a, int b) {
+            return std::chrono::duration<double, std::milli>(t[b] - t[a]).count();
+        };
+        fprintf(stderr, "mcxb_run_simulation: create %.2f launch %.2f fetch %.2f (kernel %.2f) destroy %.2f ms\n", ms(0, 1), ms(1, 2), ms(2, 3),
+                out ? out->runtime_ms : 0.f, ms(3, 4));
+    }
+
     return rc;
 }

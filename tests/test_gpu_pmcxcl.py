@@ -1,0 +1,106 @@
+"""The reference's UNCHANGED Python front-end (src/pmcxcl.cpp, pybind11 module `_pmcxcl`), relinked against the B200
+engine through integration/mcx_cuda_host.cpp (integration/build_cli.py::build_pmcxcl).  The calls are the ones of the
+reference's own documentation and benchmark table (pmcxcl/pmcxcl/__init__.py:19-30, pmcxcl/pmcxcl/bench.py:22-60);
+the known answers are the reference's statistical pins (mcxlabcl/examples/mcx_gpu_benchmarks.m:65-112,
+test/testmcx.sh:60-75)."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from mcxcl_b200 import engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "integration", "_build")
+
+
+def load_module():
+    if not glob.glob(os.path.join(BUILD, "_pmcxcl*.so")):
+        pytest.skip("integration/_build/_pmcxcl*.so not built (python integration/build_cli.py needs /root/reference)")
+    if BUILD not in sys.path:
+        sys.path.insert(0, BUILD)
+    import _pmcxcl
+    return _pmcxcl
+
+
+def cube60(**kw):
+    """pmcxcl/pmcxcl/bench.py:22-37"""
+    cfg = dict(nphoton=1000000, vol=np.ones([60, 60, 60], dtype="uint8"), tstart=0, tend=5e-9, tstep=5e-9, srcpos=[29, 29, 0], srcdir=[0, 0, 1],
+               prop=[[0, 0, 1, 1], [0.005, 1, 0.01, 1.37], [0.002, 5, 0.9, 1]], isreflect=0, seed=1648335518, session="cube60",
+               detpos=[[29, 19, 0, 1], [29, 39, 0, 1], [19, 29, 0, 1], [39, 29, 0, 1]], issrcfrom0=1)
+    cfg.update(kw)
+    return cfg
+
+
+def test_module_exports_the_reference_api():
+    """runs without a GPU: the module imports and has run / gpuinfo / version (src/pmcxcl.cpp:1648-1663)"""
+    m = load_module()
+    assert callable(m.run) and callable(m.gpuinfo) and callable(m.version)
+    assert m.version().startswith("v20")
+
+
+@pytest.mark.gpu
+def test_gpuinfo_lists_the_b200():
+    m = load_module()
+    info = m.gpuinfo()
+    assert len(info) >= 1 and "B200" in info[0]["name"]
+    mine = engine.gpuinfo()[0]
+    assert info[0]["sm"] == mine["sm"] == 148 and info[0]["autothread"] == mine["autothread"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reflect,want", [(0, 0.1769), (1, 0.2701)])
+def test_run_cube60_known_answers(reflect, want):
+    """mcx_gpu_benchmarks.m:65-66, 87-88: absorbed fraction within 0.005, energytot within 10 of nphoton"""
+    m = load_module()
+    res = m.run(cube60(isreflect=reflect))
+    st = res["stat"]
+    assert abs(st["energytot"] - 1e6) <= 10
+    assert abs(st["energyabs"] / st["energytot"] - want) < 0.005
+    flux = res["flux"]
+    assert flux.shape == (60, 60, 60, 1) and flux.dtype == np.float32 and np.isfinite(flux).all()
+    # energy deposited = sum(flux * mua) * dt / normaliser-per-photon: the fluence integral reproduces the absorbed fraction
+    absorbed = float((flux.astype(np.float64) * 0.005).sum() * 5e-9)
+    assert abs(absorbed - st["energyabs"] / st["energytot"]) < 2e-3
+    detp = res["detp"]
+    assert detp.shape[0] == 1 + 2 and detp.shape[1] > 2000          # detid + partial path per medium (default savedetflag DP)
+    assert set(np.unique(detp[0]).astype(int)) <= {1, 2, 3, 4}
+    assert st["runtime"] > 0 and st["nphoton"] == 1000000 and st["unitinmm"] == 1.0
+
+
+@pytest.mark.gpu
+def test_run_keyword_form_and_planar_source():
+    """pmcxcl.run(**cfg) (the README call) and a wide-field source: bench.py 'cube60planar', pin 25.x % (test/testmcx.sh:76-78)"""
+    m = load_module()
+    res = m.run(**cube60(isreflect=1, srctype="planar", srcpos=[10, 10, -10], srcparam1=[40, 0, 0, 0], srcparam2=[0, 40, 0, 0], nphoton=200000))
+    st = res["stat"]
+    assert 0.25 <= st["energyabs"] / st["energytot"] < 0.26
+
+
+@pytest.mark.gpu
+def test_run_matches_the_ctypes_mirror():
+    """the same dictionary through the unchanged pybind11 front-end and through mcxcl_b200.engine.run: same RNG streams,
+    same photon count => the normalised volumes agree to float rounding of the accumulation order"""
+    m = load_module()
+    cfg = cube60(isreflect=1, nphoton=100000)
+    a = m.run(cfg)
+    b = engine.run(dict(cfg))
+    assert a["flux"].shape == b["flux"].shape
+    assert abs(a["stat"]["energyabs"] - b["stat"]["energyabs"]) / b["stat"]["energyabs"] < 2e-3
+    fa, fb = a["flux"].astype(np.float64), b["flux"].astype(np.float64)
+    big = fb > 1e-3 * fb.max()
+    # dynamic photon scheduling: streams are identical, their assignment to photons is not => statistical agreement only
+    assert abs(fa[big].sum() / fb[big].sum() - 1) < 5e-3
+
+
+@pytest.mark.gpu
+def test_errors_surface_as_python_exceptions():
+    """mcx_error -> mcx_throw_exception -> RuntimeError under MCX_CONTAINER (src/pmcxcl.cpp:1565-1568)"""
+    m = load_module()
+    with pytest.raises(RuntimeError, match="optical properties"):
+        m.run(cube60(vol=3 * np.ones([60, 60, 60], dtype="uint8")))      # label 3 with a 3-row media table
+    # a device that does not exist is not an error in the reference: it prints a notice and returns nothing
+    # (src/pmcxcl.cpp:1147-1152)
+    assert len(m.run(cube60(gpuid=9))) == 0
