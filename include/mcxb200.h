@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCXB_ABI_VERSION 1
+#define MCXB_ABI_VERSION 2
 
 /* error codes returned by every entry point (0 = success).  The reference reports OpenCL errors
  * negated through ocl_assess (src/mcx_host.cpp:213-217); CUDA runtime errors are reported the same
@@ -58,9 +58,13 @@ enum mcxb_srctype {
     MCXB_SRC_PATTERN3D, MCXB_SRC_HYPERBOLOID_GAUSSIAN, MCXB_SRC_RING
 };
 
-/* output types: same numbering as TOutputType (src/mcx_utils.h:58-60); only the first three and
- * otL are on the hot path of this build */
-enum mcxb_outputtype { MCXB_OT_FLUX = 0, MCXB_OT_FLUENCE = 1, MCXB_OT_ENERGY = 2, MCXB_OT_L = 7 };
+/* output types: same numbering as TOutputType (src/mcx_utils.h:58-60).  Flux / fluence / energy / otL are forward
+ * outputs; Jacobian (absorption sensitivity), WP (scattering-count sensitivity), DCS (momentum transfer) and their
+ * time-of-flight weighted forms WLTOF / WPTOF exist only in replay mode (replay_seed != NULL).  The RF types
+ * (6, 8) and the adjoint types (11+) are not part of this build. */
+enum mcxb_outputtype { MCXB_OT_FLUX = 0, MCXB_OT_FLUENCE = 1, MCXB_OT_ENERGY = 2, MCXB_OT_JACOBIAN = 3, MCXB_OT_WP = 4, MCXB_OT_DCS = 5,
+                       MCXB_OT_L = 7, MCXB_OT_WLTOF = 9, MCXB_OT_WPTOF = 10
+                     };
 
 /* boundary codes: TBoundary (src/mcx_utils.h:65) */
 enum mcxb_boundary { MCXB_BC_UNKNOWN = 0, MCXB_BC_REFLECT, MCXB_BC_ABSORB, MCXB_BC_MIRROR, MCXB_BC_CYCLIC };
@@ -149,6 +153,16 @@ typedef struct mcxb_config {
     uint32_t nblocksize;           /* 0 = autopilot */
     int32_t  sched;                /* enum mcxb_sched */
     int32_t  accum;                /* enum mcxb_accum: precision of the device fluence accumulators */
+
+    /* ---- photon replay: Config.replay / replaydet with Config.seed == SEED_FROM_FILE (src/mcx_utils.h:133-142,
+     *      src/mcx_host.cpp:722-737; kernel src/mcx_core.cl:1590-1596, 2567-2592, 2845-2858).  When replay_seed is
+     *      set, photon i restarts its RNG stream from replay_seed[2i..2i+1] (the state mcxb_output.seeddata recorded
+     *      for a detected photon) and nphoton is the number of records. ---- */
+    const uint64_t* replay_seed;   /* 2 words per photon, or NULL = forward simulation */
+    const float*    replay_weight; /* detected weight of photon i (mcx_replayprep, src/mcx_utils.c:1355-1430) */
+    const float*    replay_tof;    /* its time of flight in seconds: selects the time gate of the sensitivity outputs */
+    const int32_t*  replay_detid;  /* its detector (low 16 bits, 1-based); needed when replaydet == -1 */
+    int32_t         replaydet;     /* -1: one output volume per detector; otherwise one volume */
 } mcxb_config;
 
 typedef struct mcxb_output {
@@ -207,6 +221,10 @@ typedef struct mcxb_sim mcxb_sim;
 int  mcxb_sim_create(const mcxb_config* cfg, int device, mcxb_sim** sim);   /* H2D of media, tables, seeds */
 int  mcxb_sim_reset(mcxb_sim* sim, void* cuda_stream);                      /* zero field / energy / counters, restore seeds */
 int  mcxb_sim_launch(mcxb_sim* sim, void* cuda_stream);                     /* enqueue the photon kernel; asynchronous */
+/* progress of a launch that may still be running: photons claimed so far (read over a side stream, does not wait
+ * for the kernel) and whether the launch has finished -- what the reference's `-D P` bar polls through its mapped
+ * gprogress word (src/mcx_host.cpp:1112-1141) */
+int  mcxb_sim_progress(mcxb_sim* sim, uint64_t* claimed, int* finished);
 int  mcxb_sim_set_photons(mcxb_sim* sim, uint64_t nphoton);                 /* change the photon budget of the next launch */
 int  mcxb_sim_reseed(mcxb_sim* sim, int32_t seed, uint64_t seed_skip);      /* new per-thread seed slice (rank r: skip r*nthread) */
 int  mcxb_sim_finalize(mcxb_sim* sim, void* cuda_stream);                   /* accumulators -> float32 volume on the device; asynchronous */

@@ -123,6 +123,16 @@ void fill_config(const Config* cfg, mcxb_config* c) {
     c->nblocksize = cfg->autopilot ? 0 : cfg->nblocksize;
     c->sched = MCXB_SCHED_DYNAMIC;
     c->accum = MCXB_ACCUM_F64;
+
+    if (cfg->seed == SEED_FROM_FILE) {
+        /* photon replay: the records mcx_replayinit / mcx_replayprep prepared (src/mcx_utils.c:1355-1470) take the place
+         * of the gseed / greplayw / greplaytof / greplaydetid buffers of src/mcx_host.cpp:722-737 */
+        c->replay_seed = static_cast<const uint64_t*>(cfg->replay.seed);
+        c->replay_weight = cfg->replay.weight;
+        c->replay_tof = cfg->replay.tof;
+        c->replay_detid = cfg->replay.detid;
+        c->replaydet = cfg->replaydet;
+    }
 }
 
 /* what this build's hot path does not cover is refused loudly, never approximated */
@@ -131,8 +141,8 @@ void check_supported(const Config* cfg) {
         mcx_error(-1, "continuous / SVMC media formats are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
     }
 
-    if (cfg->seed == SEED_FROM_FILE) {
-        mcx_error(-1, "photon replay is outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
+    if (cfg->seed == SEED_FROM_FILE && (cfg->replay.seed == NULL || cfg->outputtype == otRF || cfg->outputtype == otRFmus)) {
+        mcx_error(-1, "RF replay is outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
     }
 
     if (cfg->respin != 1) {
@@ -252,7 +262,13 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
     cfg->maxgate = (unsigned int)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);
     const size_t dimxyz = (size_t)cfg->dim.x * cfg->dim.y * cfg->dim.z;
     const unsigned int nsrcvol = (cfg->extrasrclen && cfg->srcid < 0) ? cfg->extrasrclen + 1 : 1;
-    const size_t fieldlen = dimxyz * cfg->maxgate * nsrcvol;
+    const bool replay = cfg->seed == SEED_FROM_FILE;
+    const unsigned int nrepvol = (replay && cfg->replaydet == -1) ? std::max(1u, cfg->detnum) : 1u;     /* src/mcx_host.cpp:684-689 */
+    const size_t fieldlen = dimxyz * cfg->maxgate * nsrcvol * nrepvol;
+
+    if (replay) {
+        workdev = 1;        /* "replay should only work with a single device" (src/mcx_host.cpp:723) */
+    }
 
     /* workload split (src/mcx_host.cpp:650-662, 1011-1012); the remainder goes to the first devices so
      * that exactly nphoton packets are launched */
@@ -346,6 +362,26 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
             rc = mcxb_sim_launch(sims[i], NULL);
         }
 
+        if ((cfg->debuglevel & MCX_DEBUG_PROGRESS) && rc == MCXB_OK) {
+            /* the -D P bar (src/mcx_host.cpp:1112-1141): the reference polls a mapped counter of device 0 every 100 ms;
+             * here the photon counter of device 0 is copied over a side stream while the kernel runs */
+            mcx_progressbar(-0.f, cfg);
+            int finished = 0;
+
+            while (rc == MCXB_OK && !finished) {
+                uint64_t claimed = 0;
+                rc = mcxb_sim_progress(sims[0], &claimed, &finished);
+
+                if (rc == MCXB_OK && !finished) {
+                    mcx_progressbar((float)((double)claimed / (double)std::max<uint64_t>(1, share[0])), cfg);
+                    sleep_ms(50);
+                }
+            }
+
+            mcx_progressbar(1.0f, cfg);
+            MCX_FPRINTF(cfg->flog, "\n");
+        }
+
         float kernelms = 0.f;
 
         for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
@@ -430,11 +466,38 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         fill_config(cfg, &c);
         MCX_FPRINTF(cfg->flog, "normalizing raw data ...\t");
         cfg->energyabs += cfg->energytot - cfg->energyesc;
-        const float scale = mcxb_normalizer(&c, cfg->energytot);
-        cfg->normalizer = scale;
-        cfg->his.normalizer = scale;
-        MCX_FPRINTF(cfg->flog, "source 1, normalization factor alpha=%f\n", scale);
-        mcx_normalize(cfg->exportfield, scale, (int)fieldlen, cfg->isnormalized, 0, 1);
+        const bool sens = cfg->outputtype == otJacobian || cfg->outputtype == otWP || cfg->outputtype == otDCS ||
+                          cfg->outputtype == otWLTOF || cfg->outputtype == otWPTOF;
+
+        if (replay && sens && cfg->replaydet == -1) {
+            /* every detector at once: one scale per detector volume (src/mcx_host.cpp:1398-1421) */
+            const size_t block = dimxyz * cfg->maxgate;
+
+            for (int detid = 1; detid <= (int)cfg->detnum; detid++) {
+                float scale = 0.f;
+
+                for (size_t i = 0; i < cfg->nphoton; i++) {
+                    if ((cfg->replay.detid[i] & 0xFFFF) == detid) {
+                        scale += cfg->replay.weight[i];
+                    }
+                }
+
+                if (scale > 0.f) {
+                    scale = cfg->unitinmm / scale;
+                }
+
+                cfg->normalizer = scale;
+                cfg->his.normalizer = scale;
+                MCX_FPRINTF(cfg->flog, "normalization factor for detector %d alpha=%f\n", detid, scale);
+                mcx_normalize(cfg->exportfield + (detid - 1) * block, scale, (int)block, cfg->isnormalized, 0, 1);
+            }
+        } else {
+            const float scale = mcxb_normalizer(&c, cfg->energytot);
+            cfg->normalizer = scale;
+            cfg->his.normalizer = scale;
+            MCX_FPRINTF(cfg->flog, "source 1, normalization factor alpha=%f\n", scale);
+            mcx_normalize(cfg->exportfield, scale, (int)fieldlen, cfg->isnormalized, 0, 1);
+        }
     } else {
         cfg->energyabs += cfg->energytot - cfg->energyesc;
     }

@@ -6,7 +6,7 @@ or ``python -m mcxcl_b200.build``) every entry point raises, it never reroutes t
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 DEBUG_RNG = 1
 DEBUG_STATS = 0x10000
 ACCUM_F64, ACCUM_F32 = 0, 1
@@ -75,6 +75,11 @@ class Config(C.Structure):
         ("nblocksize", C.c_uint32),
         ("sched", C.c_int32),
         ("accum", C.c_int32),
+        ("replay_seed", C.POINTER(C.c_uint64)),
+        ("replay_weight", C.POINTER(C.c_float)),
+        ("replay_tof", C.POINTER(C.c_float)),
+        ("replay_detid", C.POINTER(C.c_int32)),
+        ("replaydet", C.c_int32),
     ]
 
 
@@ -130,6 +135,7 @@ SYMBOLS = [
     ("mcxb_sim_create", C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(_VP)]),
     ("mcxb_sim_reset", C.c_int, [_VP, _VP]),
     ("mcxb_sim_launch", C.c_int, [_VP, _VP]),
+    ("mcxb_sim_progress", C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     ("mcxb_sim_set_photons", C.c_int, [_VP, C.c_uint64]),
     ("mcxb_sim_reseed", C.c_int, [_VP, C.c_int32, C.c_uint64]),
     ("mcxb_sim_finalize", C.c_int, [_VP, _VP]),

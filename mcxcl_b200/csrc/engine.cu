@@ -365,6 +365,15 @@ struct mcxb_sim {
     float* d_pattern = nullptr;
     float* d_invcdf = nullptr;
     unsigned long long* d_stats = nullptr;
+    unsigned long long* d_rseed = nullptr;      /* replay inputs */
+    float* d_rweight = nullptr;
+    float* d_rtof = nullptr;
+    int32_t* d_rdetid = nullptr;
+    std::vector<float> h_rweight;                /* host copies for the replay normalisation */
+    std::vector<int32_t> h_rdetid;
+    uint32_t nrepvol = 1;
+    unsigned long long* h_progress = nullptr;   /* pinned word the progress poll copies the photon counter into */
+    cudaStream_t pollstream = nullptr;
     /* pinned staging */
     float* h_field = nullptr;
     double* h_small = nullptr;       /* energy[2], detcount, stats[3] */
@@ -410,7 +419,7 @@ static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t npha
 
     const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
     return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->extrasrclen == 0 && cfg->issaveref == 0 &&
-           !(savedet && cfg->issaveseed > 0) && cfg->issave2pt != 0 &&
+           !(savedet && cfg->issaveseed > 0) && cfg->issave2pt != 0 && cfg->replay_seed == nullptr &&
            (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE);
 }
 
@@ -453,6 +462,17 @@ extern "C" float mcxb_normalizer(const mcxb_config* cfg, double energytot) {
         }
     } else if (cfg->outputtype == MCXB_OT_ENERGY || cfg->outputtype == MCXB_OT_L) {
         scale = (float)(1.0 / energytot);
+    } else if (cfg->replay_weight) {
+        /* sensitivity outputs of a replay: unitinmm / sum of the detected weights (src/mcx_host.cpp:1424-1432) */
+        scale = 0.f;
+
+        for (uint64_t i = 0; i < cfg->nphoton; i++) {
+            scale += cfg->replay_weight[i];
+        }
+
+        if (scale > 0.f) {
+            scale = cfg->unitinmm / scale;
+        }
     }
 
     if (cfg->extrasrclen && cfg->srcid < 0) {
@@ -495,11 +515,16 @@ static void sim_free(mcxb_sim* s) {
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();        /* pooled buffers may be handed out again at once: nothing may still be using them */
     void* bufs[] = { s->d_media, s->d_field, s->d_field32, s->d_tables, s->d_seeds, s->d_det, s->d_detcount, s->d_seedout,
-                     s->d_counter, s->d_energy, s->d_pattern, s->d_invcdf, s->d_stats, s->h_field, s->h_small
+                     s->d_counter, s->d_energy, s->d_pattern, s->d_invcdf, s->d_stats, s->h_field, s->h_small,
+                     s->d_rseed, s->d_rweight, s->d_rtof, s->d_rdetid, s->h_progress
                    };
 
     for (void* b : bufs) {
         pool().put(b);
+    }
+
+    if (s->pollstream) {
+        cudaStreamDestroy(s->pollstream);
     }
 
     if (s->ev0) {
@@ -546,8 +571,35 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         return fail(MCXB_ERR_ARG, "pattern sources need srcpattern");
     }
 
-    if (cfg->outputtype != MCXB_OT_FLUX && cfg->outputtype != MCXB_OT_FLUENCE && cfg->outputtype != MCXB_OT_ENERGY && cfg->outputtype != MCXB_OT_L) {
+    const bool forward_ot = cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE || cfg->outputtype == MCXB_OT_ENERGY ||
+                            cfg->outputtype == MCXB_OT_L;
+    const bool replay_ot = cfg->outputtype == MCXB_OT_JACOBIAN || cfg->outputtype == MCXB_OT_WP || cfg->outputtype == MCXB_OT_DCS ||
+                           cfg->outputtype == MCXB_OT_WLTOF || cfg->outputtype == MCXB_OT_WPTOF;
+
+    if (!forward_ot && !replay_ot) {
         return fail(MCXB_ERR_ARG, "output type %d is outside this build's hot path", cfg->outputtype);
+    }
+
+    if (replay_ot && !cfg->replay_seed) {
+        return fail(MCXB_ERR_ARG, "output type %d needs photon replay (replay_seed)", cfg->outputtype);
+    }
+
+    if (cfg->replay_seed) {
+        if (replay_ot && (!cfg->replay_weight || !cfg->replay_tof)) {
+            return fail(MCXB_ERR_ARG, "replay outputs need replay_weight and replay_tof");
+        }
+
+        if (cfg->replaydet == -1 && replay_ot && (!cfg->replay_detid || cfg->detnum == 0)) {
+            return fail(MCXB_ERR_ARG, "replaydet=-1 needs replay_detid and detectors");
+        }
+
+        if (cfg->nphoton >= 0xFFFFFFFFull) {
+            return fail(MCXB_ERR_ARG, "too many photons to replay");
+        }
+
+        if (cfg->seed_skip) {
+            return fail(MCXB_ERR_ARG, "replay should only work with a single device");       /* src/mcx_host.cpp:723 */
+        }
     }
 
     if (cfg->extrasrclen && !cfg->srcdata) {
@@ -587,6 +639,10 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->cfg.detpos = nullptr;
     s->cfg.invcdf = nullptr;
     s->cfg.angleinvcdf = nullptr;
+    s->cfg.replay_seed = nullptr;
+    s->cfg.replay_weight = nullptr;
+    s->cfg.replay_tof = nullptr;
+    s->cfg.replay_detid = nullptr;
 
     const uint64_t dimxyz = (uint64_t)cfg->dimx * cfg->dimy * cfg->dimz;
     const uint32_t maxgate = count_gates(cfg);
@@ -598,7 +654,9 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     const uint32_t nsrcvol = (cfg->srcid < 0) ? cfg->extrasrclen + 1 : 1;
     s->maxgate = maxgate;
     s->nsrcvol = nsrcvol;
-    s->fieldlen = dimxyz * maxgate * nsrcvol;
+    /* src/mcx_host.cpp:684-689: one volume per detector when every detector is replayed at once */
+    s->nrepvol = (cfg->replay_seed && cfg->replaydet == -1) ? std::max(1u, cfg->detnum) : 1u;
+    s->fieldlen = dimxyz * maxgate * nsrcvol * s->nrepvol;
     s->rngdebug = (cfg->debuglevel & 1u) != 0;
     const bool savedet = cfg->issavedet != 0 && !s->rngdebug;
     const uint32_t flag = savedet ? (cfg->savedetflag & 0x7Fu) : 0u;
@@ -691,6 +749,30 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
 
         CU_TRY(dev_alloc(&s->d_invcdf, device, sizeof(float) * t.size()));
         CU_TRY(cudaMemcpy(s->d_invcdf, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
+    }
+
+    /* ---- replay records (src/mcx_host.cpp:722-737) ---- */
+    if (cfg->replay_seed) {
+        const size_t n = std::max<uint64_t>(cfg->nphoton, 1);
+        CU_TRY(dev_alloc(&s->d_rseed, device, 16 * n));
+        CU_TRY(cudaMemcpy(s->d_rseed, cfg->replay_seed, 16 * (size_t)cfg->nphoton, cudaMemcpyHostToDevice));
+
+        if (cfg->replay_weight) {
+            CU_TRY(dev_alloc(&s->d_rweight, device, 4 * n));
+            CU_TRY(cudaMemcpy(s->d_rweight, cfg->replay_weight, 4 * (size_t)cfg->nphoton, cudaMemcpyHostToDevice));
+            s->h_rweight.assign(cfg->replay_weight, cfg->replay_weight + cfg->nphoton);
+        }
+
+        if (cfg->replay_tof) {
+            CU_TRY(dev_alloc(&s->d_rtof, device, 4 * n));
+            CU_TRY(cudaMemcpy(s->d_rtof, cfg->replay_tof, 4 * (size_t)cfg->nphoton, cudaMemcpyHostToDevice));
+        }
+
+        if (cfg->replay_detid) {
+            CU_TRY(dev_alloc(&s->d_rdetid, device, 4 * n));
+            CU_TRY(cudaMemcpy(s->d_rdetid, cfg->replay_detid, 4 * (size_t)cfg->nphoton, cudaMemcpyHostToDevice));
+            s->h_rdetid.assign(cfg->replay_detid, cfg->replay_detid + cfg->nphoton);
+        }
     }
 
     /* ---- kernel choice and launch shape ---- */
@@ -843,6 +925,12 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     P.seeds = s->d_seeds;
     P.energy = s->d_energy;
     P.stats = stats ? s->d_stats : nullptr;
+    P.replayseed = s->d_rseed;
+    P.replayweight = s->d_rweight;
+    P.replaytof = s->d_rtof;
+    P.replaydetid = s->d_rdetid;
+    P.replaydet = cfg->replaydet;
+    P.nrepvol = s->nrepvol;
     return MCXB_OK;
 }
 
@@ -884,6 +972,10 @@ extern "C" int mcxb_sim_reset(mcxb_sim* s, void* cuda_stream) {
 extern "C" int mcxb_sim_set_photons(mcxb_sim* s, uint64_t nphoton) {
     if (!s) {
         return fail(MCXB_ERR_ARG, "sim is NULL");
+    }
+
+    if (s->d_rseed && nphoton > s->cfg.nphoton) {
+        return fail(MCXB_ERR_ARG, "a replay cannot run more photons than it has records");
     }
 
     s->cfg.nphoton = nphoton;
@@ -930,6 +1022,43 @@ extern "C" int mcxb_sim_launch(mcxb_sim* s, void* cuda_stream) {
     CU_TRY(cudaEventRecord(s->ev1, st));
     s->launches++;
     s->launched = true;
+    return MCXB_OK;
+}
+
+extern "C" int mcxb_sim_progress(mcxb_sim* s, uint64_t* claimed, int* finished) {
+    if (!s) {
+        return fail(MCXB_ERR_ARG, "sim is NULL");
+    }
+
+    CU_TRY(cudaSetDevice(s->device));
+
+    if (!s->pollstream) {
+        /* a non-blocking stream: its copies overlap the running kernel instead of queueing behind it */
+        CU_TRY(cudaStreamCreateWithFlags(&s->pollstream, cudaStreamNonBlocking));
+        CU_TRY(host_alloc(&s->h_progress, sizeof(unsigned long long)));
+    }
+
+    if (finished) {
+        *finished = 1;
+
+        if (s->launched) {
+            const cudaError_t e = cudaEventQuery(s->ev1);
+
+            if (e == cudaErrorNotReady) {
+                *finished = 0;
+            } else if (e != cudaSuccess) {
+                return fail(MCXB_ERR_CUDA_BASE - (int)e, "cudaEventQuery failed: %s", cudaGetErrorString(e));
+            }
+        }
+    }
+
+    if (claimed) {
+        CU_TRY(cudaMemcpyAsync(s->h_progress, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->pollstream));
+        CU_TRY(cudaStreamSynchronize(s->pollstream));
+        /* the counter runs past nphoton by one refill per thread at the end; static scheduling does not use it */
+        *claimed = (s->P.sched == 1) ? ((finished && *finished) ? s->P.nphoton : 0) : std::min<uint64_t>(*s->h_progress, s->P.nphoton);
+    }
+
     return MCXB_OK;
 }
 
@@ -1022,8 +1151,38 @@ extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) 
         const float* src = s->h_field;
         const uint64_t n = s->fieldlen;
 
-        if (s->cfg.isnormalized && !s->rngdebug && out->energytot > 0.0) {     /* nothing launched: leave the zeros alone */
-            const float scale = mcxb_normalizer(&s->cfg, out->energytot);
+        const bool sens = s->d_rseed && s->cfg.outputtype > MCXB_OT_ENERGY && s->cfg.outputtype != MCXB_OT_L;
+
+        if (s->cfg.isnormalized && sens && s->cfg.replaydet == -1) {
+            /* every detector replayed at once: each detector's volumes are scaled by unitinmm / (sum of the weights
+             * detected THERE) (src/mcx_host.cpp:1398-1421) */
+            const uint64_t block = (uint64_t)s->P.dimxyz * s->maxgate;
+
+            for (uint64_t v = 0; v < (uint64_t)s->nsrcvol * s->nrepvol; v++) {
+                const int det = (int)(v % s->nrepvol) + 1;
+                float scale = 0.f;
+
+                for (size_t i = 0; i < s->h_rweight.size() && i < s->P.nphoton; i++) {
+                    if ((s->h_rdetid[i] & 0xFFFF) == det) {
+                        scale += s->h_rweight[i];
+                    }
+                }
+
+                if (scale > 0.f) {
+                    scale = s->cfg.unitinmm / scale;
+                }
+
+                out->normalizer = scale;
+
+                for (uint64_t i = v * block; i < (v + 1) * block; i++) {
+                    dst[i] = (dst[i] + src[i]) * scale;
+                }
+            }
+        } else if (s->cfg.isnormalized && !s->rngdebug && out->energytot > 0.0) {     /* nothing launched: leave the zeros alone */
+            mcxb_config nc = s->cfg;
+            nc.replay_weight = (sens && !s->h_rweight.empty()) ? s->h_rweight.data() : nullptr;
+            nc.nphoton = s->P.nphoton;
+            const float scale = mcxb_normalizer(&nc, out->energytot);
             out->normalizer = scale;
 
             for (uint64_t i = 0; i < n; i++) {

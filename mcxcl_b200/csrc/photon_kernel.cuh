@@ -79,7 +79,16 @@ struct SimParam {
     const uint32_t* seeds;        /* 4 words per thread */
     double*     energy;           /* {escaped, launched} */
     unsigned long long* stats;    /* optional {segments, deposits, scatters} counters, or NULL */
+    /* photon replay (src/mcx_core.cl:1590-1596, 2567-2592, 2845-2858): per-photon RNG state, detected weight, time of
+     * flight and detector of the photons being replayed; replayseed == NULL in a forward run */
+    const unsigned long long* replayseed;
+    const float* replayweight;
+    const float* replaytof;
+    const int*   replaydetid;
+    int32_t      replaydet;
+    uint32_t     nrepvol;         /* volumes per source in replay: detnum when replaydet == -1, else 1 */
 };
+
 
 /* per-photon state that survives across segments */
 struct Photon {
@@ -647,6 +656,8 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
     int   cursrc = 0;                                 /* source the live packet came from (1-based; 0 = single source) */
     uint32_t budget = (P.sched == 1) ? (P.threadphoton + ((int)tid < P.oddphoton ? 1u : 0u)) : 0u;
     uint32_t detarg = 0;                              /* detector argument handed to the retire step */
+    uint32_t nextid = (P.sched == 1) ? (tid * P.threadphoton + min(tid, (uint32_t)P.oddphoton)) : 0u;   /* replay: record of the next packet */
+    uint32_t curid = 0;                               /* replay: record of the live packet */
     bool relaunch = true;
     unsigned long long c_seg = 0, c_dep = 0, c_scat = 0;
 
@@ -660,7 +671,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     int tshift = min((int)P.maxgate - 1, (int)floorf((ph.tof - P.twin0) * P.Rtstep));
 
                     if (P.extrasrclen && P.srcid < 0) {
-                        tshift += (cursrc - 1) * (int)P.maxgate;
+                        tshift += (cursrc - 1) * (int)(P.nrepvol * P.maxgate);
                     }
 
                     red_add(field + ph.idx1d + (size_t)tshift * P.dimxyz, -ph.w);
@@ -692,6 +703,17 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 }
 
                 budget = (uint32_t)min((unsigned long long)P.chunk, P.nphoton - first);
+
+                if (GEN) {
+                    nextid = (uint32_t)first;
+                }
+            }
+
+            /* ------------------------------------------------------------------ replay: restart the stream (:1590-1596) */
+            if (GEN && P.replayseed) {
+                curid = nextid++;
+                rng.a = __ldg(P.replayseed + 2 * (size_t)curid);
+                rng.b = __ldg(P.replayseed + 2 * (size_t)curid + 1);
             }
 
             /* ------------------------------------------------------------------ launch (:1598-2255) */
@@ -709,6 +731,10 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     cursrc = (int)(rng_uniform(rng) * kJustBelowOne * (float)(P.extrasrclen + 1)) + 1;
                     S = srctab + 4 * (cursrc - 1);
                 }
+            }
+
+            if (GEN && P.replayseed && P.srcid >= 1) {
+                (void)rng_uniform(rng);          /* :1614-1616 */
             }
 
             uint32_t rawlabel = 0, rawdet = 0;
@@ -882,6 +908,32 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
                 ph.nscat++;
 
+                /* scattering-site sensitivities of a replayed packet (:2567-2592): WP counts the events, DCS sums the
+                 * momentum transfer 1-cos(theta), WPTOF weights the count by the time of flight; each scaled by the
+                 * detected weight and binned by the DETECTED time of flight */
+                if (GEN && P.replayseed && (P.outputtype == otWP || P.outputtype == otDCS || P.outputtype == otWPTOF)) {
+                    float sw = __ldg(P.replayweight + curid);
+                    const float rtof = __ldg(P.replaytof + curid);
+
+                    if (P.outputtype == otDCS) {
+                        sw *= 1.f - ctheta;
+                    } else if (P.outputtype == otWPTOF) {
+                        sw *= rtof;
+                    }
+
+                    uint32_t tshift = (uint32_t)max(0, min((int)floorf((rtof - P.twin0) * P.Rtstep), (int)P.maxgate - 1));
+
+                    if (P.replaydet == -1) {
+                        tshift += (uint32_t)((__ldg(P.replaydetid + curid) & 0xFFFF) - 1) * P.maxgate;
+                    }
+
+                    if (P.extrasrclen && P.srcid < 0) {
+                        tshift += (uint32_t)(cursrc - 1) * P.nrepvol * P.maxgate;
+                    }
+
+                    red_add(field + ((size_t)tshift * P.dimxyz + ph.idx1d), sw);
+                }
+
                 if (STATS) {
                     c_scat++;
                 }
@@ -952,15 +1004,6 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
         if (ph.idx1d != oldidx) {
             if ((!GEN || P.save2pt) && ph.tof >= P.twin0 && ph.tof < P.twin1) {
                 float weight;
-
-                if (GEN && P.outputtype == otEnergy) {
-                    weight = ph.w0 - ph.w;
-                } else if (GEN && P.outputtype == otL) {
-                    weight = ph.w0 * ph.pathlen;
-                } else {
-                    weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * mufu_rcp(mua));
-                }
-
                 uint32_t tshift = 0;
 
                 if (P.maxgate > 1) {
@@ -968,8 +1011,31 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     tshift = (uint32_t)min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1);
                 }
 
+                if (GEN && P.outputtype == otEnergy) {
+                    weight = ph.w0 - ph.w;
+                } else if (GEN && P.outputtype == otL) {
+                    weight = ph.w0 * ph.pathlen;
+                } else if (GEN && P.outputtype > otEnergy) {
+                    /* replay outputs (:2845-2858): the absorption Jacobian deposits detected weight x path length in
+                     * the voxel just left (WLTOF: additionally x time of flight), binned by the DETECTED time of
+                     * flight and, with replaydet == -1, by detector; WP / DCS / WPTOF deposit at scattering sites */
+                    weight = 0.f;
+
+                    if (P.replayseed && (P.outputtype == otJacobian || P.outputtype == otWLTOF)) {
+                        const float rtof = __ldg(P.replaytof + curid);
+                        weight = __ldg(P.replayweight + curid) * ph.pathlen * (P.outputtype == otWLTOF ? rtof : 1.f);
+                        tshift = (uint32_t)max(0, min((int)floorf((rtof - P.twin0) * P.Rtstep), (int)P.maxgate - 1));
+
+                        if (P.replaydet == -1) {
+                            tshift += (uint32_t)((__ldg(P.replaydetid + curid) & 0xFFFF) - 1) * P.maxgate;
+                        }
+                    }
+                } else {
+                    weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * mufu_rcp(mua));
+                }
+
                 if (GEN && P.extrasrclen && P.srcid < 0) {
-                    tshift += (uint32_t)(cursrc - 1) * P.maxgate;
+                    tshift += (uint32_t)(cursrc - 1) * P.nrepvol * P.maxgate;
                 }
 
                 if (fabsf(weight) > 0.f) {

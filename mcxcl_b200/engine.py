@@ -63,6 +63,12 @@ class Simulation:
         except Exception:
             pass
 
+    def progress(self):
+        """(photons claimed so far, launch finished) without waiting for the kernel -- the `-D P` poll"""
+        n, done = C.c_uint64(0), C.c_int(0)
+        abi.check(self.lib.mcxb_sim_progress(self.h, C.byref(n), C.byref(done)), "mcxb_sim_progress")
+        return int(n.value), bool(done.value)
+
     def set_photons(self, n):
         abi.check(self.lib.mcxb_sim_set_photons(self.h, int(n)), "mcxb_sim_set_photons")
 
@@ -151,7 +157,7 @@ def shape_field(p, field):
     """float32[fieldlen] -> (Nx,Ny,Nz,Ngate[,Nsrc]) view, the layout pmcxcl returns (column-major file order
     [Nx][Ny][Nz][Ng][Ns], README.md:1316-1323)."""
     nx, ny, nz = p.dims
-    shp = (nx, ny, nz, p.maxgate) + ((p.nsrcvol,) if p.nsrcvol > 1 else ())
+    shp = (nx, ny, nz, p.maxgate) + ((p.nrepvol,) if p.nrepvol > 1 else ()) + ((p.nsrcvol,) if p.nsrcvol > 1 else ())
     return field[:p.fieldlen].reshape(shp, order="F")
 
 

@@ -5,7 +5,7 @@ applies the defaults of ``mcx_initcfg`` (src/mcx_utils.c:203-366), the checks of
 (:1822-1964) and the transformations of ``mcx_preprocess`` (:1521-1809) and ``mcx_maskdet``
 (:4085-4198), and returns a `Prepared` object that owns the numpy buffers and the ctypes
 ``mcxb_config`` handed to the C ABI (include/mcxb200.h).  Only what the hot path consumes is
-mirrored; file formats, shapes, replay and polarised input stay with the reference's own host code
+mirrored (including the replay set-up of ``mcx_replayinit``, :1355-1421); file formats, shapes and polarised input stay with the reference's own host code
 (INTEGRATION.md shows how that code binds to the same ABI).
 """
 import ctypes as C
@@ -17,7 +17,12 @@ from . import abi
 
 SRCTYPES = ["pencil", "isotropic", "cone", "gaussian", "planar", "pattern", "fourier", "arcsine", "disk",
             "fourierx", "fourierx2d", "zgaussian", "line", "slit", "pencilarray", "pattern3d", "hyperboloid", "ring"]
-OUTPUTTYPES = {"flux": 0, "fluence": 1, "energy": 2, "length": 7, "x": 0, "f": 1, "e": 2, "l": 7}
+# names of src/pmcxcl.cpp:854-872 (wl -> jacobian, wp -> nscat, wm = momentum transfer) and the -O letters of src/mcx_utils.c:143
+OUTPUTTYPES = {"flux": 0, "fluence": 1, "energy": 2, "jacobian": 3, "wl": 3, "nscat": 4, "wp": 4, "wm": 5, "length": 7, "wltof": 9, "wptof": 10,
+               "x": 0, "f": 1, "e": 2, "j": 3, "p": 4, "m": 5, "l": 7, "t": 9, "b": 10}
+REPLAY_OUTPUTS = (3, 4, 5, 9, 10)
+SEED_FROM_FILE = -999        # src/mcx_const.h
+R_C0 = np.float32(3.335640951981520e-12)   # 1/c0 in s/mm
 BC_CODES = "_ramc"           # boundarycond[] (src/mcx_utils.c:170)
 SAVEFLAGS = "DSPMXVWI"       # saveflag[]     (src/mcx_utils.c:134)
 DET_MASK = 0x80000000
@@ -163,8 +168,12 @@ class Prepared:
         return self.c.extrasrclen + 1 if self.c.srcid < 0 else 1
 
     @property
+    def nrepvol(self):
+        return max(1, self.c.detnum) if (bool(self.c.replay_seed) and self.c.replaydet == -1) else 1
+
+    @property
     def fieldlen(self):
-        return self.dimxyz * self.maxgate * self.nsrcvol
+        return self.dimxyz * self.maxgate * self.nsrcvol * self.nrepvol
 
     @property
     def partialdata(self):
@@ -222,7 +231,23 @@ def prepare(cfg):
     c.tend = float(cfg.get("tend", 5e-9))
     c.tstep = float(cfg.get("tstep", 5e-9))
     c.nphoton = int(cfg.get("nphoton", 0))
-    c.seed = int(cfg.get("seed", 0x623F9A9E))
+    c.replaydet = int(cfg.get("replaydet", 0))
+    seedval = cfg.get("seed", 0x623F9A9E)
+    replayseed = None
+    if isinstance(seedval, np.ndarray) and seedval.ndim == 2:
+        # an array of saved RNG states = photon replay (src/pmcxcl.cpp:1019-1048): 16 bytes per photon
+        sv = np.asarray(seedval)
+        if sv.dtype == np.uint64 and sv.shape[1] == 2:
+            replayseed = np.ascontiguousarray(sv).copy()
+        else:
+            sv = sv.astype(np.uint8, copy=False)
+            if sv.shape[0] != 16:
+                raise ConfigError(-6, "the row number of cfg.seed does not match RNG seed byte-length")
+            replayseed = np.ascontiguousarray(sv.T).copy().view(np.uint64).reshape(-1, 2)
+        c.seed = SEED_FROM_FILE
+        cfg = dict(cfg, nphoton=replayseed.shape[0])
+    else:
+        c.seed = int(seedval)
     c.seed_skip = int(cfg.get("seed_skip", 0))
     c.isreflect = int(cfg.get("isreflect", 1))
     c.isnormalized = int(cfg.get("isnormalized", 1))
@@ -255,6 +280,8 @@ def prepare(cfg):
             raise ConfigError(-6, "output type %r is outside the photon-transport hot path of this build" % ot)
         ot = OUTPUTTYPES[ot.lower()]
     c.outputtype = int(ot)
+    if c.outputtype in REPLAY_OUTPUTS and replayseed is None:
+        raise ConfigError(-6, "output type %r needs photon replay: pass the saved seeds as cfg['seed'] and cfg['detphotons']" % (ot,))
     st = cfg.get("srctype", "pencil")
     if isinstance(st, str):
         if st not in SRCTYPES:
@@ -377,4 +404,47 @@ def prepare(cfg):
         c.srcpattern_len = pat.size
         if c.srctype == 5 and pat.size < int(srcp1[0, 3]) * int(srcp2[0, 3]):
             raise ConfigError(-4, "srcpattern is smaller than srcparam1.w x srcparam2.w")
+    if replayseed is not None:
+        _replayinit(p, cfg, replayseed, prop)
     return p
+
+
+def _replayinit(p, cfg, seeds, prop):
+    """mcx_replayinit (src/mcx_utils.c:1355-1421): keep the records of the replayed detector (and source), derive each
+    photon's detected weight and time of flight from its partial paths.  `prop` is already scaled by unitinmm."""
+    c = p.c
+    detps = cfg.get("detphotons")
+    if detps is None:
+        raise ConfigError(-6, "you give cfg.seed for replay, but did not specify cfg.detphotons.")
+    detps = np.asarray(detps.get("data") if isinstance(detps, dict) else detps, dtype=np.float32)
+    if detps.ndim != 2 or detps.shape[1] != seeds.shape[0]:
+        raise ConfigError(-6, "the column numbers of detphotons and seed do not match")
+    flag = parse_savedetflag(cfg.get("savedetflag", 0x5)) or 0x5
+    hasdetid = flag & 1
+    nmed = c.medianum - 1
+    if (not hasdetid and c.detnum > 1) or not (flag >> 2 & 1):
+        raise ConfigError(-6, "please rerun the baseline simulation and save detector ID (D) and partial-path (P) using cfg.savedetflag='dp'")
+    offset = (flag >> 1 & 1) * nmed
+    ids = detps[0].astype(np.int32) if hasdetid else np.ones(detps.shape[1], np.int32)
+    keep = np.ones(detps.shape[1], bool)
+    if c.replaydet > 0:
+        keep &= (ids & 0xFFFF) == c.replaydet
+    if c.srcid > 0:
+        keep &= ((ids >> 16) & 0xFFFF) == c.srcid
+    plen = detps[offset + hasdetid: offset + hasdetid + nmed].astype(np.float32)          # (nmed, N), voxel units
+    weight = np.ones(detps.shape[1], np.float32)
+    tof = np.zeros(detps.shape[1], np.float32)
+    for j in range(nmed):
+        weight *= np.exp(-prop[j + 1, 0] * plen[j]).astype(np.float32)
+        tof += plen[j] * np.float32(c.unitinmm) * R_C0 * prop[j + 1, 3]
+    keep &= ~((tof < np.float32(c.tstart)) | (tof > np.float32(c.tend)))
+    rs = np.ascontiguousarray(seeds[keep])
+    rw = np.ascontiguousarray(weight[keep])
+    rt = np.ascontiguousarray(tof[keep])
+    rd = np.ascontiguousarray(ids[keep].astype(np.int32))
+    p.keep.update(replay_seed=rs, replay_weight=rw, replay_tof=rt, replay_detid=rd)
+    c.nphoton = rs.shape[0]
+    c.replay_seed = rs.ctypes.data_as(C.POINTER(C.c_uint64))
+    c.replay_weight = rw.ctypes.data_as(C.POINTER(C.c_float))
+    c.replay_tof = rt.ctypes.data_as(C.POINTER(C.c_float))
+    c.replay_detid = rd.ctypes.data_as(C.POINTER(C.c_int32))

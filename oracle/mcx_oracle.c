@@ -1277,6 +1277,10 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
         return -1;
     }
 
+    if (cfg->replay_seed) {
+        return -3;      /* photon replay is not restated here: oracle/_ref (the reference source itself) checks it */
+    }
+
     param_t g;
     memset(&g, 0, sizeof(g));
     g.cfg = cfg;

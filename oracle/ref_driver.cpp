@@ -27,13 +27,13 @@ namespace refd {
 
 typedef void (*ref_kernel_fn)(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*,
                               const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*,
-                              void*, const void*);
+                              void*, const void*, float*, float*, int*);
 
 #define REF_DECL(name) \
-    extern "C" void mcxref_kernel_##name##_r0_d0(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*); \
-    extern "C" void mcxref_kernel_##name##_r1_d0(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*); \
-    extern "C" void mcxref_kernel_##name##_r0_d1(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*); \
-    extern "C" void mcxref_kernel_##name##_r1_d1(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*);
+    extern "C" void mcxref_kernel_##name##_r0_d0(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*); \
+    extern "C" void mcxref_kernel_##name##_r1_d0(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*); \
+    extern "C" void mcxref_kernel_##name##_r0_d1(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*); \
+    extern "C" void mcxref_kernel_##name##_r1_d1(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*);
 #define REF_ROW(name) { mcxref_kernel_##name##_r0_d0, mcxref_kernel_##name##_r1_d0, mcxref_kernel_##name##_r0_d1, mcxref_kernel_##name##_r1_d1 }
 
 REF_DECL(pencil) REF_DECL(isotropic) REF_DECL(cone) REF_DECL(gaussian) REF_DECL(planar) REF_DECL(pattern)
@@ -97,7 +97,17 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     const unsigned int maxgate = (unsigned int)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);
     const unsigned int nsrcvol = (cfg->srctype == MCXB_SRC_PATTERN || cfg->srctype == MCXB_SRC_PATTERN3D) ? cfg->srcnum
                                  : ((cfg->srcid < 0) ? (cfg->extrasrclen + 1) : 1);
-    const size_t fieldlen = (size_t)dimxyz * maxgate * nsrcvol;
+    /* photon replay (src/mcx_host.cpp:684-689, 722-737): one volume per detector when replaydet == -1.  The
+     * reference maps work-item t to record t*threadphoton + min(t, oddphoton-1) + k (src/mcx_core.cl:1591), which
+     * is the identity only when every work-item owns at most one photon, so a replay runs with nphoton+1 work-items */
+    const bool replay = cfg->replay_seed != NULL;
+    const unsigned int nrepvol = (replay && cfg->replaydet == -1) ? (cfg->detnum ? cfg->detnum : 1) : 1;
+
+    if (replay) {
+        nthread = (uint32_t)cfg->nphoton + 1;
+    }
+
+    const size_t fieldlen = (size_t)dimxyz * maxgate * nsrcvol * nrepvol;
 
     const unsigned int flag = cfg->issavedet ? cfg->savedetflag : 0;
     const unsigned int partialdata = (cfg->medianum - 1) * (SAVE_NSCAT(flag) + SAVE_PPATH(flag) + SAVE_MOM(flag));
@@ -144,7 +154,8 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     param.issaveref = (uint)cfg->issaveref;
     param.isspecular = cfg->isspecular > 0;
     param.maxgate = maxgate;
-    param.seed = cfg->seed;
+    param.seed = replay ? -999 /* SEED_FROM_FILE */ : cfg->seed;
+    param.replaydet = cfg->replaydet;
     param.outputtype = (uint)cfg->outputtype;
     param.threadphoton = (uint)(cfg->nphoton / nthread);
     param.oddphoton = (int)(cfg->nphoton - (uint64_t)param.threadphoton * nthread);
@@ -184,8 +195,15 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
         gdetpos[i] = to_f4(cfg->detpos[i]);
     }
 
-    std::vector<uint32_t> seeds((size_t)nthread * 4);
-    mcxref_seeds(cfg->seed, cfg->seed_skip, nthread, seeds.data());
+    std::vector<uint32_t> seeds((size_t)nthread * 4 + 4);
+
+    if (replay) {
+        /* gseed holds the recorded RNG states (src/mcx_host.cpp:724); gpu_rng_init still reads one record per work-item */
+        memset(seeds.data(), 0, seeds.size() * 4);
+        memcpy(seeds.data(), cfg->replay_seed, 16 * (size_t)cfg->nphoton);
+    } else {
+        mcxref_seeds(cfg->seed, cfg->seed_skip, nthread, seeds.data());
+    }
 
     const ref_kernel_fn kern = ref_kernels[cfg->srctype][(ref_needs_reflection(cfg) ? 1 : 0) + (cfg->issavedet ? 2 : 0)];
 
@@ -232,7 +250,8 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
             kern(cfg->vol, tfield[tid].data(), genergy.data(), seeds.data(),
                  cfg->issavedet ? tdet[tid].data() : NULL, gproperty.data(), (float*)cfg->srcpattern,
                  gdetpos.data(), &progress, &tdetcount[tid],
-                 cfg->issaveseed ? tseed[tid].data() : NULL, (float*)cfg->invcdf, (float*)cfg->angleinvcdf, shared.data(), &param);
+                 cfg->issaveseed ? tseed[tid].data() : NULL, (float*)cfg->invcdf, (float*)cfg->angleinvcdf, shared.data(), &param,
+                 (float*)cfg->replay_weight, (float*)cfg->replay_tof, (int*)cfg->replay_detid);
         }
 
         cnt_seg[tid] = clshim_cnt_isgreater;
@@ -278,7 +297,7 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     res->energytot = etot;
     res->energyesc = eesc;
 
-    if (res->energy) {
+    if (res->energy && !replay) {       /* the caller sized this buffer for ITS work-item count */
         memcpy(res->energy, genergy.data(), sizeof(float) * 2 * nthread);
     }
 

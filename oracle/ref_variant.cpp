@@ -24,11 +24,12 @@ extern "C" void REF_CAT(mcxref_kernel_, REF_SUFFIX)(
     const unsigned int* media, float* field, float* genergy, unsigned int* n_seed,
     float* n_det, const void* gproperty, float* srcpattern, const void* gdetpos,
     volatile unsigned int* gprogress, unsigned int* detectedphoton,
-    unsigned long* gseeddata, float* ginvcdf, float* gangleinvcdf, void* sharedmem, const void* gcfg) {
+    unsigned long* gseeddata, float* ginvcdf, float* gangleinvcdf, void* sharedmem, const void* gcfg,
+    float* replayweight, float* photontof, int* photondetid) {
     using namespace REF_CAT(refk_, REF_SUFFIX);
     mcx_main_loop(media, field, genergy, n_seed, n_det, (const float4*)gproperty, srcpattern,
                   (const float4*)gdetpos, gprogress, detectedphoton,
-                  /*replayweight*/ NULL, /*photontof*/ NULL, /*photondetid*/ NULL,
+                  replayweight, photontof, photondetid,
                   (RandType*)gseeddata, /*gjumpdebug*/ NULL, /*gdebugdata*/ NULL,
                   ginvcdf, gangleinvcdf, (RandType*)sharedmem, /*gsmatrix*/ NULL,
                   (const MCXParam*)gcfg);

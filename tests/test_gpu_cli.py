@@ -72,6 +72,53 @@ def test_boundary_detector_flags(tmp_path):
     assert rc == 0 and m and 9700 <= int(m.group(1)) <= 9999
 
 
+def test_saving_photon_seeds_jnii(tmp_path):
+    """test/testmcx.sh:116-118: `--bench cube60 -q 1 -F jnii -S 0` prints 'after encoding: 13x.x%' for the seed block"""
+    rc, out = mcx(["--bench", "cube60", "-q", "1", "-F", "jnii", "-S", "0", "-n", "1e5"], tmp_path)
+    assert rc == 0 and re.search(r"after encoding: 13[0-9]\.[0-9]+%", out), out[-1500:]
+
+
+def test_photon_replay_through_the_cli(tmp_path):
+    """test/testmcx.sh:120-128: a baseline run saves seeds into replaytest_detp.jdat, `-E` replays them: the replay
+    simulates and detects exactly the photons the baseline detected, and absorbs 3[0-8].x %"""
+    rc, out1 = mcx(["--bench", "cube60", "-s", "replaytest", "-q", "1", "-S", "0", "-n", "1e5"], tmp_path)
+    assert rc == 0, out1[-2000:]
+    rc, out2 = mcx(["--bench", "cube60", "-E", "replaytest_detp.jdat", "-S", "0", "-n", "1e5"], tmp_path)
+    assert rc == 0, out2[-2000:]
+    nums = re.findall(r"(?:simulated|detected)\s+([0-9.]+) photons", out1 + out2)[-2:]
+    assert len(nums) == 2 and nums[0] == nums[1], (nums, out2[-1500:])
+    assert re.search(r"absorbed:.*3[0-8]\.[0-9]+%", out2), out2[-1500:]
+    base = int(re.search(r"detected\s+([0-9]+) photons", out1).group(1))
+    assert int(float(nums[0])) == base
+
+
+def test_replay_jacobian_through_the_cli(tmp_path):
+    """`-E seeds -O J`: the absorption Jacobian of the replayed photons, written by the reference's writer; its integral
+    times the normaliser's inverse is sum_i w_i L_i, i.e. positive and finite, with one time gate"""
+    rc, out1 = mcx(["--bench", "cube60", "-s", "rj", "-q", "1", "-S", "0", "-n", "1e5"], tmp_path)
+    assert rc == 0
+    rc, out2 = mcx(["--bench", "cube60", "-E", "rj_detp.jdat", "-O", "J", "-F", "mc2", "-s", "rjout", "-n", "1e5"], tmp_path)
+    assert rc == 0, out2[-2000:]
+    jac = np.fromfile(os.path.join(tmp_path, "rjout.mc2"), dtype=np.float32)
+    assert jac.size == 216000 and np.isfinite(jac).all() and jac.min() >= 0 and jac.sum() > 0
+    # normalised by unitinmm / sum(w): the integral is the weighted mean path length of the detected photons (mm)
+    assert 20 < jac.astype(np.float64).sum() < 200
+
+
+def test_detected_photon_flags_w(tmp_path):
+    """test/testmcx.sh:134-136: `-w dspxvw -F jnii` writes six compressed blocks (detid, nscat, ppath, p, v, w0)"""
+    rc, out = mcx(["--bench", "cube60", "-w", "dspxvw", "-F", "jnii", "-S", "0", "-n", "1e5"], tmp_path)
+    assert rc == 0 and len(re.findall(r"compressing data \[zlib\]", out)) == 6, out[-1500:]
+
+
+def test_progress_bar(tmp_path):
+    """test/testmcx.sh:138-140: `-D P` ends with 'Progress: [...] 100%'"""
+    rc, out = mcx(["--bench", "cube60", "-D", "P", "-n", "2e7", "-S", "0", "-d", "0"], tmp_path)
+    assert rc == 0 and re.search(r"Progress: .* 100%", out), out[-800:]
+    shown = sorted(set(int(x) for x in re.findall(r"\]\s+([0-9]+)%", out)))
+    assert shown[-1] == 100 and len(shown) > 2           # intermediate values were drawn while the kernel ran
+
+
 def test_unsupported_modes_fail_loudly(tmp_path):
     rc, out = mcx(["--bench", "cube60", "-n", "1e4", "-r", "2", "-S", "0"], tmp_path)
     assert rc != 0 and "respin" in out

@@ -104,3 +104,24 @@ def test_errors_surface_as_python_exceptions():
     # a device that does not exist is not an error in the reference: it prints a notice and returns nothing
     # (src/pmcxcl.cpp:1147-1152)
     assert len(m.run(cube60(gpuid=9))) == 0
+
+
+@pytest.mark.gpu
+def test_replay_through_the_unchanged_front_end():
+    """baseline with issaveseed -> res['seeds'] (16 x N bytes) and res['detp']; then cfg['seed'] = seeds, cfg['detphotons']
+    = detp, outputtype 'jacobian' (src/pmcxcl.cpp:1006-1048; mcx_replayinit src/mcx_utils.c:1355-1421)"""
+    m = load_module()
+    base = m.run(cube60(issaveseed=1, savedetflag="dp", nphoton=300000))
+    seeds, detp = base["seeds"], base["detp"]
+    n = detp.shape[1]
+    assert seeds.shape == (16, n) and n > 700
+    rep = m.run(cube60(seed=seeds, detphotons=detp, savedetflag="dp", nphoton=300000))
+    assert rep["detp"].shape[1] == n                                   # every replayed photon is detected again
+    assert abs(rep["stat"]["energytot"] - n) < 1e-3
+    jac = m.run(cube60(seed=seeds, detphotons=detp, savedetflag="dp", outputtype="jacobian", nphoton=300000))["flux"]
+    mine = engine.run(cube60(seed=seeds, detphotons=detp, savedetflag="dp", outputtype="jacobian", nphoton=300000))["flux"]
+    assert jac.shape == mine.shape == (60, 60, 60, 1)
+    # same records, same streams, same kernel: only the order of the floating-point accumulation differs
+    np.testing.assert_allclose(jac.astype(np.float64).sum(), mine.astype(np.float64).sum(), rtol=1e-5)
+    w = np.exp(-0.005 * detp[1] - 0.002 * detp[2])
+    np.testing.assert_allclose(jac.astype(np.float64).sum(), float((w * (detp[1] + detp[2])).sum() / w.sum()), rtol=1e-4)
