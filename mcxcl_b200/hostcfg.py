@@ -442,7 +442,7 @@ def _replayinit(p, cfg, seeds, prop):
     rw = np.ascontiguousarray(weight[keep])
     rt = np.ascontiguousarray(tof[keep])
     rd = np.ascontiguousarray(ids[keep].astype(np.int32))
-    p.keep.update(replay_seed=rs, replay_weight=rw, replay_tof=rt, replay_detid=rd)
+    p.keep.update(replay_seed=rs, replay_weight=rw, replay_tof=rt, replay_detid=rd, replay_index=np.nonzero(keep)[0])
     c.nphoton = rs.shape[0]
     c.replay_seed = rs.ctypes.data_as(C.POINTER(C.c_uint64))
     c.replay_weight = rw.ctypes.data_as(C.POINTER(C.c_float))

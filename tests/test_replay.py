@@ -40,6 +40,7 @@ def expected_sums(p, detp):
     """per-photon records -> the right-hand sides of the identities in the module docstring (media 1..M)"""
     M = p.c.medianum - 1
     w = p.keep["replay_weight"].astype(np.float64)
+    detp = detp[p.keep["replay_index"]]         # mcx_replayinit drops records outside the time window (src/mcx_utils.c:1408-1411)
     # the scattering counts are uint32 bit patterns inside the float record (src/mcx_core.cl:2503-2520)
     nscat = np.ascontiguousarray(detp[:, 1:1 + M]).view(np.uint32).astype(np.float64)
     plen, mom = detp[:, 1 + M:1 + 2 * M], detp[:, 1 + 2 * M:1 + 3 * M]
@@ -117,10 +118,12 @@ def test_gpu_replay_retraces_every_photon(gpu_base):
     cfg, base = gpu_base
     p = hostcfg.prepare(replay_cfg(cfg, base["detp"], base["seeds"], issaveseed=1))
     rep = engine.run_prepared(p)
-    assert rep["energytot"] == p.c.nphoton == base["detected"]
-    assert rep["detected"] == base["detected"]
-    assert np.array_equal(sort_rows(base["detp"]), sort_rows(rep["detp"]))
-    assert np.array_equal(sort_rows(base["seeds"].astype(np.int64)), sort_rows(rep["seeds"].astype(np.int64)))
+    kept = p.keep["replay_index"]               # all but the odd record whose time of flight rounds past tend
+    assert base["detected"] - 3 <= p.c.nphoton == len(kept) <= base["detected"]
+    assert rep["energytot"] == p.c.nphoton
+    assert rep["detected"] == p.c.nphoton
+    assert np.array_equal(sort_rows(base["detp"][kept]), sort_rows(rep["detp"]))
+    assert np.array_equal(sort_rows(base["seeds"][kept].astype(np.int64)), sort_rows(rep["seeds"].astype(np.int64)))
     assert 0.30 <= rep["absorbed"] < 0.39
 
 
@@ -171,7 +174,7 @@ def test_gpu_replay_of_every_detector_at_once_and_time_gates(gpu_base):
     out = engine.run_prepared(p)
     vol = out["field"].astype(np.float64).reshape(4, 5, 216000)
     w, tof, det = p.keep["replay_weight"].astype(np.float64), p.keep["replay_tof"], p.keep["replay_detid"]
-    plen = base["detp"][:, 3:5].sum(axis=1)
+    plen = base["detp"][p.keep["replay_index"], 3:5].sum(axis=1)
     gate = np.minimum(np.floor(tof / np.float32(1e-9)).astype(int), 4)
     for d in range(1, 5):
         for g in range(5):
