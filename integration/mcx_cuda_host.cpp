@@ -261,7 +261,8 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
 
     cfg->maxgate = (unsigned int)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);
     const size_t dimxyz = (size_t)cfg->dim.x * cfg->dim.y * cfg->dim.z;
-    const unsigned int nsrcvol = (cfg->extrasrclen && cfg->srcid < 0) ? cfg->extrasrclen + 1 : 1;
+    const bool sharing = cfg->srctype == MCX_SRC_PATTERN && cfg->srcnum > 1;      /* photon sharing: one volume per pattern */
+    const unsigned int nsrcvol = sharing ? cfg->srcnum : ((cfg->extrasrclen && cfg->srcid < 0) ? cfg->extrasrclen + 1 : 1);
     const bool replay = cfg->seed == SEED_FROM_FILE;
     const unsigned int nrepvol = (replay && cfg->replaydet == -1) ? std::max(1u, cfg->detnum) : 1u;     /* src/mcx_host.cpp:684-689 */
     const size_t fieldlen = dimxyz * cfg->maxgate * nsrcvol * nrepvol;
@@ -460,6 +461,8 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         return;
     }
 
+    std::vector<float> srcpw, srcetot, srceabs;
+
     /* ---- normalise once with the global launched energy (:1382-1465) ---- */
     if (cfg->issave2pt && cfg->isnormalized && !(cfg->debuglevel & MCX_DEBUG_RNG) && cfg->energytot > 0.0) {
         mcxb_config c;
@@ -490,6 +493,48 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
                 cfg->his.normalizer = scale;
                 MCX_FPRINTF(cfg->flog, "normalization factor for detector %d alpha=%f\n", detid, scale);
                 mcx_normalize(cfg->exportfield + (detid - 1) * block, scale, (int)block, cfg->isnormalized, 0, 1);
+            }
+        } else if (sharing) {
+            /* per-pattern totals and scales, the reference's post-processing (src/mcx_host.cpp:1351-1380, 1436-1462) */
+            const unsigned int psize = (unsigned int)((int)cfg->srcparam1.w * (int)cfg->srcparam2.w);
+            const float ref = mcxb_normalizer(&c, cfg->energytot);
+            srcpw.assign(cfg->srcnum, 0.f);
+            srcetot.assign(cfg->srcnum, 0.f);
+            srceabs.assign(cfg->srcnum, 0.f);
+
+            for (unsigned int i = 0; i < cfg->srcnum; i++) {
+                float kahanc = 0.f;
+
+                for (unsigned int j = 0; j < psize; j++) {
+                    mcx_kahanSum(&srcpw[i], &kahanc, cfg->srcpattern[j * cfg->srcnum + i]);
+                }
+
+                srcetot[i] = cfg->nphoton * srcpw[i] / (float)psize;
+                kahanc = 0.f;
+
+                if (cfg->outputtype == otEnergy) {
+                    for (size_t j = 0; j < fieldlen / cfg->srcnum; j++) {
+                        mcx_kahanSum(&srceabs[i], &kahanc, cfg->exportfield[j * cfg->srcnum + i]);
+                    }
+                } else {
+                    for (unsigned int j = 0; j < cfg->maxgate; j++) {
+                        for (size_t k = 0; k < dimxyz; k++) {
+                            mcx_kahanSum(&srceabs[i], &kahanc, cfg->exportfield[(j * dimxyz + k) * cfg->srcnum + i] * mcx_updatemua((unsigned int)cfg->vol[k], cfg));
+                        }
+                    }
+                }
+            }
+
+            for (unsigned int i = 0; i < cfg->srcnum; i++) {
+                const float scale = psize / srcpw[i] * ref;
+
+                if (i == 0) {
+                    cfg->normalizer = scale;
+                    cfg->his.normalizer = scale;
+                }
+
+                MCX_FPRINTF(cfg->flog, "source %d, normalization factor alpha=%f\n", i + 1, scale);
+                mcx_normalize(cfg->exportfield, scale, (int)(fieldlen / cfg->srcnum), cfg->isnormalized, i, cfg->srcnum);
             }
         } else {
             const float scale = mcxb_normalizer(&c, cfg->energytot);
@@ -528,8 +573,15 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
 
     MCX_FPRINTF(cfg->flog, "simulated %zu photons (%zu) with %d devices (repeat x%d)\nMCX simulation speed: " S_BOLD S_BLUE "%.2f photon/ms" S_RESET "\n",
                 cfg->nphoton, cfg->nphoton, workdev, cfg->respin, (double)cfg->nphoton / std::max(1u, cfg->runtime));
-    MCX_FPRINTF(cfg->flog, "total simulated energy: %.2f\tabsorbed: " S_BOLD S_BLUE "%5.5f%%" S_RESET "\n(loss due to initial specular reflection is excluded in the total)\n",
-                cfg->energytot, (cfg->energytot - cfg->energyesc) / cfg->energytot * 100.f);
+    if (sharing && !srcetot.empty()) {
+        for (unsigned int i = 0; i < cfg->srcnum; i++) {       /* src/mcx_host.cpp:1681-1688 */
+            MCX_FPRINTF(cfg->flog, "source #%d total simulated energy: %.2f\tabsorbed: " S_BOLD S_BLUE "%5.5f%%" S_RESET "\n(loss due to initial specular reflection is excluded in the total)\n",
+                        i + 1, srcetot[i], srceabs[i] / srcetot[i] * 100.f);
+        }
+    } else {
+        MCX_FPRINTF(cfg->flog, "total simulated energy: %.2f\tabsorbed: " S_BOLD S_BLUE "%5.5f%%" S_RESET "\n(loss due to initial specular reflection is excluded in the total)\n",
+                    cfg->energytot, (cfg->energytot - cfg->energyesc) / cfg->energytot * 100.f);
+    }
     mcx_flush(cfg);
     free(gpu);
 }

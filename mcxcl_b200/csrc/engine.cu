@@ -369,6 +369,7 @@ struct mcxb_sim {
     float* d_rweight = nullptr;
     float* d_rtof = nullptr;
     int32_t* d_rdetid = nullptr;
+    std::vector<float> h_srcpw;                  /* photon sharing: sum of each pattern (src/mcx_host.cpp:1357-1362) */
     std::vector<float> h_rweight;                /* host copies for the replay normalisation */
     std::vector<int32_t> h_rdetid;
     uint32_t nrepvol = 1;
@@ -419,7 +420,7 @@ static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t npha
 
     const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
     return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->extrasrclen == 0 && cfg->issaveref == 0 &&
-           !(savedet && cfg->issaveseed > 0) && cfg->issave2pt != 0 && cfg->replay_seed == nullptr &&
+           !(savedet && cfg->issaveseed > 0) && cfg->issave2pt != 0 && cfg->replay_seed == nullptr && cfg->srcnum <= 1 &&
            (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE);
 }
 
@@ -564,7 +565,23 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     }
 
     if (cfg->srcnum > 1) {
-        return fail(MCXB_ERR_ARG, "photon-sharing pattern sources (srcnum>1) are outside this build's hot path");
+        /* photon sharing: the reference's host only completes it for the 2-D pattern source (its per-pattern sums
+         * srcpw[] are computed for MCX_SRC_PATTERN alone, src/mcx_host.cpp:1351-1364, and dereferenced for both) */
+        if (cfg->srctype != MCXB_SRC_PATTERN) {
+            return fail(MCXB_ERR_ARG, "photon sharing (srcnum>1) needs the 'pattern' source type");
+        }
+
+        if (cfg->extrasrclen) {
+            return fail(MCXB_ERR_ARG, "simulating multiple sources currently can not be used with photon-sharing");    /* src/mcx_utils.c:1660 */
+        }
+
+        if (cfg->issaveref || cfg->replay_seed) {
+            return fail(MCXB_ERR_ARG, "photon sharing cannot be combined with issaveref or replay in this build");
+        }
+
+        if (cfg->srcpattern_len < (uint64_t)cfg->src.param1.w * (uint64_t)cfg->src.param2.w * cfg->srcnum) {
+            return fail(MCXB_ERR_ARG, "srcpattern is smaller than srcparam1.w x srcparam2.w x srcnum");
+        }
     }
 
     if ((cfg->srctype == MCXB_SRC_PATTERN || cfg->srctype == MCXB_SRC_PATTERN3D) && (!cfg->srcpattern || cfg->srcpattern_len == 0)) {
@@ -651,7 +668,8 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         return fail(MCXB_ERR_ARG, "incorrect time gate settings");
     }
 
-    const uint32_t nsrcvol = (cfg->srcid < 0) ? cfg->extrasrclen + 1 : 1;
+    /* output volumes: one per pattern with photon sharing, one per source with srcid < 0 (src/mcx_host.cpp:679) */
+    const uint32_t nsrcvol = (cfg->srcnum > 1) ? cfg->srcnum : ((cfg->srcid < 0) ? cfg->extrasrclen + 1 : 1);
     s->maxgate = maxgate;
     s->nsrcvol = nsrcvol;
     /* src/mcx_host.cpp:684-689: one volume per detector when every detector is replayed at once */
@@ -727,6 +745,25 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
 
         CU_TRY(dev_alloc(&s->d_tables, device, sizeof(float4) * tablen));
         CU_TRY(cudaMemcpy(s->d_tables, tab.data(), sizeof(float4) * tablen, cudaMemcpyHostToDevice));
+    }
+
+    if (cfg->srcnum > 1) {
+        /* Kahan sums like mcx_kahanSum (src/mcx_host.cpp:1357-1362) */
+        const uint64_t psize = (uint64_t)cfg->src.param1.w * (uint64_t)cfg->src.param2.w;
+        s->h_srcpw.assign(cfg->srcnum, 0.f);
+
+        for (uint32_t i = 0; i < cfg->srcnum; i++) {
+            float sum = 0.f, kc = 0.f;
+
+            for (uint64_t j = 0; j < psize; j++) {
+                const float y = cfg->srcpattern[j * cfg->srcnum + i] - kc;
+                const float t = sum + y;
+                kc = (t - sum) - y;
+                sum = t;
+            }
+
+            s->h_srcpw[i] = sum;
+        }
     }
 
     if (cfg->srcpattern && cfg->srcpattern_len) {
@@ -1177,6 +1214,23 @@ extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) 
                 for (uint64_t i = v * block; i < (v + 1) * block; i++) {
                     dst[i] = (dst[i] + src[i]) * scale;
                 }
+            }
+        } else if (s->cfg.isnormalized && s->cfg.srcnum > 1 && out->energytot > 0.0) {
+            /* photon sharing: pattern i is scaled by psize / sum(pattern i) (src/mcx_host.cpp:1436-1447); the volumes
+             * are interleaved pattern-fastest, as mcx_normalize(field, scale, n, op, i, srcnum) walks them */
+            const float ref = mcxb_normalizer(&s->cfg, out->energytot);
+            const float psize = (float)((int)s->cfg.src.param1.w * (int)s->cfg.src.param2.w);
+            const uint32_t ns = s->cfg.srcnum;
+            std::vector<float> scale(ns);
+
+            for (uint32_t i = 0; i < ns; i++) {
+                scale[i] = psize / s->h_srcpw[i] * ref;
+            }
+
+            out->normalizer = scale[0];
+
+            for (uint64_t i = 0; i < n; i++) {
+                dst[i] = (dst[i] + src[i]) * scale[i % ns];
             }
         } else if (s->cfg.isnormalized && !s->rngdebug && out->energytot > 0.0) {     /* nothing launched: leave the zeros alone */
             mcxb_config nc = s->cfg;

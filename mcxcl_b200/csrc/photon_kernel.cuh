@@ -261,7 +261,7 @@ __device__ __forceinline__ void locate(const SimParam& P, Photon& ph, uint32_t& 
  * ------------------------------------------------------------------------------------------------- */
 template <int SRC, typename MediaT>
 __device__ __forceinline__ void sample_source(const SimParam& P, const float4* __restrict__ S, Rng& rng, Photon& ph,
-        uint32_t& rawlabel, uint32_t& rawdet, float& fx, float& fy, float& fz, bool& aimed) {
+        uint32_t& rawlabel, uint32_t& rawdet, float& fx, float& fy, float& fz, bool& aimed, uint32_t& patidx) {
     const int st = (SRC == srcAny) ? P.srctype : SRC;
     const float4 pos = S[0], dir = S[1], p1 = S[2], p2 = S[3];
     ph.px = pos.x;
@@ -301,7 +301,16 @@ __device__ __forceinline__ void sample_source(const SimParam& P, const float4* _
         ph.pz += rx * p1.z + ry * p2.z;
 
         if (st == srcPattern) {
-            ph.w = pos.w * __ldg(P.srcpattern + (int)(ry * kJustBelowOne * p2.w) * (int)p1.w + (int)(rx * kJustBelowOne * p1.w));
+            const int cell = (int)(ry * kJustBelowOne * p2.w) * (int)p1.w + (int)(rx * kJustBelowOne * p1.w);
+
+            if (P.srcnum > 1) {
+                /* photon sharing (:1694-1705): one packet of unit weight carries every pattern; the deposit scales it
+                 * by the srcnum pattern values of the launch cell */
+                patidx = (uint32_t)cell;
+                ph.w = 1.f;
+            } else {
+                ph.w = pos.w * __ldg(P.srcpattern + cell);
+            }
         } else if (st == srcPattern3D) {
             ph.w = pos.w * __ldg(P.srcpattern + (int)(rz * kJustBelowOne * p1.z) * (int)p1.y * (int)p1.x
                                  + (int)(ry * kJustBelowOne * p1.y) * (int)p1.x + (int)(rx * kJustBelowOne * p1.x));
@@ -658,6 +667,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
     uint32_t detarg = 0;                              /* detector argument handed to the retire step */
     uint32_t nextid = (P.sched == 1) ? (tid * P.threadphoton + min(tid, (uint32_t)P.oddphoton)) : 0u;   /* replay: record of the next packet */
     uint32_t curid = 0;                               /* replay: record of the live packet */
+    uint32_t patidx = 0;                              /* photon sharing: pattern cell the live packet was launched from */
     bool relaunch = true;
     unsigned long long c_seg = 0, c_dep = 0, c_scat = 0;
 
@@ -746,7 +756,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 bool aimed;
                 ph.slen = 0.f;
                 ph.tof = 0.f;
-                sample_source<SRC, MediaT>(P, S, rng, ph, rawlabel, rawdet, fx, fy, fz, aimed);
+                sample_source<SRC, MediaT>(P, S, rng, ph, rawlabel, rawdet, fx, fy, fz, aimed, patidx);
 
                 if (fabsf(ph.w) <= P.minenergy) {
                     continue;
@@ -1038,7 +1048,19 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     tshift += (uint32_t)(cursrc - 1) * P.nrepvol * P.maxgate;
                 }
 
-                if (fabsf(weight) > 0.f) {
+                if (GEN && P.srcnum > 1) {
+                    /* photon sharing (:2902-2911): volumes interleaved pattern-fastest */
+                    const float* pw = P.srcpattern + (size_t)patidx * P.srcnum;
+                    AccT* dst = field + ((size_t)tshift * P.dimxyz + oldidx) * P.srcnum;
+
+                    for (uint32_t i = 0; i < P.srcnum; i++) {
+                        const float wi = __ldg(pw + i);
+
+                        if (fabsf(wi) > 0.f) {
+                            red_add(dst + i, weight * wi);
+                        }
+                    }
+                } else if (fabsf(weight) > 0.f) {
                     red_add(field + ((size_t)tshift * P.dimxyz + oldidx), weight);
 
                     if (STATS) {

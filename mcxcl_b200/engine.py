@@ -157,6 +157,8 @@ def shape_field(p, field):
     """float32[fieldlen] -> (Nx,Ny,Nz,Ngate[,Nsrc]) view, the layout pmcxcl returns (column-major file order
     [Nx][Ny][Nz][Ng][Ns], README.md:1316-1323)."""
     nx, ny, nz = p.dims
+    if p.c.srcnum > 1:          # photon sharing: patterns interleaved fastest, pmcxcl returns (srcnum*Nx, Ny, Nz, Ng) (src/pmcxcl.cpp:1330)
+        return field[:p.fieldlen].reshape((p.c.srcnum * nx, ny, nz, p.maxgate), order="F")
     shp = (nx, ny, nz, p.maxgate) + ((p.nrepvol,) if p.nrepvol > 1 else ()) + ((p.nsrcvol,) if p.nsrcvol > 1 else ())
     return field[:p.fieldlen].reshape(shp, order="F")
 

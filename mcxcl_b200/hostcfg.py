@@ -351,8 +351,8 @@ def prepare(cfg):
             raise ConfigError(-4, "simulating multiple sources currently can not be used with photon-sharing")
         if c.srcid > nsrc:
             raise ConfigError(-4, "srcid exceeds total defined source count")
-    if c.srcnum > 1:
-        raise ConfigError(-4, "photon-sharing pattern sources (srcnum>1) are outside the hot path of this build")
+    if c.srcnum > 1 and c.srctype != 5:
+        raise ConfigError(-4, "photon sharing (srcnum>1) needs the 'pattern' source type")
 
     maxlabel = int((flat & MED_MASK).max())
     if c.medianum <= maxlabel:
@@ -402,7 +402,7 @@ def prepare(cfg):
         p.keep["srcpattern"] = pat
         c.srcpattern = pat.ctypes.data_as(C.POINTER(C.c_float))
         c.srcpattern_len = pat.size
-        if c.srctype == 5 and pat.size < int(srcp1[0, 3]) * int(srcp2[0, 3]):
+        if c.srctype == 5 and pat.size < int(srcp1[0, 3]) * int(srcp2[0, 3]) * max(1, c.srcnum):
             raise ConfigError(-4, "srcpattern is smaller than srcparam1.w x srcparam2.w")
     if replayseed is not None:
         _replayinit(p, cfg, replayseed, prop)
