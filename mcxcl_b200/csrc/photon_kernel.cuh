@@ -706,13 +706,26 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     break;
                 }
 
-                const unsigned long long first = atomicAdd(P.counter, (unsigned long long)P.chunk);
+                /* guided self-scheduling: claim P.chunk photons while plenty are left, fewer as the counter approaches
+                 * nphoton (about half of an even share of what remains), so that all threads run dry within one
+                 * photon of each other instead of within one chunk.  The peek is a plain load: a stale value only
+                 * changes the size of the claim, never its correctness. */
+                uint32_t want = P.chunk;
+#ifndef MCXB_NO_GUIDED
+                {
+                    const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(P.counter);
+                    const float left = (seen < P.nphoton) ? (float)(P.nphoton - seen) : 0.f;
+                    const float share = left * __frcp_rn(2.f * (float)(gridDim.x * kBlock));
+                    want = (uint32_t)fminf((float)P.chunk, fmaxf(1.f, share));
+                }
+#endif
+                const unsigned long long first = atomicAdd(P.counter, (unsigned long long)want);
 
                 if (first >= P.nphoton) {
                     break;
                 }
 
-                budget = (uint32_t)min((unsigned long long)P.chunk, P.nphoton - first);
+                budget = (uint32_t)min((unsigned long long)want, P.nphoton - first);
 
                 if (GEN) {
                     nextid = (uint32_t)first;
