@@ -66,26 +66,38 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons DURING the timed region"""
+    """nvidia-smi clocks and throttle reasons DURING the timed region: ONE `nvidia-smi -lms 200` process, as in the
+    profiling recipe (B200_PROFILING.md).  Spawning a new nvidia-smi per sample re-initialises NVML every time and was
+    measured to slow the photon kernel by 3.5 % (362 ms vs 348 ms for cube60b 1e8)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        super().start()
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            line = line.strip()
+            if line:
+                self.rows.append([x.strip() for x in line.split(",")])
 
     def summary(self):
-        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         self.join(timeout=6)
         if not self.rows:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
@@ -169,7 +181,6 @@ def main():
     nph = int(args.photons)
     cfg = benchmarks.get(args.workload, nph)
     p = hostcfg.prepare(cfg)
-    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=device)      # > 126 MB of L2
 
     def barrier():
         if world > 1:
@@ -179,6 +190,10 @@ def main():
     # ------------------------------------------------------------------ device-resident steps
     sim = engine.Simulation(p, local)
     sim.reseed(p.c.seed, rank * sim.nthread)
+    # the L2-flush buffer is allocated AFTER the simulation's buffers: with the 384 MB block allocated first the driver
+    # places the (2 MB) working set differently and the same kernel was measured 3.5 % slower (360.4 ms vs 348.0 ms,
+    # profiles/README.md "placement"); a front-end that calls the engine has no such block in the way
+    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=device)      # > 126 MB of L2
     sampler = ClockSampler(local)
     kernel_ms, step_ms = [], []
     launches = 0
@@ -201,10 +216,13 @@ def main():
             kernel_ms.append(sim.kernel_ms())
             launches += 2
 
+    # the sampler starts BEFORE the warm-up: nvidia-smi takes about a second to initialise NVML over all GPUs of the box,
+    # and that start-up (not the 200 ms sampling itself) was measured to cost the first timed steps ~60 ms
+    sampler.start()
     for _ in range(args.warmup):
         step(False)
     barrier()
-    sampler.start()
+    sampler.rows.clear()                       # keep only what is sampled during the timed region
     for _ in range(args.steps):
         step(True)
     barrier()
@@ -216,7 +234,7 @@ def main():
         dist.all_reduce(kern, op=dist.ReduceOp.MAX)
     total_ms, kern_ms = float(total_ms.item()), float(kern.item())
     res = sim.fetch() if rank == 0 else None
-    nthread, kname = sim.nthread, sim.kernel_name
+    nthread, kname, copies = sim.nthread, sim.kernel_name, sim.acc_copies
     sim.close()
 
     # ------------------------------------------------------------------ end to end through the public host-buffer API
@@ -279,14 +297,15 @@ def main():
         line = dict(metric="photons/ms", value=value, unit="photons/ms", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=value / PUBLISHED_PHOTONS_PER_MS,
                     dtype="f32", data="synthetic",
-                    config=dict(workload=args.workload, nphoton_per_gpu=nph, volume="%dx%dx%d" % p.dims, media="u8 labels", accumulators="fp64 RED",
+                    config=dict(workload=args.workload, nphoton_per_gpu=nph, volume="%dx%dx%d" % p.dims, media="u8 labels", accumulators="fp64 RED, %d copies summed by finalize" % copies,
                                 nthread=nthread, block=256, scheduling="dynamic photon counter", l2="flushed between steps (384 MB memset)",
                                 parallelism="photon shards x%d + NCCL reduce/gather" % world if world > 1 else "single GPU",
                                 baseline_ref="README.md:618: 12953.37 photon/ms on a Titan V-class GPU (OpenCL), 1e7 photons",
                                 absorbed=res["absorbed"], detected=res["detected"]),
                     clocks=clocks,
                     e2e=dict(value=nph * world * args.steps / e2e_total, unit="photons/ms", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), ms_per_step=e2e_total / args.steps),
-                    gpu_launches=launches, kernel_ms=kern_ms, kernel_photons_per_ms=nph / kern_ms)
+                    gpu_launches=launches, kernel_ms=kern_ms, kernel_photons_per_ms=nph / kern_ms,
+                    kernel_ms_steps=[round(x, 2) for x in kernel_ms])
         if roof:
             line["roofline"] = roof
         if cpu:

@@ -240,6 +240,7 @@ void*    mcxb_sim_seeddata_devptr(mcxb_sim* sim);   /* uint64[maxdetphoton*2] or
 uint64_t mcxb_sim_fieldlen(mcxb_sim* sim);
 uint32_t mcxb_sim_reclen(mcxb_sim* sim);
 uint32_t mcxb_sim_nthread(mcxb_sim* sim);           /* threads (= RNG streams) this simulation uses */
+uint32_t mcxb_sim_acc_copies(mcxb_sim* sim);        /* replicated accumulator volumes on the device (summed by finalize) */
 const char* mcxb_sim_kernel_name(mcxb_sim* sim);    /* which specialisation was selected */
 float mcxb_sim_last_kernel_ms(mcxb_sim* sim);       /* CUDA-event time of the most recent launch (syncs on it) */
 void mcxb_sim_destroy(mcxb_sim* sim);

@@ -148,6 +148,7 @@ SYMBOLS = [
     ("mcxb_sim_fieldlen", C.c_uint64, [_VP]),
     ("mcxb_sim_reclen", C.c_uint32, [_VP]),
     ("mcxb_sim_nthread", C.c_uint32, [_VP]),
+    ("mcxb_sim_acc_copies", C.c_uint32, [_VP]),
     ("mcxb_sim_kernel_name", C.c_char_p, [_VP]),
     ("mcxb_sim_last_kernel_ms", C.c_float, [_VP]),
     ("mcxb_sim_destroy", None, [_VP]),

@@ -120,8 +120,13 @@ def digimouse(nphoton=1e6, variant="shipped"):
     return cfg
 
 
+def digimouse_tg(nphoton=1e6):
+    """BASELINE.json's "multi-source time-gated" digimouse: 4 sources x 10 gates x 9.8 M voxels"""
+    return digimouse(nphoton, "multisrc_tg")
+
+
 BENCHMARKS = {"cube60": cube60, "cube60b": cube60b, "cube60planar": cube60planar, "qtest": qtest,
-              "skinvessel": skinvessel, "colin27": colin27, "digimouse": digimouse}
+              "skinvessel": skinvessel, "colin27": colin27, "digimouse": digimouse, "digimouse_tg": digimouse_tg}
 
 
 def get(name, nphoton=1e6, **kw):

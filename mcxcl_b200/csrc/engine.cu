@@ -373,6 +373,7 @@ struct mcxb_sim {
     std::vector<float> h_rweight;                /* host copies for the replay normalisation */
     std::vector<int32_t> h_rdetid;
     uint32_t nrepvol = 1;
+    uint32_t acccopies = 1;                     /* replicated accumulator volumes (photon_kernel.cuh) */
     unsigned long long* h_progress = nullptr;   /* pinned word the progress poll copies the photon counter into */
     cudaStream_t pollstream = nullptr;
     /* pinned staging */
@@ -485,9 +486,15 @@ extern "C" float mcxb_normalizer(const mcxb_config* cfg, double energytot) {
 
 /* ---- small device kernels -------------------------------------------------------------------- */
 template <typename AccT>
-__global__ void finalize_kernel(const AccT* __restrict__ acc, float* __restrict__ out, size_t n) {
+__global__ void finalize_kernel(const AccT* __restrict__ acc, float* __restrict__ out, size_t n, uint32_t copies) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        out[i] = (float)acc[i];
+        AccT sum = acc[i];
+
+        for (uint32_t c = 1; c < copies; c++) {
+            sum += acc[c * n + i];
+        }
+
+        out[i] = (float)sum;
     }
 }
 
@@ -866,7 +873,18 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     }
 
     /* ---- outputs ---- */
-    CU_TRY(dev_alloc(&s->d_field, device, (s->acc64 ? 8 : 4) * s->fieldlen));
+    {
+        /* accumulator copies: as many as fit a 40 MB budget (a third of the 126 MB L2), at most 8 */
+        const uint64_t one = (uint64_t)(s->acc64 ? 8 : 4) * s->fieldlen;
+        uint64_t k = std::min<uint64_t>(8, std::max<uint64_t>(1, ((uint64_t)40 << 20) / std::max<uint64_t>(one, 1)));
+
+        if (const char* e = getenv("MCXB_ACC_COPIES")) {
+            k = std::max(1, atoi(e));
+        }
+
+        s->acccopies = s->rngdebug ? 1u : (uint32_t)std::min<uint64_t>(k, s->nblock);
+        CU_TRY(dev_alloc(&s->d_field, device, one * s->acccopies));
+    }
     CU_TRY(dev_alloc(&s->d_field32, device, 4 * s->fieldlen));
     CU_TRY(dev_alloc(&s->d_energy, device, 2 * sizeof(double)));
     CU_TRY(dev_alloc(&s->d_counter, device, sizeof(unsigned long long)));
@@ -968,6 +986,15 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     P.replaydetid = s->d_rdetid;
     P.replaydet = cfg->replaydet;
     P.nrepvol = s->nrepvol;
+    P.acccopies = s->acccopies;
+    P.accstride = s->fieldlen;
+
+    if (getenv("MCXB_DEBUG_PTRS")) {
+        fprintf(stderr, "mcxb buffers: media %p field %p field32 %p tables %p seeds %p det %p detcount %p counter %p energy %p\n",
+                s->d_media, s->d_field, (void*)s->d_field32, (void*)s->d_tables, (void*)s->d_seeds, (void*)s->d_det, (void*)s->d_detcount,
+                (void*)s->d_counter, (void*)s->d_energy);
+    }
+
     return MCXB_OK;
 }
 
@@ -996,7 +1023,7 @@ extern "C" int mcxb_sim_reset(mcxb_sim* s, void* cuda_stream) {
 
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CU_TRY(cudaSetDevice(s->device));
-    CU_TRY(cudaMemsetAsync(s->d_field, 0, (s->acc64 ? 8 : 4) * s->fieldlen, st));
+    CU_TRY(cudaMemsetAsync(s->d_field, 0, (s->acc64 ? 8 : 4) * s->fieldlen * s->acccopies, st));
     CU_TRY(cudaMemsetAsync(s->d_energy, 0, 2 * sizeof(double), st));
     CU_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
     CU_TRY(cudaMemsetAsync(s->d_detcount, 0, sizeof(uint32_t), st));
@@ -1113,9 +1140,9 @@ extern "C" int mcxb_sim_finalize(mcxb_sim* s, void* cuda_stream) {
     const int grid = (int)std::min<uint64_t>((s->fieldlen + 255) / 256, 148 * 8);
 
     if (s->acc64) {
-        finalize_kernel<double> <<< grid, 256, 0, st>>>((const double*)s->d_field, s->d_field32, s->fieldlen);
+        finalize_kernel<double> <<< grid, 256, 0, st>>>((const double*)s->d_field, s->d_field32, s->fieldlen, s->acccopies);
     } else {
-        finalize_kernel<float> <<< grid, 256, 0, st>>>((const float*)s->d_field, s->d_field32, s->fieldlen);
+        finalize_kernel<float> <<< grid, 256, 0, st>>>((const float*)s->d_field, s->d_field32, s->fieldlen, s->acccopies);
     }
 
     CU_TRY(cudaGetLastError());
@@ -1272,6 +1299,9 @@ extern "C" uint64_t mcxb_sim_fieldlen(mcxb_sim* s) {
 }
 extern "C" uint32_t mcxb_sim_reclen(mcxb_sim* s) {
     return s ? s->reclen : 0;
+}
+extern "C" uint32_t mcxb_sim_acc_copies(mcxb_sim* s) {
+    return s ? s->acccopies : 0;
 }
 extern "C" uint32_t mcxb_sim_nthread(mcxb_sim* s) {
     return s ? s->nthread : 0;

@@ -87,6 +87,9 @@ struct SimParam {
     const int*   replaydetid;
     int32_t      replaydet;
     uint32_t     nrepvol;         /* volumes per source in replay: detnum when replaydet == -1, else 1 */
+    /* replicated accumulators: CTA b adds into copy (b % acccopies); the copies are summed by finalize_kernel */
+    uint32_t     acccopies;
+    unsigned long long accstride; /* elements between two copies (= fieldlen) */
 };
 
 
@@ -634,7 +637,12 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
     const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
     const MediaT* __restrict__ media = static_cast<const MediaT*>(P.media);
-    AccT* __restrict__ field = static_cast<AccT*>(P.field);
+    /* Small volumes are accumulated into several copies (engine.cu picks the count): the few voxels next to the source
+     * receive a reduction from nearly every packet, and reductions to one address are serialised by the L2 slice that
+     * owns it (measured: the same kernel ran 349 / 361 / 404 ms depending on which physical pages backed a single
+     * copy, i.e. on which hot lines happened to share a slice).  Spreading the packets over k copies divides the load
+     * on every hot line by k at no cost in the loop: the copy is folded into the base pointer here. */
+    AccT* __restrict__ field = static_cast<AccT*>(P.field) + (size_t)(blockIdx.x % P.acccopies) * P.accstride;
     const float n0 = tab[0].w;
     /* partial-path rows of this thread, biased so that the row of label L is ppath_len[L * kBlock] */
     float* const ppath_len = ppath + ((int)(((P.savedetflag >> 1) & 1u) * (P.medianum - 1)) - 1) * kBlock;
@@ -1074,7 +1082,18 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                         }
                     }
                 } else if (fabsf(weight) > 0.f) {
+#if defined(MCXB_EXP_NODEPOSIT)
+                    /* timing experiment only (tools/): what the kernel costs without its reductions */
+                    if (weight == 123456.789f) {
+                        red_add(field + ((size_t)tshift * P.dimxyz + oldidx), weight);
+                    }
+
+#elif defined(MCXB_EXP_SPREAD)
+                    /* timing experiment only: same number of reductions, hot spots destroyed by a per-thread offset */
+                    red_add(field + ((size_t)tshift * P.dimxyz + (oldidx + tid * 977u) % P.dimxyz), weight);
+#else
                     red_add(field + ((size_t)tshift * P.dimxyz + oldidx), weight);
+#endif
 
                     if (STATS) {
                         c_dep++;

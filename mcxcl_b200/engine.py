@@ -44,6 +44,7 @@ class Simulation:
         self.fieldlen = int(self.lib.mcxb_sim_fieldlen(self.h))
         self.reclen = int(self.lib.mcxb_sim_reclen(self.h))
         self.nthread = int(self.lib.mcxb_sim_nthread(self.h))
+        self.acc_copies = int(self.lib.mcxb_sim_acc_copies(self.h))
         self.kernel_name = self.lib.mcxb_sim_kernel_name(self.h).decode()
 
     def close(self):
