@@ -239,11 +239,12 @@ def main():
 
     # ------------------------------------------------------------------ end to end through the public host-buffer API
     e2e_ms = []
+    p_all = p.clone_for(nphoton=nph * world)           # the whole job's budget; every rank takes its share of it
     for i in range(2 + args.steps):
         barrier()
         t0 = time.perf_counter()
         if world > 1:
-            out = multigpu.run_distributed(dict(cfg, nphoton=nph * world))
+            out = multigpu.run_distributed(p_all)
         else:
             out = engine.run_prepared(p, local)
         barrier()

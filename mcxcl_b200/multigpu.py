@@ -124,8 +124,15 @@ def run_distributed(cfg, workload=None):
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     device = torch.device("cuda", torch.cuda.current_device())
-    shares = split_photons(cfg["nphoton"], workload or [1.0] * world)
-    p = hostcfg.prepare(dict(cfg, nphoton=shares[rank]))
+    if isinstance(cfg, hostcfg.Prepared):
+        # already validated / pre-processed input (what a front-end holds after mcx_preprocess): only the budget changes
+        total = int(cfg.c.nphoton)
+        shares = split_photons(total, workload or [1.0] * world)
+        p = cfg.clone_for(nphoton=shares[rank])
+    else:
+        total = int(cfg["nphoton"])
+        shares = split_photons(total, workload or [1.0] * world)
+        p = hostcfg.prepare(dict(cfg, nphoton=shares[rank]))
     with engine.Simulation(p, device.index) as sim:
         sim.reseed(p.c.seed, rank * sim.nthread)
         sim.reset()
@@ -141,7 +148,7 @@ def run_distributed(cfg, workload=None):
             res["saved"] = res["detp"].shape[0]
             if seeds is not None:
                 res["seeds"] = seeds.cpu().numpy().view(np.uint64).reshape(-1, 2)
-        res["nphoton"] = int(cfg["nphoton"])
+        res["nphoton"] = total
         res["shares"] = shares
         res["flux"] = engine.shape_field(p, res["field"])
         return res

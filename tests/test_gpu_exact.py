@@ -157,3 +157,31 @@ def test_rotation_and_refraction_close_to_reference(lib, ref):
     got = v.copy()
     abi.check(lib.mcxb_test_refract(0, got.ctypes.data, n1.ctypes.data, n2.ctypes.data, face.ctypes.data, n), "refract")
     close_enough(got, want)
+
+
+def test_accumulator_copies_do_not_change_the_result(monkeypatch):
+    """The device sums k replicated accumulator volumes (engine.cu `acccopies`; CTA b adds into copy b mod k).  With the
+    static photon split every thread walks the same packets whatever k is, so the deposits are the same multiset and the
+    volumes can differ only by the order of the fp64 additions: equal to float32 rounding, identical energy ledger."""
+    from mcxcl_b200 import benchmarks, engine, hostcfg
+    cfg = benchmarks.get("cube60b", 300000)
+    cfg.update(sched=1, isnormalized=0)
+    out = {}
+    for k in (1, 8):
+        monkeypatch.setenv("MCXB_ACC_COPIES", str(k))
+        with engine.Simulation(hostcfg.prepare(cfg)) as sim:
+            assert sim.acc_copies == k
+            sim.reset()
+            sim.launch()
+            out[k] = sim.fetch()
+    monkeypatch.delenv("MCXB_ACC_COPIES")
+    assert out[1]["energytot"] == out[8]["energytot"] == 300000
+    assert out[1]["energyesc"] == pytest.approx(out[8]["energyesc"], rel=1e-12)      # fp64 atomics: order of the warp sums
+    assert out[1]["detected"] == out[8]["detected"]
+    a, b = out[1]["field"].astype(np.float64), out[8]["field"].astype(np.float64)
+    assert a.sum() > 0 and np.allclose(a, b, rtol=3e-7, atol=0)
+    # default policy: as many copies as fit 40 MB, at most 8 -> 8 for the 1.7 MB cube, 1 for a 57 MB atlas volume
+    with engine.Simulation(hostcfg.prepare(benchmarks.get("cube60b", 10))) as sim:
+        assert sim.acc_copies == 8
+    with engine.Simulation(hostcfg.prepare(benchmarks.get("colin27", 10))) as sim:
+        assert sim.acc_copies == 1
