@@ -591,7 +591,8 @@ __device__ __forceinline__ void save_detected(const SimParam& P, const float4* _
  *   GEN      false = the common configuration, with everything below decided at compile time:
  *              3-D domain, Henyey-Greenstein phase function, no gscatter switch, one source, flux or fluence
  *              output with save2pt on, no diffuse-reflectance / seed saving, all six boundary codes "unknown"
- *              (i.e. governed by isreflect alone) and no detect-on-face flags;
+ *              (i.e. governed by isreflect alone), no detect-on-face flags, and the default detected-photon
+ *              record (detector id + partial paths);
  *            true  = every option read from SimParam at run time.
  * ------------------------------------------------------------------------------------------------- */
 #ifndef MCXB_BLOCK
@@ -642,10 +643,14 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
      * owns it (measured: the same kernel ran 349 / 361 / 404 ms depending on which physical pages backed a single
      * copy, i.e. on which hot lines happened to share a slice).  Spreading the packets over k copies divides the load
      * on every hot line by k at no cost in the loop: the copy is folded into the base pointer here. */
-    AccT* __restrict__ field = static_cast<AccT*>(P.field) + (size_t)(blockIdx.x % P.acccopies) * P.accstride;
+    const uint32_t copyoff = (uint32_t)((blockIdx.x % P.acccopies) * P.accstride);     /* < 2^32: copies exist for small volumes only */
+    AccT* __restrict__ field = static_cast<AccT*>(P.field) + copyoff;
     const float n0 = tab[0].w;
     /* partial-path rows of this thread, biased so that the row of label L is ppath_len[L * kBlock] */
-    float* const ppath_len = ppath + ((int)(((P.savedetflag >> 1) & 1u) * (P.medianum - 1)) - 1) * kBlock;
+    /* what a detected-photon record holds: read at run time by the generic kernels, the default "DP" (detector id +
+     * partial paths, src/mcx_utils.c:266) in the common-configuration kernels, where the tests on it then fold away */
+    const uint32_t detflag = GEN ? P.savedetflag : 0x5u;
+    float* const ppath_len = ppath + ((int)(((detflag >> 1) & 1u) * (P.medianum - 1)) - 1) * kBlock;
 
     Rng rng;
     rng_seed(rng, P.seeds + 4 * (size_t)tid);
@@ -918,7 +923,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
 
                 if (SAVEDET) {
-                    const uint32_t flag = P.savedetflag;
+                    const uint32_t flag = detflag;
                     const uint32_t M = P.medianum - 1;
 
                     if (flag & 0x02u) {
@@ -1092,7 +1097,14 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     /* timing experiment only: same number of reductions, hot spots destroyed by a per-thread offset */
                     red_add(field + ((size_t)tshift * P.dimxyz + (oldidx + tid * 977u) % P.dimxyz), weight);
 #else
-                    red_add(field + ((size_t)tshift * P.dimxyz + oldidx), weight);
+                    /* the usual case -- one gate, one volume -- is a 32-bit index on the (uniform) base pointer */
+                    size_t e = (size_t)(oldidx + copyoff);
+
+                    if (tshift) {
+                        e += (size_t)tshift * P.dimxyz;
+                    }
+
+                    red_add(static_cast<AccT*>(P.field) + e, weight);
 #endif
 
                     if (STATS) {
@@ -1112,7 +1124,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
         if (ph.label != oldlabel || ph.tof > P.twin1 || fabsf(ph.w) < P.minenergy) {
             if (SAVEDET) {
                 if (ph.label != oldlabel) {
-                    if ((P.savedetflag & 0x04u) && oldlabel) {
+                    if ((detflag & 0x04u) && oldlabel) {
                         ppath_len[oldlabel * kBlock] += pacc;
                     }
 
