@@ -1042,7 +1042,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 float weight;
                 uint32_t tshift = 0;
 
-                if (P.maxgate > 1) {
+                if (GEN && P.maxgate > 1) {
                     /* clamped: (tof-twin0)*Rtstep can round up to maxgate for tof one ulp below twin1 */
                     tshift = (uint32_t)min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1);
                 }
@@ -1097,14 +1097,22 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     /* timing experiment only: same number of reductions, hot spots destroyed by a per-thread offset */
                     red_add(field + ((size_t)tshift * P.dimxyz + (oldidx + tid * 977u) % P.dimxyz), weight);
 #else
-                    /* the usual case -- one gate, one volume -- is a 32-bit index on the (uniform) base pointer */
-                    size_t e = (size_t)(oldidx + copyoff);
+                    /* the usual case -- one gate, one volume -- is a 32-bit index on the (uniform) base pointer; the
+                     * common-configuration kernels branch around the gate arithmetic instead of predicating it */
+                    if (GEN) {
+                        size_t e = (size_t)(oldidx + copyoff);
 
-                    if (tshift) {
-                        e += (size_t)tshift * P.dimxyz;
+                        if (tshift) {
+                            e += (size_t)tshift * P.dimxyz;
+                        }
+
+                        red_add(static_cast<AccT*>(P.field) + e, weight);
+                    } else if (P.maxgate > 1) {
+                        const uint32_t gate = (uint32_t)min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1);
+                        red_add(static_cast<AccT*>(P.field) + ((size_t)gate * P.dimxyz + (oldidx + copyoff)), weight);
+                    } else {
+                        red_add(static_cast<AccT*>(P.field) + (oldidx + copyoff), weight);
                     }
-
-                    red_add(static_cast<AccT*>(P.field) + e, weight);
 #endif
 
                     if (STATS) {
