@@ -421,7 +421,7 @@ static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t npha
 
     const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
     return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->extrasrclen == 0 && cfg->issaveref == 0 &&
-           !(savedet && cfg->issaveseed > 0) && cfg->issave2pt != 0 && cfg->replay_seed == nullptr && cfg->srcnum <= 1 &&
+           cfg->issave2pt != 0 && cfg->replay_seed == nullptr && cfg->srcnum <= 1 &&
            (!savedet || (cfg->savedetflag & 0x7Fu) == 0x5u) &&
            (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE);
 }

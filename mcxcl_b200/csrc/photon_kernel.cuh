@@ -590,7 +590,7 @@ __device__ __forceinline__ void save_detected(const SimParam& P, const float4* _
  *   STATS    count segments / deposits / scattering events (instrumented build, used to measure SURVEY 8(d))
  *   GEN      false = the common configuration, with everything below decided at compile time:
  *              3-D domain, Henyey-Greenstein phase function, no gscatter switch, one source, flux or fluence
- *              output with save2pt on, no diffuse-reflectance / seed saving, all six boundary codes "unknown"
+ *              output with save2pt on, no diffuse-reflectance output, all six boundary codes "unknown"
  *              (i.e. governed by isreflect alone), no detect-on-face flags, and the default detected-photon
  *              record (detector id + partial paths);
  *            true  = every option read from SimParam at run time.
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             }
 
             /* ------------------------------------------------------------------ launch (:1598-2255) */
-            if (GEN && P.issaveseed) {
+            if (SAVEDET && P.issaveseed) {      /* once per packet: a run-time test costs nothing here */
                 photonseed[0] = rng.a;
                 photonseed[kBlock] = rng.b;
             }

@@ -88,11 +88,12 @@ def test_run_matches_the_ctypes_mirror():
     a = m.run(cfg)
     b = engine.run(dict(cfg))
     assert a["flux"].shape == b["flux"].shape
-    assert abs(a["stat"]["energyabs"] - b["stat"]["energyabs"]) / b["stat"]["energyabs"] < 2e-3
+    # two realisations of 1e5 packets: sigma of the absorbed fraction is about 0.8 % of its value (tests/util.py:absorbed_sigma)
+    assert abs(a["stat"]["energyabs"] - b["stat"]["energyabs"]) / b["stat"]["energyabs"] < 4e-2
     fa, fb = a["flux"].astype(np.float64), b["flux"].astype(np.float64)
     big = fb > 1e-3 * fb.max()
     # dynamic photon scheduling: streams are identical, their assignment to photons is not => statistical agreement only
-    assert abs(fa[big].sum() / fb[big].sum() - 1) < 5e-3
+    assert abs(fa[big].sum() / fb[big].sum() - 1) < 4e-2
 
 
 @pytest.mark.gpu
