@@ -914,15 +914,14 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 } else {
                     const float gg = (GEN && (uint32_t)ph.nscat > P.gscatter) ? 0.f : g;
 
-                    if (fabsf(gg) > kEps) {
-                        /* Henyey-Greenstein inverse CDF (:2487-2490); sin(acos(c)) == sqrt(1-c^2) on [0,pi] */
-                        float t = (1.f - g * g) * mufu_rcp(1.f - g + 2.f * g * rng_uniform(rng));
-                        t *= t;
-                        ctheta = (1.f + g * g - t) * mufu_rcp(2.f * g);
-                        ctheta = fmaxf(-1.f, fminf(1.f, ctheta));
-                    } else {
-                        ctheta = 2.f * rng_uniform(rng) - 1.f;
-                    }
+                    /* Henyey-Greenstein inverse CDF (:2487-2490), or the isotropic 2u-1 when |g| <= EPS (:2495-2496);
+                     * both from the same draw, chosen with a select (the HG expression is finite garbage for g == 0);
+                     * sin(acos(c)) == sqrt(1-c^2) on [0,pi] */
+                    const float u = rng_uniform(rng);
+                    float t = (1.f - g * g) * mufu_rcp(1.f - g + 2.f * g * u);
+                    t *= t;
+                    const float chg = fmaxf(-1.f, fminf(1.f, (1.f + g * g - t) * mufu_rcp(2.f * g)));
+                    ctheta = (fabsf(gg) > kEps) ? chg : (2.f * u - 1.f);
                 }
 
                 stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
@@ -1040,6 +1039,37 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
         }
 
         /* ------------------------------------------------------------------ deposit (:2816-2929) */
+#ifndef MCXB_NESTED_DEPOSIT
+        if (!GEN) {
+            /* common configuration (flux / fluence, one volume per gate): ONE divergent region instead of three nested
+             * ones -- every level of nesting costs a BSSY / BRA / BSYNC triple per warp-iteration */
+            const bool moved = ph.idx1d != oldidx;
+            const float weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * mufu_rcp(mua));
+
+            if (moved && ph.tof >= P.twin0 && ph.tof < P.twin1 && fabsf(weight) > 0.f) {
+#if defined(MCXB_EXP_NODEPOSIT)
+
+                if (weight == 123456.789f)
+#endif
+                {
+                    if (P.maxgate > 1) {
+                        /* clamped: (tof-twin0)*Rtstep can round up to maxgate for tof one ulp below twin1 */
+                        const uint32_t gate = (uint32_t)min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1);
+                        red_add(static_cast<AccT*>(P.field) + ((size_t)gate * P.dimxyz + (oldidx + copyoff)), weight);
+                    } else {
+                        red_add(static_cast<AccT*>(P.field) + (oldidx + copyoff), weight);
+                    }
+                }
+
+                if (STATS) {
+                    c_dep++;
+                }
+            }
+
+            ph.w0 = moved ? ph.w : ph.w0;
+            ph.pathlen = moved ? 0.f : ph.pathlen;
+        } else
+#endif
         if (ph.idx1d != oldidx) {
             if ((!GEN || P.save2pt) && ph.tof >= P.twin0 && ph.tof < P.twin1) {
                 float weight;
