@@ -1070,8 +1070,10 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             ph.pathlen = moved ? 0.f : ph.pathlen;
         } else
 #endif
-        if (ph.idx1d != oldidx) {
-            if ((!GEN || P.save2pt) && ph.tof >= P.twin0 && ph.tof < P.twin1) {
+        {
+            const bool moved = ph.idx1d != oldidx;
+
+            if (moved && (!GEN || P.save2pt) && ph.tof >= P.twin0 && ph.tof < P.twin1) {
                 float weight;
                 uint32_t tshift = 0;
 
@@ -1154,8 +1156,8 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 }
             }
 
-            ph.w0 = ph.w;
-            ph.pathlen = 0.f;
+            ph.w0 = moved ? ph.w : ph.w0;
+            ph.pathlen = moved ? 0.f : ph.pathlen;
         }
 
         /* Everything below only has work to do for the few packets that changed medium (which includes leaving the
