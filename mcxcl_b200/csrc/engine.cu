@@ -385,7 +385,8 @@ struct mcxb_sim {
     float last_ms = 0.f;
 };
 
-static const KernelEntry* find_kernel(int src, bool refl, bool det, bool m16, bool acc64, bool stats, bool common) {
+/* det: 0 = no detector capture, 1 = the default record, 2 = any record flags (generic kernels take 1 and 2 alike) */
+static const KernelEntry* find_kernel(int src, bool refl, int det, bool m16, bool acc64, bool stats, bool common) {
     typedef const KernelEntry* (*GroupFn)(int*);
     static const GroupFn groups[kNumGroups] = { mcxb_kernel_group_0, mcxb_kernel_group_1, mcxb_kernel_group_2, mcxb_kernel_group_3,
                                                 mcxb_kernel_group_4, mcxb_kernel_group_5, mcxb_kernel_group_6
@@ -400,7 +401,9 @@ static const KernelEntry* find_kernel(int src, bool refl, bool det, bool m16, bo
             const KernelEntry* e = groups[g](&n);
 
             for (int i = 0; i < n; i++) {
-                if (e[i].src == wantsrc[pass] && e[i].generic == wantgen[pass] && e[i].reflect == refl && e[i].savedet == det &&
+                const bool detok = wantgen[pass] ? ((e[i].savedet != 0) == (det != 0)) : (e[i].savedet == det);
+
+                if (e[i].src == wantsrc[pass] && e[i].generic == wantgen[pass] && e[i].reflect == refl && detok &&
                         e[i].media16 == m16 && e[i].acc64 == acc64 && e[i].stats == stats) {
                     return e + i;
                 }
@@ -422,7 +425,6 @@ static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t npha
     const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
     return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->extrasrclen == 0 && cfg->issaveref == 0 &&
            cfg->issave2pt != 0 && cfg->replay_seed == nullptr && cfg->srcnum <= 1 &&
-           (!savedet || (cfg->savedetflag & 0x7Fu) == 0x5u) &&
            (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE);
 }
 
@@ -825,8 +827,9 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     const bool refl = needs_reflection(cfg);
     const bool stats = (cfg->debuglevel & MCXB_DEBUG_STATS) != 0;
     const bool common = is_common_config(cfg, savedet, nphase);
-    const KernelEntry* ke = stats ? find_kernel(srcAny, true, true, s->media16, true, true, false)
-                            : find_kernel(cfg->srctype, refl, savedet, s->media16, s->acc64, false, common);
+    const int detmode = savedet ? (flag == 0x5u ? 1 : 2) : 0;
+    const KernelEntry* ke = stats ? find_kernel(srcAny, true, 1, s->media16, true, true, false)
+                            : find_kernel(cfg->srctype, refl, detmode, s->media16, s->acc64, false, common);
 
     if (!ke) {
         return fail(MCXB_ERR_ARG, "no kernel specialisation for this configuration");

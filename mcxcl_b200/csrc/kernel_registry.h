@@ -15,7 +15,9 @@ typedef void (*PhotonKernelFn)(const SimParam);
 
 struct KernelEntry {
     int  src;          /* SrcType or srcAny */
-    bool reflect, savedet, media16, acc64, stats, generic;
+    bool reflect;
+    int  savedet;      /* 0 none, 1 default record folded at compile time, 2 record flags at run time */
+    bool media16, acc64, stats, generic;
     PhotonKernelFn fn;
     const char* name;
 };

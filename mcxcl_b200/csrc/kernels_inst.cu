@@ -19,25 +19,28 @@
 
 namespace mcxb {
 
-#define MCXB_K(SRC, R, D, M, A, S, G) { SRC, R, D, sizeof(M) == 2, sizeof(A) == 8, S, G, photon_kernel<SRC, R, D, M, A, S, G>, #SRC "/" #R #D "/" #M "/" #A "/" #G }
-#define MCXB_RD(SRC, M, A, G) MCXB_K(SRC, false, false, M, A, false, G), MCXB_K(SRC, true, false, M, A, false, G), \
-                              MCXB_K(SRC, false, true, M, A, false, G), MCXB_K(SRC, true, true, M, A, false, G)
+#define MCXB_K(SRC, R, D, M, A, S, G) { SRC, R, D, sizeof(M) == 2, sizeof(A) == 8, S, G, photon_kernel<SRC, R, D, M, A, S, G>, #SRC "/" #R "/det" #D "/" #M "/" #A "/" #G }
+/* reflection x detector capture (0 = none, 1 = default record) */
+#define MCXB_RD(SRC, M, A, G) MCXB_K(SRC, false, 0, M, A, false, G), MCXB_K(SRC, true, 0, M, A, false, G), \
+                              MCXB_K(SRC, false, 1, M, A, false, G), MCXB_K(SRC, true, 1, M, A, false, G)
+/* common-configuration kernels that read the record flags at run time (any -w / savedetflag) */
+#define MCXB_D2(SRC, M, A) MCXB_K(SRC, false, 2, M, A, false, false), MCXB_K(SRC, true, 2, M, A, false, false)
 
 static const KernelEntry entries[] = {
 #if MCXB_INST_GROUP == 0
-    MCXB_RD(srcPencil, uint8_t, double, false), MCXB_RD(srcPencil, uint8_t, float, false)
+    MCXB_RD(srcPencil, uint8_t, double, false), MCXB_RD(srcPencil, uint8_t, float, false), MCXB_D2(srcPencil, uint8_t, double)
 #elif MCXB_INST_GROUP == 1
-    MCXB_RD(srcDisk, uint8_t, double, false), MCXB_RD(srcDisk, uint8_t, float, false)
+    MCXB_RD(srcDisk, uint8_t, double, false), MCXB_RD(srcDisk, uint8_t, float, false), MCXB_D2(srcDisk, uint8_t, double)
 #elif MCXB_INST_GROUP == 2
     MCXB_RD(srcPlanar, uint8_t, double, false), MCXB_RD(srcFourier, uint8_t, double, false)
 #elif MCXB_INST_GROUP == 3
     MCXB_RD(srcIsotropic, uint8_t, double, false), MCXB_RD(srcCone, uint8_t, double, false)
 #elif MCXB_INST_GROUP == 4
-    MCXB_RD(srcAny, uint8_t, double, false), MCXB_RD(srcAny, uint8_t, float, false)
+    MCXB_RD(srcAny, uint8_t, double, false), MCXB_RD(srcAny, uint8_t, float, false), MCXB_D2(srcAny, uint8_t, double), MCXB_D2(srcAny, uint8_t, float)
 #elif MCXB_INST_GROUP == 5
-    MCXB_RD(srcAny, uint8_t, double, true), MCXB_RD(srcAny, uint8_t, float, true), MCXB_K(srcAny, true, true, uint8_t, double, true, true)
+    MCXB_RD(srcAny, uint8_t, double, true), MCXB_RD(srcAny, uint8_t, float, true), MCXB_K(srcAny, true, 1, uint8_t, double, true, true)
 #elif MCXB_INST_GROUP == 6
-    MCXB_RD(srcAny, uint16_t, double, true), MCXB_RD(srcAny, uint16_t, float, true), MCXB_K(srcAny, true, true, uint16_t, double, true, true)
+    MCXB_RD(srcAny, uint16_t, double, true), MCXB_RD(srcAny, uint16_t, float, true), MCXB_K(srcAny, true, 1, uint16_t, double, true, true)
 #endif
 };
 

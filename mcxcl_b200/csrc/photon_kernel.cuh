@@ -584,15 +584,15 @@ __device__ __forceinline__ void save_detected(const SimParam& P, const float4* _
  * Compile-time axes (the reference JIT-specialises on the same ones, src/mcx_host.cpp:857-971):
  *   SRC      source type, or srcAny = decided at run time
  *   REFLECT  index-mismatch handling compiled in (MCX_DO_REFLECTION)
- *   SAVEDET  detected-photon capture compiled in (MCX_SAVE_DETECTORS)
+ *   SAVEDET  detected-photon capture (MCX_SAVE_DETECTORS): 0 = compiled out, 1 = the default record "DP" (detector id +
+ *            partial paths, src/mcx_utils.c:266) folded at compile time, 2 = record flags read at run time
  *   MediaT   uint8_t (<=127 labels) or uint16_t media words
  *   AccT     double or float fluence accumulators
  *   STATS    count segments / deposits / scattering events (instrumented build, used to measure SURVEY 8(d))
  *   GEN      false = the common configuration, with everything below decided at compile time:
  *              3-D domain, Henyey-Greenstein phase function, no gscatter switch, one source, flux or fluence
  *              output with save2pt on, no diffuse-reflectance output, all six boundary codes "unknown"
- *              (i.e. governed by isreflect alone), no detect-on-face flags, and the default detected-photon
- *              record (detector id + partial paths);
+ *              (i.e. governed by isreflect alone) and no detect-on-face flags;
  *            true  = every option read from SimParam at run time.
  * ------------------------------------------------------------------------------------------------- */
 #ifndef MCXB_BLOCK
@@ -603,7 +603,7 @@ constexpr int kBlock = MCXB_BLOCK;
     #define MCXB_MINBLOCKS 4      /* 64 registers/thread, 32 resident warps per SM: +8% over 3 (80 registers) on B200 */
 #endif
 
-template <int SRC, bool REFLECT, bool SAVEDET, typename MediaT, typename AccT, bool STATS, bool GEN>
+template <int SRC, bool REFLECT, int SAVEDET, typename MediaT, typename AccT, bool STATS, bool GEN>
 __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __grid_constant__ SimParam P) {
     extern __shared__ float4 smem[];
     float4* tab = smem;                                   /* optical properties, row 0 = background */
@@ -647,9 +647,9 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
     AccT* __restrict__ field = static_cast<AccT*>(P.field) + copyoff;
     const float n0 = tab[0].w;
     /* partial-path rows of this thread, biased so that the row of label L is ppath_len[L * kBlock] */
-    /* what a detected-photon record holds: read at run time by the generic kernels, the default "DP" (detector id +
-     * partial paths, src/mcx_utils.c:266) in the common-configuration kernels, where the tests on it then fold away */
-    const uint32_t detflag = GEN ? P.savedetflag : 0x5u;
+    /* what a detected-photon record holds: read at run time by the generic kernels and by SAVEDET == 2, the default
+     * "DP" (detector id + partial paths, src/mcx_utils.c:266) with SAVEDET == 1, where the tests on it then fold away */
+    const uint32_t detflag = (GEN || SAVEDET == 2) ? P.savedetflag : 0x5u;
     float* const ppath_len = ppath + ((int)(((detflag >> 1) & 1u) * (P.medianum - 1)) - 1) * kBlock;
 
     Rng rng;

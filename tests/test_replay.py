@@ -122,8 +122,17 @@ def test_gpu_replay_retraces_every_photon(gpu_base):
     assert base["detected"] - 3 <= p.c.nphoton == len(kept) <= base["detected"]
     assert rep["energytot"] == p.c.nphoton
     assert rep["detected"] == p.c.nphoton
-    assert np.array_equal(sort_rows(base["detp"][kept]), sort_rows(rep["detp"]))
-    assert np.array_equal(sort_rows(base["seeds"][kept].astype(np.int64)), sort_rows(rep["seeds"].astype(np.int64)))
+    # pair the records through the saved RNG states (unique per packet).  The baseline runs in a common-configuration
+    # kernel and the replay in the generic one: same arithmetic, but the two instantiations may contract a*b+c
+    # differently, so integer fields must agree exactly and float fields to rounding
+    bs, rs = base["seeds"][kept].astype(np.int64), rep["seeds"].astype(np.int64)
+    ob, orr = np.lexsort(bs.T[::-1]), np.lexsort(rs.T[::-1])
+    assert np.array_equal(bs[ob], rs[orr])
+    b, r = base["detp"][kept][ob], rep["detp"][orr]
+    M = p.c.medianum - 1
+    assert np.array_equal(b[:, 0], r[:, 0])                                             # detector id
+    assert np.array_equal(b[:, 1:1 + M].view(np.uint32), r[:, 1:1 + M].view(np.uint32))  # scattering counts
+    np.testing.assert_allclose(b[:, 1 + M:], r[:, 1 + M:], rtol=2e-4, atol=1e-5)         # partial paths, momentum transfer
     assert 0.30 <= rep["absorbed"] < 0.39
 
 
