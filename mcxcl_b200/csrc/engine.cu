@@ -423,7 +423,7 @@ static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t npha
     }
 
     const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
-    return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->extrasrclen == 0 && cfg->issaveref == 0 &&
+    return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->issaveref == 0 &&
            cfg->issave2pt != 0 && cfg->replay_seed == nullptr && cfg->srcnum <= 1 &&
            (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE);
 }
@@ -843,7 +843,8 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->kname = ke->name;
     const uint32_t ftablen = (nphase + nangle + 1u) & ~1u;
     s->smem = sizeof(float4) * tablen + sizeof(float) * ftablen + (ke->savedet ? sizeof(float) * partialdata * kBlock : 0)
-              + (cfg->issaveseed ? 2 * sizeof(unsigned long long) * kBlock : 0);
+              + ((savedet && cfg->issaveseed) ? 2 * sizeof(unsigned long long) * kBlock : 0)
+              + (cfg->extrasrclen ? sizeof(int) * kBlock : 0);      /* source id per thread (common kernels) */
 
     if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
         return fail(MCXB_ERR_NOMEM, "configuration needs %zu bytes of shared memory per block (limit %zu)", s->smem, (size_t)prop.sharedMemPerBlockOptin);
@@ -994,6 +995,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     P.replaydetid = s->d_rdetid;
     P.replaydet = cfg->replaydet;
     P.nrepvol = s->nrepvol;
+    P.widedep = (maxgate > 1 ? 1u : 0u) | ((cfg->extrasrclen && cfg->srcid < 0) ? 2u : 0u);
     P.acccopies = s->acccopies;
     P.accstride = s->fieldlen;
 

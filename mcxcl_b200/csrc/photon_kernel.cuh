@@ -88,6 +88,7 @@ struct SimParam {
     int32_t      replaydet;
     uint32_t     nrepvol;         /* volumes per source in replay: detnum when replaydet == -1, else 1 */
     /* replicated accumulators: CTA b adds into copy (b % acccopies); the copies are summed by finalize_kernel */
+    uint32_t     widedep;         /* common kernels: bit 0 = more than one gate, bit 1 = one volume per source */
     uint32_t     acccopies;
     unsigned long long accstride; /* elements between two copies (= fieldlen) */
 };
@@ -590,7 +591,7 @@ __device__ __forceinline__ void save_detected(const SimParam& P, const float4* _
  *   AccT     double or float fluence accumulators
  *   STATS    count segments / deposits / scattering events (instrumented build, used to measure SURVEY 8(d))
  *   GEN      false = the common configuration, with everything below decided at compile time:
- *              3-D domain, Henyey-Greenstein phase function, no gscatter switch, one source, flux or fluence
+ *              3-D domain, Henyey-Greenstein phase function, no gscatter switch, flux or fluence
  *              output with save2pt on, no diffuse-reflectance output, all six boundary codes "unknown"
  *              (i.e. governed by isreflect alone) and no detect-on-face flags;
  *            true  = every option read from SimParam at run time.
@@ -627,6 +628,14 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
     float* ppath = ppath_base + threadIdx.x;
     unsigned long long* photonseed = seed_base + threadIdx.x;
+    /* multi-source runs in the common-configuration kernels: the source a packet came from is needed once per detected
+     * photon and, with one volume per source, once per deposit -- kept in shared memory (one word per thread, after the
+     * seed rows) so that single-source runs do not carry a live register for it; the generic kernels use a register */
+    int* const srcslot = reinterpret_cast<int*>(seed_base + ((SAVEDET && P.issaveseed) ? 2 * kBlock : 0)) + threadIdx.x;
+
+    if (!GEN && P.extrasrclen) {
+        *srcslot = 0;
+    }
 
     if (SAVEDET) {
         for (uint32_t i = 0; i < P.partialdata; i++) {
@@ -702,7 +711,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
                 if (SAVEDET) {
                     if ((detarg & kDetMask) && ph.label == 0 && (!GEN || P.issaveref < 2)) {
-                        save_detected(P, dettab, ppath, kBlock, ph, detarg, w0init, cursrc, photonseed);
+                        save_detected(P, dettab, ppath, kBlock, ph, detarg, w0init, GEN ? cursrc : (P.extrasrclen ? *srcslot : 0), photonseed);
                     }
                 }
             }
@@ -760,12 +769,18 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
             const float4* S = srctab;
 
-            if (GEN && P.extrasrclen && P.srcid != 1) {
+            if (P.extrasrclen && P.srcid != 1) {       /* (:1602-1612) once per packet */
                 if (P.srcid > 1) {
                     S = srctab + 4 * (P.srcid - 1);
                 } else {
-                    cursrc = (int)(rng_uniform(rng) * kJustBelowOne * (float)(P.extrasrclen + 1)) + 1;
-                    S = srctab + 4 * (cursrc - 1);
+                    const int pick = (int)(rng_uniform(rng) * kJustBelowOne * (float)(P.extrasrclen + 1)) + 1;
+                    S = srctab + 4 * (pick - 1);
+
+                    if (GEN) {
+                        cursrc = pick;
+                    } else {
+                        *srcslot = pick;
+                    }
                 }
             }
 
@@ -1052,9 +1067,14 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 if (weight == 123456.789f)
 #endif
                 {
-                    if (P.maxgate > 1) {
+                    if (P.widedep) {        /* several gates (bit 0) and / or one volume per source (bit 1): ONE uniform test */
                         /* clamped: (tof-twin0)*Rtstep can round up to maxgate for tof one ulp below twin1 */
-                        const uint32_t gate = (uint32_t)min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1);
+                        uint32_t gate = (uint32_t)max(0, min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1));
+
+                        if (P.widedep & 2u) {
+                            gate += (uint32_t)(*srcslot - 1) * P.maxgate;
+                        }
+
                         red_add(static_cast<AccT*>(P.field) + ((size_t)gate * P.dimxyz + (oldidx + copyoff)), weight);
                     } else {
                         red_add(static_cast<AccT*>(P.field) + (oldidx + copyoff), weight);
