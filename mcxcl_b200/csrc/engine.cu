@@ -884,7 +884,9 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         uint64_t k = std::min<uint64_t>(8, std::max<uint64_t>(1, ((uint64_t)40 << 20) / std::max<uint64_t>(one, 1)));
 
         if (const char* e = getenv("MCXB_ACC_COPIES")) {
-            k = std::max(1, atoi(e));
+            /* tuning override, bounded: at most 16 copies and at most 1 GB of accumulators */
+            k = (uint64_t)std::min(16, std::max(1, atoi(e)));
+            k = std::max<uint64_t>(1, std::min<uint64_t>(k, ((uint64_t)1 << 30) / std::max<uint64_t>(one, 1)));
         }
 
         if (k * s->fieldlen > 0xFFFFFFFFull) {

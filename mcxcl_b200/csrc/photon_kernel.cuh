@@ -142,8 +142,13 @@ __device__ __forceinline__ bool voxel_in_grid(const SimParam& P, int ix, int iy,
  * march a packet launched outside the volume (or inside a zero voxel) up to the first non-zero voxel
  * (src/mcx_core.cl:1350-1455).  Returns the linear index of the entry voxel or -1.
  * ------------------------------------------------------------------------------------------------- */
+#ifdef MCXB_EXP_NOCALL
+    #define MCXB_ENTER_INLINE __forceinline__
+#else
+    #define MCXB_ENTER_INLINE __noinline__
+#endif
 template <typename MediaT>
-__device__ __noinline__ int enter_volume(const SimParam& P, const float4* __restrict__ tab, Photon& ph) {
+__device__ MCXB_ENTER_INLINE int enter_volume(const SimParam& P, const float4* __restrict__ tab, Photon& ph) {
     const MediaT* __restrict__ media = static_cast<const MediaT*>(P.media);
     int count = 1;
     ph.ix = (int)(short)floorf(ph.px);
@@ -700,7 +705,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 e_escaped += ph.w;
 
                 if (GEN && P.issaveref == 1 && ph.label == 0 && ph.idx1d != kOutsideMin && ph.idx1d != kOutsideMax && ph.w > 0.f) {
-                    int tshift = min((int)P.maxgate - 1, (int)floorf((ph.tof - P.twin0) * P.Rtstep));
+                    int tshift = max(0, min((int)P.maxgate - 1, (int)floorf((ph.tof - P.twin0) * P.Rtstep)));
 
                     if (P.extrasrclen && P.srcid < 0) {
                         tshift += (cursrc - 1) * (int)(P.nrepvol * P.maxgate);
@@ -737,7 +742,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 {
                     const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(P.counter);
                     const float left = (seen < P.nphoton) ? (float)(P.nphoton - seen) : 0.f;
-                    const float share = left * __frcp_rn(2.f * (float)(gridDim.x * kBlock));
+                    const float share = left * mufu_rcp(2.f * (float)(gridDim.x * kBlock));
                     want = (uint32_t)fminf((float)P.chunk, fmaxf(1.f, share));
                 }
 #endif
@@ -1041,6 +1046,10 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
         if ((uint32_t)ph.ix < P.nx && (uint32_t)ph.iy < P.ny && (uint32_t)ph.iz < P.nz) {
             ph.idx1d = linear_index(P, ph.ix, ph.iy, ph.iz);
             fetch_voxel(media, ph.idx1d, ph.label, ph.detflag);
+            /* a packet that entered a label-0 voxel INSIDE the grid and was not retired there (no index mismatch, or
+             * reflection compiled out) keeps label 0 for the rest of its life: the reference restores
+             * mediaid = mediaidold whenever the voxel just left had label 0 (:2816, 2927-2929) */
+            ph.label = oldlabel ? ph.label : 0u;
         } else {
             ph.label = 0;
             ph.idx1d = (ph.ix < 0 || ph.iy < 0 || ph.iz < 0) ? kOutsideMin : kOutsideMax;
@@ -1061,7 +1070,8 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             const bool moved = ph.idx1d != oldidx;
             const float weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * mufu_rcp(mua));
 
-            if (moved && ph.tof >= P.twin0 && ph.tof < P.twin1 && fabsf(weight) > 0.f) {
+            /* nothing is deposited into a label-0 voxel (:2816: "&& mediaidold") */
+            if (moved && oldlabel && ph.tof >= P.twin0 && ph.tof < P.twin1 && fabsf(weight) > 0.f) {
 #if defined(MCXB_EXP_NODEPOSIT)
 
                 if (weight == 123456.789f)
@@ -1093,7 +1103,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
         {
             const bool moved = ph.idx1d != oldidx;
 
-            if (moved && (!GEN || P.save2pt) && ph.tof >= P.twin0 && ph.tof < P.twin1) {
+            if (moved && oldlabel && (!GEN || P.save2pt) && ph.tof >= P.twin0 && ph.tof < P.twin1) {
                 float weight;
                 uint32_t tshift = 0;
 

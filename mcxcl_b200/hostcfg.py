@@ -163,8 +163,10 @@ class Prepared:
 
     @property
     def nsrcvol(self):
-        if self.c.srctype in (5, 15):
-            return max(1, self.c.srcnum)
+        # same rule as the engine (csrc/engine.cu, src/mcx_host.cpp:679): one volume per pattern with photon sharing,
+        # else one per source when srcid < 0
+        if self.c.srcnum > 1:
+            return self.c.srcnum
         return self.c.extrasrclen + 1 if self.c.srcid < 0 else 1
 
     @property

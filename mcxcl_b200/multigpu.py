@@ -43,6 +43,16 @@ def gather_plan(counts, maxdetphoton):
     return offs, lens, at
 
 
+def seed_offsets(dist, world, nthread, device=None):
+    """exclusive prefix sum over ranks of the number of RNG streams (= threads) each rank runs"""
+    import torch
+    mine = torch.tensor([int(nthread)], dtype=torch.int64, device=device)
+    every = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(every, mine)
+    counts = [int(x) for x in every.tolist()]
+    return [sum(counts[:r]) for r in range(world)]
+
+
 class _DevArray:
     """exposes a raw device pointer to torch through __cuda_array_interface__ (zero copy)"""
 
@@ -71,10 +81,10 @@ def combine_tensors(dist, rank, world, field, energy, detcount, records, reclen,
     dist.reduce(energy, dst=0, op=dist.ReduceOp.SUM)
     if records is None:
         return None, None, [0] * world
-    mine = torch.tensor([int(detcount)], dtype=torch.int64, device=field.device)
-    gathered = [torch.zeros(1, dtype=torch.int64, device=field.device) for _ in range(world)]
-    dist.all_gather(gathered, mine)
-    counts = [int(x.item()) for x in gathered]
+    mine = detcount.to(torch.int64).reshape(1) if torch.is_tensor(detcount) else torch.tensor([int(detcount)], dtype=torch.int64, device=field.device)
+    gathered = torch.zeros(world, dtype=torch.int64, device=field.device)
+    dist.all_gather_into_tensor(gathered, mine)
+    counts = [int(x) for x in gathered.tolist()]          # ONE device->host sync for all ranks' counts
     reclen = max(1, int(reclen))
     stored = [min(x, int(maxdetphoton)) for x in counts]
     offs, lens, total = gather_plan(stored, maxdetphoton)
@@ -111,7 +121,7 @@ def combine(sim, dist, rank, world, device):
     if not (c.issavedet and ptr["detphoton"]):
         return combine_tensors(dist, rank, world, field, energy, 0, None, 0, 0)
     reclen = max(1, sim.reclen)
-    mine = int(_as_tensor(ptr["detcount"], (1,), "<i4", device).item())
+    mine = _as_tensor(ptr["detcount"], (1,), "<i4", device)      # stays on the device: gathered with everyone else's
     local = _as_tensor(ptr["detphoton"], (c.maxdetphoton * reclen,), "<f4", device)
     seeds = _as_tensor(ptr["seeddata"], (c.maxdetphoton * 2,), "<i8", device) if (c.issaveseed and ptr["seeddata"]) else None
     return combine_tensors(dist, rank, world, field, energy, mine, local, reclen, c.maxdetphoton, seeds)
@@ -134,7 +144,9 @@ def run_distributed(cfg, workload=None):
         shares = split_photons(total, workload or [1.0] * world)
         p = hostcfg.prepare(dict(cfg, nphoton=shares[rank]))
     with engine.Simulation(p, device.index) as sim:
-        sim.reseed(p.c.seed, rank * sim.nthread)
+        # rank r takes the slice of the ONE rand() stream that follows the slices of ranks 0..r-1 (src/mcx_host.cpp:759-768):
+        # the exclusive prefix sum of the per-rank thread counts, which need not be equal (different devices / nthread)
+        sim.reseed(p.c.seed, seed_offsets(dist, world, sim.nthread, device)[rank])
         sim.reset()
         sim.launch()
         detp, seeds, counts = combine(sim, dist, rank, world, device)

@@ -174,3 +174,56 @@ def test_jnii_output_and_json_input_file(tmp_path):
     r = engine.run(cfg)
     assert abs(absorbed(out) / 100 - r["stat"]["absorbed"]) < 0.01
     np.testing.assert_allclose(vol.astype(np.float64).sum(), r["flux"].astype(np.float64).sum(), rtol=0.02)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 1
+QTEST_INP = """1000000              # total photon (not used)
+29012392             # RNG seed, negative to generate
+30.0 30.0 1.0        # source position (mm)
+0 0 1                # initial directional vector
+0.e+00 5.e-09 5.e-9  # time-gates(s): start, end, step
+cubic60.json         # volume ('uchar' format)
+1 60 10 50            # x: voxel size, dim, start/end indices
+1 60 10 50            # y: voxel size, dim, start/end indices
+1 60 1  20            # z: voxel size, dim, start/end indices
+1                    # num of media
+1 0.01 0.005 1.0  # scat(1/mm), g, mua (1/mm), n
+4\t1            # detector number and radius (mm)
+30.0\t20.0\t1.0  # detector 1 position (mm)
+30.0\t40.0\t1.0  # ...
+20.0\t30.0\t1.0
+40.0\t30.0\t1.0
+"""
+QTEST_SHAPES = {"Shapes": [{"Name": "cube60"}, {"Origin": [0, 0, 0]}, {"Grid": {"Tag": 1, "Size": [60, 60, 60]}}]}
+
+
+def test_quicktest_inp_deck_through_the_cli(tmp_path):
+    """BASELINE config 1: the legacy .inp deck of example/quicktest (qtest.inp:1-16 + cubic60.json, command of
+    run_qtest.sh:3 at 1e6 photons) read by the reference's own mcx_loadconfig (src/mcx_utils.c:2087-2398) and run on
+    the CUDA engine; compared with the engine driven through the Python mirror of the same deck (benchmarks.qtest)
+    and with the committed reference series of cube60 (same geometry; n = 1 instead of 1.37 changes nothing with
+    matched boundaries: the medium-1 row is the only difference and there is no index mismatch in either)."""
+    with open(os.path.join(tmp_path, "qtest.inp"), "w") as f:
+        f.write(QTEST_INP)
+    with open(os.path.join(tmp_path, "cubic60.json"), "w") as f:
+        json.dump(QTEST_SHAPES, f)
+    n = 1000000
+    rc, out = mcx(["-A", "-n", str(n), "-f", "qtest.inp", "-F", "mc2", "-s", "qt", "-w", "DP"], tmp_path)
+    assert rc == 0, out[-2000:]
+    r = engine.run(benchmarks.get("qtest", n))
+    a = absorbed(out) / 100
+    assert abs(a - r["stat"]["absorbed"]) < 0.003, (a, r["stat"]["absorbed"])
+    m = re.search(r"detected\s+([0-9]+) photons", out)
+    assert m and abs(int(m.group(1)) - r["stat"]["detected"]) < 6 * np.sqrt(2.0 * r["stat"]["detected"])
+    mc2 = np.fromfile(os.path.join(tmp_path, "qt.mc2"), dtype=np.float32)
+    assert mc2.size == 216000
+    x, y = mc2.astype(np.float64).reshape(60, 60, 60), r["flux"][..., 0].astype(np.float64).transpose(2, 1, 0)
+    np.testing.assert_allclose(x.sum(), y.sum(), rtol=0.01)
+    np.testing.assert_allclose(x.sum(axis=(1, 2))[:30], y.sum(axis=(1, 2))[:30], rtol=0.03)
+    # the source voxel (29,29,0) after the 1-based -> 0-based shift of the .inp reader holds the peak
+    assert np.unravel_index(np.argmax(x), x.shape) == (0, 29, 29)
+    raw = open(os.path.join(tmp_path, "qt.mch"), "rb").read()
+    magic, version, maxmedia, detnum, colcount, totalphoton, detected, savedphoton = struct.unpack("<4s7I", raw[:32])
+    assert magic == b"MCXH" and maxmedia == 1 and detnum == 4 and colcount == 2 and totalphoton == n
+    rec = np.frombuffer(raw[64:64 + 4 * colcount * savedphoton], dtype=np.float32).reshape(-1, colcount)
+    assert set(np.unique(rec[:, 0]).astype(int)) == {1, 2, 3, 4}

@@ -73,6 +73,34 @@ def test_voxelwise_heldout_reference_run_calibrates_the_test(ref):
     assert abs(np.mean(z)) < 0.2 and 0.85 < np.std(z) < 1.25 and np.mean(np.abs(z) > 3) < 0.03
 
 
+def test_quicktest_deck_matches_reference(ref):
+    """BASELINE config 1 (example/quicktest/qtest.inp:1-16 at 1e6 photons, the deck of run_qtest.sh): absorbed fraction
+    within 0.5 %, voxel-wise z-scores against a reference series generated here on the box's host cores (8 seeds x
+    2e5 photons), the four detectors of the deck."""
+    n, runs = 200000, 8
+    fields, absd, det = [], [], []
+    for k in range(runs):
+        cfg = benchmarks.get("qtest", n)
+        cfg["seed"] = 29012392 + k                       # the .inp file's seed line
+        _, o = run_ref(ref, cfg, work=4096)
+        fields.append(o["field"].astype(np.float64))
+        absd.append(o["absorbed"])
+        det.append(o["detected"])
+    f = np.stack(fields)
+    mean, std = f.mean(0), f.std(0, ddof=1)
+    p, r = run_gpu(benchmarks.get("qtest", 1000000))
+    assert r["energytot"] == 1000000
+    assert abs(r["absorbed"] - np.mean(absd)) / np.mean(absd) < 0.005
+    want = np.mean(det) * 5
+    assert abs(r["detected"] - want) < 5 * np.sqrt(want * (1 + 5.0 / runs))
+    assert set(np.unique(r["detp"][:, 0]).astype(int)) == {1, 2, 3, 4} and r["reclen"] == 2
+    # voxel-wise: the 1e6-photon GPU field scaled to the size of one reference run; its own noise is sigma/sqrt(5)
+    sel = (mean > 1e-4 * mean.max()) & (std > 0)
+    z = (raw_field(p, r)[sel] / 5.0 - mean[sel]) / (std[sel] * np.sqrt(1.0 / 5 + 1.0 / runs))
+    # Student-t with 7 degrees of freedom: standard deviation 1.18, P(|t| > 3) = 2 %
+    assert abs(np.mean(z)) < 0.2 and 0.85 < np.std(z) < 1.4 and np.mean(np.abs(z) > 3) < 0.05, (np.mean(z), np.std(z), np.mean(np.abs(z) > 3))
+
+
 def test_detected_photons_cube60b():
     g = golden("cube60b")
     n = int(g["nphoton"])
@@ -89,46 +117,47 @@ def test_detected_photons_cube60b():
     assert 110 < det[:, 1].mean() < 133                           # mean partial path 121-122 voxels
 
 
-def test_skinvessel_binned_field():
-    g = golden("skinvessel")
-    n = int(g["nphoton"])
-    p, r = run_gpu(benchmarks.get("skinvessel", n), seed=int(g["seed0"]) + 50)
-    assert abs(r["absorbed"] - g["absorbed"].mean()) < 5 * max(g["absorbed"].std(ddof=1), 1e-3)
-    assert ("%.3f" % (100 * g["absorbed"].mean())).startswith("39.")          # test/testmcx.sh:112-114
-    binned = bin_field(raw_field(p, r), p.dims, int(g["bin"]))
-    idx, mean, std = g["idx"], g["mean"].astype(np.float64), g["std"].astype(np.float64)
-    sel = mean > 1e-3 * mean.max()
-    z = (binned[idx][sel] - mean[sel]) / (std[sel] * np.sqrt(1 + 1.0 / int(g["runs"])))
-    assert abs(np.mean(z)) < 0.1 and np.std(z) < 1.4 and np.mean(np.abs(z) > 3) < 0.06
-
-
-@pytest.mark.parametrize("deck", ["colin27", "digimouse"])
-def test_atlas_decks_match_reference_series(deck):
-    """colin27 (pencil beam, Fresnel scalp/air interface, 4 detectors) and digimouse as shipped (fourier wide-field
-    source launched outside the volume): the reference's own tests hold no known answers for them, so the pin is a
-    series of 8 reference runs (tests/golden/make_golden.py); statistics on 8x8x8-voxel blocks above 1e-4 of the peak.
-    The GPU run uses 10x the photons of one reference run, so its own noise is sigma/sqrt(10)."""
+@pytest.mark.parametrize("deck", ["skinvessel", "colin27", "digimouse"])
+def test_large_decks_voxelwise_against_reference_series(deck):
+    """skinvessel (200^3, disk source), colin27 (pencil beam, Fresnel scalp/air interface, 4 detectors) and digimouse as
+    shipped (fourier wide-field source launched outside the volume), VOXEL-wise: the reference's own tests hold no fluence
+    pins for them (skinvessel: absorbed 39.x % only), so the pin is a series of 8 reference runs of 1e6 photons
+    (tests/golden/make_golden.py).  Voxels above 1e-4 of the peak (BASELINE.json's criterion; where more than 2e5 qualify,
+    the fixture holds a deterministic hash subsample of them), plus 8x8x8-voxel blocks over the whole volume.  The GPU
+    run uses 10x the photons of one reference run, so its own noise is sigma/sqrt(10); z = (x/10 - mean) / (sigma
+    sqrt(1/10 + 1/8)) then follows Student's t with 7 degrees of freedom: standard deviation 1.18, P(|t| > 3) = 2 %."""
     g = golden(deck)
     n, runs, k = int(g["nphoton"]), int(g["runs"]), 10
+    assert n == 1000000 and int(g["bin"]) == 8
     p, r = run_gpu(benchmarks.get(deck, k * n), seed=int(g["seed0"]) + 50)
     ref = float(g["absorbed"].mean())
     assert abs(r["absorbed"] - ref) / ref < 0.005                         # BASELINE.json: absorbed fraction within 0.5 %
+    if deck == "skinvessel":
+        assert ("%.3f" % (100 * ref)).startswith("39.")                   # test/testmcx.sh:112-114
     if deck == "colin27":
         assert r["energytot"] == k * n
         want = float(g["detected"].mean())
         assert abs(r["detected"] / k - want) < 5 * np.sqrt(want / k + want / runs)
         assert r["reclen"] == 7 and r["detp"].shape == (r["saved"], 7)      # detid + partial path in 6 media
-    else:
+    if deck == "digimouse":
         # launched weight per packet of the fourier pattern: (1 + cos)/2 averaged over the aperture
         e = g["energytot"] / n
         assert abs(r["energytot"] / (k * n) - e.mean()) < 5 * np.hypot(e.std(ddof=1) / np.sqrt(runs), e.std(ddof=1) / np.sqrt(k))
-    binned = bin_field(raw_field(p, r), p.dims, int(g["bin"])) / k
+    raw = raw_field(p, r) / k
+    scale = np.sqrt(1.0 / k + 1.0 / runs)
+    # voxel-wise
     idx, mean, std = g["idx"], g["mean"].astype(np.float64), g["std"].astype(np.float64)
     ok = std > 0
-    z = (binned[idx][ok] - mean[ok]) / (std[ok] * np.sqrt(1.0 / k + 1.0 / runs))
-    # Student-t with 7 degrees of freedom: P(|t| > 3) = 2 %
-    assert abs(np.mean(z)) < 0.3 and np.std(z) < 1.5 and np.mean(np.abs(z) > 3) < 0.08, (np.mean(z), np.std(z), np.mean(np.abs(z) > 3))
-    np.testing.assert_allclose(raw_field(p, r).sum() / k, g["total"].mean(), rtol=5 * g["total"].std(ddof=1) / g["total"].mean() / np.sqrt(runs) + 0.01)
+    assert ok.mean() > 0.99 and idx.size >= 15000
+    z = (raw[idx][ok] - mean[ok]) / (std[ok] * scale)
+    assert abs(np.mean(z)) < 0.2 and 0.85 < np.std(z) < 1.4 and np.mean(np.abs(z) > 3) < 0.045, (np.mean(z), np.std(z), np.mean(np.abs(z) > 3))
+    # 8x8x8 blocks: every deposit of the run is inside one of them
+    bidx, bmean, bstd = g["bidx"], g["bmean"].astype(np.float64), g["bstd"].astype(np.float64)
+    binned = bin_field(raw, p.dims, 8)
+    ok = bstd > 0
+    zb = (binned[bidx][ok] - bmean[ok]) / (bstd[ok] * scale)
+    assert abs(np.mean(zb)) < 0.3 and np.std(zb) < 1.5 and np.mean(np.abs(zb) > 3) < 0.08, (np.mean(zb), np.std(zb), np.mean(np.abs(zb) > 3))
+    np.testing.assert_allclose(raw.sum(), g["total"].mean(), rtol=5 * g["total"].std(ddof=1) / g["total"].mean() / np.sqrt(runs) + 0.01)
 
 
 # ------------------------------------------------------------------------------------------------ every source type
@@ -203,6 +232,34 @@ def test_interior_fresnel_interfaces(ref):
         np.testing.assert_allclose(gf[lab == m].sum(), of[lab == m].sum(), rtol=0.02)
     assert gf[lab == 0].sum() == 0 and of[lab == 0].sum() == 0
     assert r["reclen"] == 4 and r["detp"].shape[1] == 4                         # detid + one partial path per medium
+
+
+@pytest.mark.parametrize("case", ["absorbing_boundaries", "matched_indices"])
+def test_label_zero_voxels_inside_the_grid(ref, case):
+    """A packet that enters a label-0 voxel INSIDE the grid without being retired (isreflect=0, or no index mismatch)
+    stays label 0 for the rest of its life in the reference (src/mcx_core.cl:2816 "&& mediaidold", :2927-2929
+    mediaid = mediaidold): nothing is deposited in the pocket, and behind it the packet no longer interacts.  Detector
+    capture is off: with it the reference indexes its partial-path row with label-1 = 0xFFFFFFFF for such a packet
+    (:2787, undefined behaviour -- the host build of the reference source segfaults there)."""
+    if case == "absorbing_boundaries":
+        cfg = decks.two_layer(200000, isreflect=0, issavedet=0)
+    else:
+        cfg = decks.two_layer(200000, isreflect=1, issavedet=0, prop=[[0, 0, 1, 1.33], [0.005, 1.0, 0.01, 1.37], [0.02, 5.0, 0.9, 1.5], [0.001, 0.5, 0.8, 1.33]])
+    p, r = run_gpu(cfg)
+    _, o = run_ref(ref, cfg)
+    sig = np.hypot(absorbed_sigma(2e5, r["absorbed"]), absorbed_sigma(2e5, o["absorbed"]))
+    assert abs(r["absorbed"] - o["absorbed"]) < 5 * sig, (r["absorbed"], o["absorbed"])
+    lab = p.keep["vol"] & 0x7FFFFFFF
+    gf, of = raw_field(p, r), o["field"].astype(np.float64)
+    assert gf[lab == 0].sum() == 0 and of[lab == 0].sum() == 0
+    for m in (1, 2, 3):
+        np.testing.assert_allclose(gf[lab == m].sum(), of[lab == m].sum(), rtol=0.02)
+    # the shadow of the pocket: the slab of label-3 voxels right behind it (z 40..59 under the 20x20 opening)
+    v3 = p.keep["vol"].reshape(60, 60, 60)          # [z][y][x] view of the x-fastest volume
+    sel = np.zeros((60, 60, 60), bool)
+    sel[40:, 20:40, 20:40] = True
+    sel &= (v3 & 0x7FFFFFFF) == 3
+    np.testing.assert_allclose(gf[sel.ravel()].sum(), of[sel.ravel()].sum(), rtol=0.3)       # a few hundred packets reach it
 
 
 def test_sixteen_bit_media_path(ref):

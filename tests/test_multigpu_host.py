@@ -57,6 +57,9 @@ def _worker(rank, world, port, case, outdir):
         seeds[:stored, 1] = np.arange(stored)
         records = torch.from_numpy(rec.ravel()) if case["savedet"] else None
         np.save(os.path.join(outdir, "field%d.npy" % rank), field.numpy().copy())
+        # seed slices: exclusive prefix sum of unequal per-rank thread counts
+        offs = multigpu.seed_offsets(dist, world, 1000 * (rank + 1))
+        assert offs == [0, 1000], offs
         out, oseeds, counts = multigpu.combine_tensors(dist, rank, world, field, energy, count, records, reclen, maxdet,
                                                        torch.from_numpy(seeds.ravel()) if case["seeds"] else None)
         if rank == 0:
