@@ -207,6 +207,34 @@ int mcxb_list_gpu(mcxb_gpuinfo* info, int maxinfo);
  * HOST buffers of cfg, runs the photon kernel, reads back, folds and normalises into `out`. */
 int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_output* out);
 
+/* ---- one call, several GPUs of one box, ONE host process ------------------------------------------------------
+ * replaces the multi-device branch of mcx_run_simulation: the `-G 1101` device mask / `-W a,b,c` workload split
+ * (src/mcx_host.cpp:650-662, 1011-1012, src/mcx_utils.c:4845-4865), one slice of the single rand() stream per device
+ * (src/mcx_host.cpp:759-768), all devices inside one timing window (:1098-1168) -- and, where the reference reads every
+ * device back and sums volumes, energies and detected-photon lists on the host (:1218-1232, 1292-1306), an NCCL
+ * exchange over NVLink: reduce(float32 volume) + reduce(float64 energy pair) to devices[0], all-gather of the
+ * detected counts, variable-length send/recv of the records (and RNG states) into devices[0]'s buffer; then one
+ * device-to-host copy and one normalisation with the global launched energy.
+ *   devices   CUDA ordinals, devices[0] collects the result;  workload: ndev weights or NULL (= equal shares)
+ *   out       as for mcxb_run_simulation (runtime_ms = the slowest device's kernel window)
+ *   info      optional per-device report
+ * NCCL is bound at run time (dlopen libnccl.so.2); with ndev == 1 the call is mcxb_run_simulation. */
+#define MCXB_MAX_DEVICES 16
+typedef struct mcxb_multi_info {
+    int32_t  ndev;
+    int32_t  nccl_version;                   /* e.g. 22703 */
+    uint64_t share[MCXB_MAX_DEVICES];        /* photons given to each device */
+    uint32_t detected[MCXB_MAX_DEVICES];     /* photons each device detected */
+    uint32_t nthread[MCXB_MAX_DEVICES];      /* RNG streams (= threads) of each device: its slice of the seed stream */
+    float    kernel_ms[MCXB_MAX_DEVICES];
+} mcxb_multi_info;
+int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devices, int ndev, const float* workload, mcxb_output* out,
+                              mcxb_multi_info* info);
+/* the photon split used by the call above: nphoton * w_i / sum(w) rounded down, remainder to the first devices */
+void mcxb_split_photons(uint64_t nphoton, const float* workload, int ndev, uint64_t* share);
+/* NCCL version found at run time (0 = no usable libnccl.so.2) */
+int mcxb_nccl_version(void);
+
 /* last error message of the calling thread ("" if none) */
 const char* mcxb_last_error(void);
 

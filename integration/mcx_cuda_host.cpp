@@ -24,9 +24,11 @@
  *   devices  cfg->deviceid[] '1' flags select CUDA devices, cfg->workload[] weights split the photons
  *            (:650-662, 1011-1012); every device gets the next slice of ONE rand() stream (:759-768).
  *
- * Several selected GPUs are driven from this one host thread, like the reference drives several OpenCL
- * devices: the kernels are enqueued on all devices first and collected afterwards; results are summed on
- * the host.  (The one-process-per-GPU NCCL path lives in mcxcl_b200/multigpu.py.)
+ * Several selected GPUs (`-G 1101`, `-W a,b,c`) are driven from this one host process through
+ * mcxb_run_simulation_multi: photon shards, one seed-stream slice per device, then an NCCL reduce of the volumes and
+ * energies and a gather of the detected-photon records onto the first device, ONE read-back and one normalisation --
+ * in place of the reference's per-device read-back and host-side summing (src/mcx_host.cpp:1218-1232, 1292-1306).
+ * Only the `-D P` progress bar keeps the device-by-device form (it polls device 0 while the kernels run).
  */
 #include "mcx_host.h"
 #include "mcx_tictoc.h"
@@ -133,6 +135,13 @@ void fill_config(const Config* cfg, mcxb_config* c) {
         c->replay_detid = cfg->replay.detid;
         c->replaydet = cfg->replaydet;
     }
+}
+
+/* floats per detected-photon record (hostdetreclen, src/mcx_host.cpp:494-496) */
+unsigned int record_length(const Config* cfg) {
+    const unsigned int flag = cfg->issavedet ? (cfg->savedetflag & 0x7Fu) : 0u;
+    const unsigned int nmed = cfg->medianum - 1;
+    return nmed * ((flag >> 1 & 1u) + (flag >> 2 & 1u) + (flag >> 3 & 1u)) + (flag & 1u) + 3 * ((flag >> 4 & 1u) + (flag >> 5 & 1u)) + (flag >> 6 & 1u);
 }
 
 /* what this build's hot path does not cover is refused loudly, never approximated */
@@ -301,12 +310,101 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         }
     }
 
-    /* ---- create one resident simulation per device; seed slices follow each other in ONE stream ---- */
-    std::vector<mcxb_sim*> sims(workdev, (mcxb_sim*)NULL);
+    std::vector<mcxb_sim*> sims;
     uint64_t seedskip = 0;
     int rc = MCXB_OK;
+    const bool multi = workdev > 1 && !(cfg->debuglevel & MCX_DEBUG_PROGRESS) && !(cfg->debuglevel & MCX_DEBUG_RNG);
 
-    for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+    if (multi) {
+        /* ---- all selected devices in ONE engine call: shards + NCCL exchange + one read-back ---- */
+        const unsigned int reclen = record_length(cfg);
+
+        if (cfg->exportfield == NULL && cfg->issave2pt) {
+            cfg->exportfield = (float*)calloc(fieldlen, sizeof(float));
+        }
+
+        if (cfg->issavedet && cfg->exportdetected == NULL) {
+            cfg->exportdetected = (float*)malloc(std::max<size_t>(1, (size_t)reclen * cfg->maxdetphoton) * sizeof(float));
+        }
+
+        if (cfg->issavedet && cfg->issaveseed && cfg->seeddata == NULL) {
+            cfg->seeddata = malloc(std::max<size_t>(1, (size_t)cfg->maxdetphoton) * 16);
+        }
+
+        cfg->his.colcount = reclen;
+        cfg->his.maxmedia = cfg->medianum - 1;
+        cfg->his.detnum = cfg->detnum;
+        cfg->his.srcnum = cfg->srcnum;
+        cfg->his.savedetflag = cfg->savedetflag;
+        cfg->his.totalsource = cfg->extrasrclen + 1;
+        cfg->his.detected = 0;
+        cfg->his.respin = 1;
+        cfg->detectedcount = 0;
+        cfg->energytot = cfg->energyesc = cfg->energyabs = 0.0;
+        cfg->runtime = 0;
+
+        mcx_printheader(cfg);
+        MCX_FPRINTF(cfg->flog, "- code name: [%s] compiled for sm_100a\n", kEngineName);
+        MCX_FPRINTF(cfg->flog, "- RNG: %s, photon scheduling: persistent threads with a per-GPU photon counter; %u devices combined over NCCL %d\n",
+                    MCX_RNG_NAME, workdev, mcxb_nccl_version());
+        MCX_FPRINTF(cfg->flog, "initializing streams ...\t");
+        mcx_flush(cfg);
+
+        mcxb_config c;
+        fill_config(cfg, &c);
+        int devs[MAX_DEVICE];
+        float wl[MAX_DEVICE];
+
+        for (unsigned int i = 0; i < workdev; i++) {
+            devs[i] = (int)(intptr_t)devices[i] - 1;
+            wl[i] = cfg->workload[i];
+        }
+
+        mcxb_output out;
+        mcxb_multi_info info;
+        memset(&out, 0, sizeof(out));
+        out.field = cfg->issave2pt ? cfg->exportfield : NULL;
+        out.fieldlen = fieldlen;
+        out.detphoton = cfg->issavedet ? cfg->exportdetected : NULL;
+        out.seeddata = (cfg->issavedet && cfg->issaveseed) ? (uint64_t*)cfg->seeddata : NULL;
+        const unsigned int tic0 = GetTimeMillis();
+        MCX_FPRINTF(cfg->flog, "lauching mcx_main_loop for time window [%.1fns %.1fns] ...\n", cfg->tstart * 1e9, cfg->tend * 1e9);
+        rc = mcxb_run_simulation_multi(&c, devs, (int)workdev, wl, &out, &info);
+
+        if (rc == MCXB_OK) {
+            for (unsigned int i = 0; i < workdev; i++) {
+                MCX_FPRINTF(cfg->flog, "- [device %d(%d): %s] threadph=%d extra=%d np=%.1f nthread=%u nblock=%d repetition=%d\n",
+                            i, gpu[i].id, gpu[i].name, (int)(info.share[i] / info.nthread[i]), (int)(info.share[i] % info.nthread[i]),
+                            (double)info.share[i], info.nthread[i], (int)gpu[i].autoblock, 1);
+            }
+
+            cfg->runtime = std::max(1u, (unsigned int)(out.runtime_ms + 0.5f));
+            MCX_FPRINTF(cfg->flog, "kernel complete:  \t%d ms\nretrieving flux ... \t", cfg->runtime);
+
+            if (cfg->issavedet) {
+                if (out.detected > cfg->maxdetphoton) {
+                    MCX_FPRINTF(cfg->flog, S_RED "WARNING: the detected photon number is more than what your have specified (%u > %d), please use the -H option to specify a greater number\t" S_RESET,
+                                out.detected, cfg->maxdetphoton);
+                } else {
+                    MCX_FPRINTF(cfg->flog, "detected " S_BOLD S_BLUE "%d photons" S_RESET ", total: " S_BOLD S_BLUE "%d" S_RESET "\t", out.detected, out.detected);
+                }
+
+                cfg->his.detected = out.detected;
+                cfg->detectedcount = out.saved;
+            }
+
+            cfg->energytot = out.energytot;
+            cfg->energyesc = out.energyesc;
+            MCX_FPRINTF(cfg->flog, "transfer complete:        %d ms\n", GetTimeMillis() - tic0);
+            mcx_flush(cfg);
+        }
+    } else {
+        sims.assign(workdev, (mcxb_sim*)NULL);
+    }
+
+    /* ---- -D P / single device: one resident simulation per device; seed slices follow each other in ONE stream ---- */
+
+    for (unsigned int i = 0; i < sims.size() && rc == MCXB_OK; i++) {
         mcxb_config c;
         fill_config(cfg, &c);
         c.nphoton = share[i];
@@ -319,7 +417,7 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         }
     }
 
-    if (rc == MCXB_OK) {
+    if (rc == MCXB_OK && !multi) {
         if (cfg->exportfield == NULL && cfg->issave2pt) {
             cfg->exportfield = (float*)calloc(fieldlen, sizeof(float));
         }
@@ -451,7 +549,7 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         mcx_flush(cfg);
     }
 
-    for (unsigned int i = 0; i < workdev; i++) {
+    for (size_t i = 0; i < sims.size(); i++) {
         mcxb_sim_destroy(sims[i]);      /* full teardown before any error is raised (:35-49, 1846-1848) */
     }
 

@@ -116,6 +116,20 @@ class GPUInfo(C.Structure):
     ]
 
 
+MAX_DEVICES = 16
+
+
+class MultiInfo(C.Structure):
+    """struct mcxb_multi_info"""
+    _fields_ = [
+        ("ndev", C.c_int32), ("nccl_version", C.c_int32),
+        ("share", C.c_uint64 * MAX_DEVICES),
+        ("detected", C.c_uint32 * MAX_DEVICES),
+        ("nthread", C.c_uint32 * MAX_DEVICES),
+        ("kernel_ms", C.c_float * MAX_DEVICES),
+    ]
+
+
 class TraceStep(C.Structure):
     """struct mcxb_trace_step"""
     _fields_ = [
@@ -130,6 +144,9 @@ _VP = C.c_void_p
 SYMBOLS = [
     ("mcxb_list_gpu", C.c_int, [C.POINTER(GPUInfo), C.c_int]),
     ("mcxb_run_simulation", C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(Output)]),
+    ("mcxb_run_simulation_multi", C.c_int, [C.POINTER(Config), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float), C.POINTER(Output), C.POINTER(MultiInfo)]),
+    ("mcxb_split_photons", None, [C.c_uint64, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint64)]),
+    ("mcxb_nccl_version", C.c_int, []),
     ("mcxb_last_error", C.c_char_p, []),
     ("mcxb_release_cached_buffers", None, []),
     ("mcxb_sim_create", C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(_VP)]),

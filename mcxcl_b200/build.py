@@ -66,13 +66,13 @@ def build(force=False, jobs=None, verbose=True, defines=(), variant=None):
         work.append(([NVCC] + flags + ["-DMCXB_INST_GROUP=%d" % g, "-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", obj],
                      os.path.join(objdir, "kernels_g%d.log" % g)))
         objs.append(obj)
-    for name in ("engine", "testhooks"):
+    for name in ("engine", "engine_multi", "testhooks"):
         obj = os.path.join(objdir, name + ".o")
         work.append(([NVCC] + flags + ["-c", os.path.join(CSRC, name + ".cu"), "-o", obj], os.path.join(objdir, name + ".log")))
         objs.append(obj)
     with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as ex:
         list(ex.map(_run, work))
-    _run(([NVCC, "-shared", "-o", lib] + objs + ["-lcudart"], os.path.join(objdir, "link.log")))
+    _run(([NVCC, "-shared", "-o", lib] + objs + ["-lcudart", "-ldl"], os.path.join(objdir, "link.log")))
     with open(stamp, "w") as f:
         f.write(digest)
     if verbose:

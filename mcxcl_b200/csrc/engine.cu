@@ -54,6 +54,12 @@ extern "C" const char* mcxb_last_error(void) {
     return g_last_error.c_str();
 }
 
+/* not part of the public header: lets the other translation units of the library (engine_multi.cu) report through the
+ * same per-thread message */
+extern "C" void mcxb_set_last_error(const char* msg) {
+    g_last_error = msg ? msg : "";
+}
+
 /* -------------------------------------------------------------------------------------------------
  * glibc-compatible rand() stream (TYPE_3 additive feedback generator, degree 31, separation 3), so the
  * per-thread seeds are the ones the reference host produces with srand(seed); rand() without
@@ -386,7 +392,7 @@ struct mcxb_sim {
 };
 
 /* det: 0 = no detector capture, 1 = the default record, 2 = any record flags (generic kernels take 1 and 2 alike) */
-static const KernelEntry* find_kernel(int src, bool refl, int det, bool m16, bool acc64, bool stats, bool common) {
+static const KernelEntry* find_kernel(int src, bool refl, int det, bool m16, bool acc64, bool stats, bool common, bool queue = false) {
     typedef const KernelEntry* (*GroupFn)(int*);
     static const GroupFn groups[kNumGroups] = { mcxb_kernel_group_0, mcxb_kernel_group_1, mcxb_kernel_group_2, mcxb_kernel_group_3,
                                                 mcxb_kernel_group_4, mcxb_kernel_group_5, mcxb_kernel_group_6
@@ -404,7 +410,7 @@ static const KernelEntry* find_kernel(int src, bool refl, int det, bool m16, boo
                 const bool detok = wantgen[pass] ? ((e[i].savedet != 0) == (det != 0)) : (e[i].savedet == det);
 
                 if (e[i].src == wantsrc[pass] && e[i].generic == wantgen[pass] && e[i].reflect == refl && detok &&
-                        e[i].media16 == m16 && e[i].acc64 == acc64 && e[i].stats == stats) {
+                        e[i].media16 == m16 && e[i].acc64 == acc64 && e[i].stats == stats && (e[i].queue != 0) == (queue && !wantgen[pass])) {
                     return e + i;
                 }
             }
@@ -449,6 +455,9 @@ static bool needs_reflection(const mcxb_config* cfg) {
 
     return cfg->isreflect || (!allabsorb && !allunknown);
 }
+
+/* the scattering-queue kernels are chosen when the mean mus per voxel is at most this (see sim_create_impl) */
+static constexpr double kQueueMaxMus = 2.5;
 
 static uint32_t count_gates(const mcxb_config* cfg) {
     return (uint32_t)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);
@@ -704,6 +713,25 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     }
 
     s->media16 = maxlabel > 127;
+    /* mean scattering coefficient per voxel edge over the non-zero voxels (mus is already scaled by unitinmm): decides
+     * between the kernels with and without the scattering queue below */
+    double mus_voxel = 0.0;
+    {
+        std::vector<uint64_t> hist(cfg->medianum, 0);
+
+        for (uint64_t i = 0; i < dimxyz; i++) {
+            hist[cfg->vol[i] & 0x7FFFFFFFu]++;
+        }
+
+        double sum = 0.0, cnt = 0.0;
+
+        for (uint32_t m = 1; m < cfg->medianum; m++) {
+            sum += (double)hist[m] * cfg->prop[m].y;
+            cnt += (double)hist[m];
+        }
+
+        mus_voxel = cnt > 0.0 ? sum / cnt : 0.0;
+    }
 
     if (maxlabel > 32767) {
         return fail(MCXB_ERR_ARG, "more than 32767 media labels are not supported");
@@ -828,8 +856,29 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     const bool stats = (cfg->debuglevel & MCXB_DEBUG_STATS) != 0;
     const bool common = is_common_config(cfg, savedet, nphase);
     const int detmode = savedet ? (flag == 0x5u ? 1 : 2) : 0;
-    const KernelEntry* ke = stats ? find_kernel(srcAny, true, 1, s->media16, true, true, false)
-                            : find_kernel(cfg->srctype, refl, detmode, s->media16, s->acc64, false, common);
+    /* Scattering queue (photon_kernel.cuh): pays where a packet crosses several voxels per scattering event.  Measured on
+     * B200: +8..10 % at mus = 1 per voxel (cube60 / cube60b), +20 % at mus <= 0.2 (skinvessel), -9..-12 % at mus = 8..40
+     * (colin27, digimouse).  Not used when seeds are recorded (a replay must see the reference's draw order) or when the
+     * record holds anything but the default fields. */
+    bool queue = common && !stats && detmode < 2 && !s->media16 && s->acc64 && cfg->issaveseed <= 0 && mus_voxel <= kQueueMaxMus;
+
+    if (const char* e = getenv("MCXB_SCATTER_QUEUE")) {       /* tuning override: 0 = never, 1 = whenever a queue kernel exists */
+        queue = queue ? atoi(e) != 0 : (atoi(e) != 0 && common && !stats && detmode < 2 && !s->media16 && s->acc64 && cfg->issaveseed <= 0);
+    }
+
+    const KernelEntry* ke = nullptr;
+
+    if (stats) {
+        ke = find_kernel(srcAny, true, 1, s->media16, true, true, false);
+    } else {
+        if (queue) {
+            ke = find_kernel(cfg->srctype, refl, detmode, s->media16, s->acc64, false, common, true);
+        }
+
+        if (!ke) {
+            ke = find_kernel(cfg->srctype, refl, detmode, s->media16, s->acc64, false, common, false);
+        }
+    }
 
     if (!ke) {
         return fail(MCXB_ERR_ARG, "no kernel specialisation for this configuration");
@@ -839,23 +888,43 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         s->acc64 = true;
     }
 
-    s->fn = ke->fn;
-    s->kname = ke->name;
     const uint32_t ftablen = (nphase + nangle + 1u) & ~1u;
-    s->smem = sizeof(float4) * tablen + sizeof(float) * ftablen + (ke->savedet ? sizeof(float) * partialdata * kBlock : 0)
-              + ((savedet && cfg->issaveseed) ? 2 * sizeof(unsigned long long) * kBlock : 0)
-              + (cfg->extrasrclen ? sizeof(int) * kBlock : 0);      /* source id per thread (common kernels) */
-
-    if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
-        return fail(MCXB_ERR_NOMEM, "configuration needs %zu bytes of shared memory per block (limit %zu)", s->smem, (size_t)prop.sharedMemPerBlockOptin);
-    }
-
-    if (s->smem > 48 * 1024) {
-        CU_TRY(cudaFuncSetAttribute((const void*)s->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
-    }
-
     int perSM = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (const void*)s->fn, kBlock, s->smem));
+
+    for (int attempt = 0; attempt < 2; attempt++) {
+        s->fn = ke->fn;
+        s->kname = ke->name;
+        s->smem = sizeof(float4) * ke->queue * kBlock      /* scattering queue (photon_kernel.cuh) */
+                  + sizeof(float4) * tablen + sizeof(float) * ftablen + (ke->savedet ? sizeof(float) * partialdata * kBlock : 0)
+                  + ((savedet && cfg->issaveseed) ? 2 * sizeof(unsigned long long) * kBlock : 0)
+                  + (cfg->extrasrclen ? sizeof(int) * kBlock : 0);      /* source id per thread (common kernels) */
+        const bool fits = s->smem <= (size_t)prop.sharedMemPerBlockOptin;
+
+        if (fits) {
+            if (s->smem > 48 * 1024) {
+                CU_TRY(cudaFuncSetAttribute((const void*)s->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+            }
+
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (const void*)s->fn, kBlock, s->smem));
+        }
+
+        if (ke->queue && (!fits || perSM < MCXB_MINBLOCKS)) {
+            /* the queue's shared memory would cost resident blocks (many partial-path rows): scatter in place instead */
+            ke = find_kernel(cfg->srctype, refl, detmode, s->media16, s->acc64, false, common, false);
+
+            if (!ke) {
+                return fail(MCXB_ERR_ARG, "no kernel specialisation for this configuration");
+            }
+
+            continue;
+        }
+
+        if (!fits) {
+            return fail(MCXB_ERR_NOMEM, "configuration needs %zu bytes of shared memory per block (limit %zu)", s->smem, (size_t)prop.sharedMemPerBlockOptin);
+        }
+
+        break;
+    }
 
     if (perSM < 1) {
         return fail(MCXB_ERR_NOMEM, "photon kernel does not fit on an SM");

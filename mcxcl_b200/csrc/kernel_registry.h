@@ -18,6 +18,7 @@ struct KernelEntry {
     bool reflect;
     int  savedet;      /* 0 none, 1 default record folded at compile time, 2 record flags at run time */
     bool media16, acc64, stats, generic;
+    int  queue;        /* depth of the scattering queue (shared memory, 16 bytes x depth per thread), 0 = none */
     PhotonKernelFn fn;
     const char* name;
 };

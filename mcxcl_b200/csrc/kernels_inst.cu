@@ -2,7 +2,8 @@
  * kernels_inst.cu -- explicit instantiations of photon_kernel, one group per compilation
  * (nvcc ... -DMCXB_INST_GROUP=k).  See kernel_registry.h.
  *
- *   "common" = the GEN=false form of the kernel (photon_kernel.cuh), "generic" = every option at run time
+ *   "common" = the GEN=false form of the kernel (photon_kernel.cuh), "generic" = every option at run time; every
+ *   common group also carries its fp64 kernels with the scattering queue (q8)
  *   group 0: pencil beam,           8-bit media, common
  *   group 1: disk source,           8-bit media, common
  *   group 2: planar + fourier,      8-bit media, common
@@ -19,24 +20,31 @@
 
 namespace mcxb {
 
-#define MCXB_K(SRC, R, D, M, A, S, G) { SRC, R, D, sizeof(M) == 2, sizeof(A) == 8, S, G, photon_kernel<SRC, R, D, M, A, S, G>, #SRC "/" #R "/det" #D "/" #M "/" #A "/" #G }
+#define MCXB_STR2(x) #x
+#define MCXB_STR(x) MCXB_STR2(x)
+#define MCXB_KQ(SRC, R, D, M, A, S, G, Q) { SRC, R, D, sizeof(M) == 2, sizeof(A) == 8, S, G, Q, photon_kernel<SRC, R, D, M, A, S, G, Q>, #SRC "/" #R "/det" #D "/" #M "/" #A "/" #G "/q" MCXB_STR(Q) }
+#define MCXB_K(SRC, R, D, M, A, S, G) MCXB_KQ(SRC, R, D, M, A, S, G, 0)
 /* reflection x detector capture (0 = none, 1 = default record) */
 #define MCXB_RD(SRC, M, A, G) MCXB_K(SRC, false, 0, M, A, false, G), MCXB_K(SRC, true, 0, M, A, false, G), \
                               MCXB_K(SRC, false, 1, M, A, false, G), MCXB_K(SRC, true, 1, M, A, false, G)
+/* the same four common-configuration kernels with the scattering queue (weakly scattering media, photon_kernel.cuh) */
+#define MCXB_RDQ(SRC, M, A) MCXB_KQ(SRC, false, 0, M, A, false, false, MCXB_QUEUE_DEPTH), MCXB_KQ(SRC, true, 0, M, A, false, false, MCXB_QUEUE_DEPTH), \
+                            MCXB_KQ(SRC, false, 1, M, A, false, false, MCXB_QUEUE_DEPTH), MCXB_KQ(SRC, true, 1, M, A, false, false, MCXB_QUEUE_DEPTH)
 /* common-configuration kernels that read the record flags at run time (any -w / savedetflag) */
 #define MCXB_D2(SRC, M, A) MCXB_K(SRC, false, 2, M, A, false, false), MCXB_K(SRC, true, 2, M, A, false, false)
 
 static const KernelEntry entries[] = {
 #if MCXB_INST_GROUP == 0
-    MCXB_RD(srcPencil, uint8_t, double, false), MCXB_RD(srcPencil, uint8_t, float, false), MCXB_D2(srcPencil, uint8_t, double)
+    MCXB_RD(srcPencil, uint8_t, double, false), MCXB_RD(srcPencil, uint8_t, float, false), MCXB_D2(srcPencil, uint8_t, double), MCXB_RDQ(srcPencil, uint8_t, double)
 #elif MCXB_INST_GROUP == 1
-    MCXB_RD(srcDisk, uint8_t, double, false), MCXB_RD(srcDisk, uint8_t, float, false), MCXB_D2(srcDisk, uint8_t, double)
+    MCXB_RD(srcDisk, uint8_t, double, false), MCXB_RD(srcDisk, uint8_t, float, false), MCXB_D2(srcDisk, uint8_t, double), MCXB_RDQ(srcDisk, uint8_t, double)
 #elif MCXB_INST_GROUP == 2
-    MCXB_RD(srcPlanar, uint8_t, double, false), MCXB_RD(srcFourier, uint8_t, double, false)
+    MCXB_RD(srcPlanar, uint8_t, double, false), MCXB_RD(srcFourier, uint8_t, double, false), MCXB_RDQ(srcPlanar, uint8_t, double), MCXB_RDQ(srcFourier, uint8_t, double)
 #elif MCXB_INST_GROUP == 3
-    MCXB_RD(srcIsotropic, uint8_t, double, false), MCXB_RD(srcCone, uint8_t, double, false)
+    MCXB_RD(srcIsotropic, uint8_t, double, false), MCXB_RD(srcCone, uint8_t, double, false), MCXB_RDQ(srcIsotropic, uint8_t, double), MCXB_RDQ(srcCone, uint8_t, double)
 #elif MCXB_INST_GROUP == 4
-    MCXB_RD(srcAny, uint8_t, double, false), MCXB_RD(srcAny, uint8_t, float, false), MCXB_D2(srcAny, uint8_t, double), MCXB_D2(srcAny, uint8_t, float)
+    MCXB_RD(srcAny, uint8_t, double, false), MCXB_RD(srcAny, uint8_t, float, false), MCXB_D2(srcAny, uint8_t, double), MCXB_D2(srcAny, uint8_t, float),
+    MCXB_RDQ(srcAny, uint8_t, double)
 #elif MCXB_INST_GROUP == 5
     MCXB_RD(srcAny, uint8_t, double, true), MCXB_RD(srcAny, uint8_t, float, true), MCXB_K(srcAny, true, 1, uint8_t, double, true, true)
 #elif MCXB_INST_GROUP == 6

@@ -154,6 +154,40 @@ def run_prepared(prepared, device=0, field=None):
     return _result(p, out, field, det, seeds)
 
 
+def run_prepared_multi(prepared, devices, workload=None, field=None):
+    """One call, several GPUs of this box, one host process: mcxb_run_simulation_multi (photon shards, NCCL reduce of
+    the volume and energies, gather of the detected-photon records onto devices[0]).  Returns the result dictionary of
+    run_prepared plus `multi` = the per-device report."""
+    lib = abi.load()
+    p = prepared
+    c = p.c
+    out = abi.Output()
+    if field is None:
+        field = np.zeros(p.fieldlen, dtype=np.float32)
+    out.field = field.ctypes.data_as(C.POINTER(C.c_float))
+    out.fieldlen = field.size
+    det = seeds = None
+    if c.issavedet and not (c.debuglevel & 1):
+        det = np.zeros((c.maxdetphoton, max(1, p.reclen)), dtype=np.float32)
+        out.detphoton = det.ctypes.data_as(C.POINTER(C.c_float))
+        if c.issaveseed:
+            seeds = np.zeros((c.maxdetphoton, 2), dtype=np.uint64)
+            out.seeddata = seeds.ctypes.data_as(C.POINTER(C.c_uint64))
+    devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+    wl = None
+    if workload is not None:
+        assert len(workload) == len(devices)
+        wl = (C.c_float * len(devices))(*[float(w) for w in workload])
+    info = abi.MultiInfo()
+    abi.check(lib.mcxb_run_simulation_multi(C.byref(c), devs, len(devices), wl, C.byref(out), C.byref(info)), "mcxb_run_simulation_multi")
+    res = _result(p, out, field, det, seeds)
+    n = info.ndev
+    res["multi"] = dict(ndev=n, nccl_version=info.nccl_version, share=[int(info.share[i]) for i in range(n)],
+                        detected=[int(info.detected[i]) for i in range(n)], nthread=[int(info.nthread[i]) for i in range(n)],
+                        kernel_ms=[float(info.kernel_ms[i]) for i in range(n)])
+    return res
+
+
 def shape_field(p, field):
     """float32[fieldlen] -> (Nx,Ny,Nz,Ngate[,Nsrc]) view, the layout pmcxcl returns (column-major file order
     [Nx][Ny][Nz][Ng][Ns], README.md:1316-1323)."""

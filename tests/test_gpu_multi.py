@@ -1,16 +1,18 @@
 """Multi-GPU paths on a box with at least two B200s (skipped on a single-GPU box):
   * one process per GPU over NCCL (mcxcl_b200.multigpu.run_distributed, launched with torch.distributed.run);
-  * several GPUs from one process through the reference boundary (`mcxcl -G 11`, integration/mcx_cuda_host.cpp)."""
+  * several GPUs from ONE process behind the C ABI (mcxb_run_simulation_multi: NCCL reduce + record gather inside the
+    library), called directly and through the reference boundary (`mcxcl -G 11`, integration/mcx_cuda_host.cpp)."""
 import json
 import os
 import re
+import struct
 import subprocess
 import sys
 
 import numpy as np
 import pytest
 
-from mcxcl_b200 import benchmarks, engine
+from mcxcl_b200 import benchmarks, engine, hostcfg
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -61,13 +63,57 @@ def test_nccl_photon_shards_combine_on_rank0(tmp_path):
     assert res["rawsum"] * 0.005 == pytest.approx(res["energyabs"], rel=2e-3)      # sum(field)*mua == absorbed energy
 
 
+def test_multi_gpu_call_behind_the_c_abi():
+    """mcxb_run_simulation_multi on two devices: workload split, disjoint seed slices, NCCL reduce of volume + energies,
+    gather of the variable-length records and their RNG states onto device 0"""
+    need_two_gpus()
+    cfg = benchmarks.get("cube60b", 400001)
+    cfg["issaveseed"] = 1
+    p = hostcfg.prepare(cfg)
+    r = engine.run_prepared_multi(p, [0, 1], workload=[3.0, 1.0])
+    m = r["multi"]
+    assert m["ndev"] == 2 and m["nccl_version"] >= 20000
+    assert m["share"] == [300001, 100000]
+    assert r["energytot"] == 400001                                 # every packet launched exactly once over the two devices
+    assert r["detected"] == sum(m["detected"]) == r["saved"] == r["detp"].shape[0] == r["seeds"].shape[0]
+    assert min(m["detected"]) > 0 and abs(m["detected"][0] / m["detected"][1] - 3.0) < 0.6
+    assert len({tuple(x) for x in r["seeds"].tolist()}) == r["saved"]        # no RNG state twice: the seed slices are disjoint
+    assert set(np.unique(r["detp"][:, 0]).astype(int)) == {1, 2, 3, 4}
+    raw = r["field"].astype(np.float64) / r["normalizer"]
+    assert raw.sum() * 0.005 == pytest.approx(r["energyabs"], rel=2e-3)      # sum(field) * mua == absorbed energy
+    one = engine.run_prepared(p)
+    assert abs(r["absorbed"] - one["absorbed"]) < 0.004
+    assert abs(r["detected"] - one["detected"]) < 6 * np.sqrt(2 * one["detected"])
+    assert r["normalizer"] == pytest.approx(one["normalizer"], rel=1e-6)
+    # equal shares by default, records clipped at maxdetphoton like the reference (src/mcx_host.cpp:1207-1216)
+    p2 = hostcfg.prepare(dict(benchmarks.get("cube60b", 400000), maxdetphoton=1000))
+    r2 = engine.run_prepared_multi(p2, [0, 1])
+    assert r2["multi"]["share"] == [200000, 200000] and r2["detected"] > 1000 and r2["saved"] == 1000 == r2["detp"].shape[0]
+    # a replay is single-device only (src/mcx_host.cpp:723)
+    with pytest.raises(RuntimeError, match="single device"):
+        rp = hostcfg.prepare(dict(benchmarks.get("cube60b", r["saved"]), seed=np.ascontiguousarray(r["seeds"]).view(np.uint8).reshape(-1, 16).T.copy(),
+                                  detphotons=np.ascontiguousarray(r["detp"].T), outputtype="jacobian"))
+        engine.run_prepared_multi(rp, [0, 1])
+
+
 def test_two_devices_from_one_process_through_the_reference_boundary(tmp_path):
     need_two_gpus()
     exe = os.path.join(ROOT, "integration", "_build", "mcxcl")
     if not os.path.exists(exe):
         pytest.skip("integration/_build/mcxcl not built")
-    r = subprocess.run([exe, "--bench", "cube60b", "-n", "400001", "-G", "11", "-W", "3,1", "-S", "0"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, "--bench", "cube60b", "-n", "400001", "-G", "11", "-W", "3,1", "-w", "DP", "-F", "mc2", "-s", "two"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     out = re.sub(r"\x1b\[[0-9;]*m", "", r.stdout + r.stderr)
     assert r.returncode == 0, out[-2000:]
     assert "with 2 devices" in out and re.search(r"total simulated energy: 400001\.00\s+absorbed:\s*27\.[0-9]+%", out), out[-1500:]
     assert re.search(r"np=300001\.0", out) and re.search(r"np=100000\.0", out)
+    assert "combined over NCCL" in out
+    # the records of BOTH devices reach the .mch file the reference's writer produces
+    m = re.search(r"detected\s+([0-9]+) photons", out)
+    raw = open(os.path.join(tmp_path, "two.mch"), "rb").read()
+    magic, version, maxmedia, detnum, colcount, totalphoton, detected, savedphoton = struct.unpack("<4s7I", raw[:32])
+    assert magic == b"MCXH" and colcount == 3 and totalphoton == 400001 and savedphoton == detected == int(m.group(1))
+    rec = np.frombuffer(raw[64:64 + 4 * colcount * savedphoton], dtype=np.float32).reshape(-1, colcount)
+    assert set(np.unique(rec[:, 0]).astype(int)) == {1, 2, 3, 4} and 1500 < savedphoton < 2200
+    mc2 = np.fromfile(os.path.join(tmp_path, "two.mc2"), dtype=np.float32)
+    one = engine.run(benchmarks.get("cube60b", 400001))
+    np.testing.assert_allclose(mc2.astype(np.float64).sum(), one["flux"].astype(np.float64).sum(), rtol=0.01)

@@ -189,6 +189,38 @@ def test_source_types_match_reference(ref, name):
     assert abs((gy * ax).sum() / gy.sum() - (oy * ax).sum() / oy.sum()) < 0.35
 
 
+def test_scattering_queue_kernels_are_chosen_by_medium_and_agree_with_in_place_scattering(monkeypatch):
+    """The kernels with the per-thread scattering queue (photon_kernel.cuh) draw the same events in another order: they are
+    picked for weakly scattering volumes only, never when seeds are recorded for a replay, and give the same statistics as
+    the kernels that scatter in place."""
+    def kernel(cfg):
+        with engine.Simulation(hostcfg.prepare(cfg)) as sim:
+            return sim.kernel_name
+    assert kernel(benchmarks.get("cube60b", 1000)).endswith("/q8")                   # mus = 1 per voxel
+    assert kernel(benchmarks.get("skinvessel", 1000)).endswith("/q8")                # mus <= 0.19 per voxel
+    assert kernel(benchmarks.get("colin27", 1000)).endswith("/q0")                   # mus = 8..41 per voxel
+    assert kernel(benchmarks.get("digimouse", 1000)).endswith("/q0")
+    assert kernel(dict(benchmarks.get("cube60b", 1000), issaveseed=1)).endswith("/q0")
+    assert kernel(dict(benchmarks.get("cube60b", 1000), savedetflag="dspm")).endswith("/q0")
+    g = golden("cube60b")
+    n = int(g["nphoton"])
+    out = {}
+    for q in ("1", "0"):
+        monkeypatch.setenv("MCXB_SCATTER_QUEUE", q)
+        cfg = benchmarks.get("cube60b", 10 * n)
+        assert kernel(cfg).endswith("/q8" if q == "1" else "/q0")
+        p, r = run_gpu(cfg, seed=int(g["seed0"]) + 7)
+        out[q] = (p, r)
+        z, ok = zscores(raw_field(p, r) / 10.0, g)
+        z = z * np.sqrt(1.0 + 1.0 / 12) / np.sqrt(0.1 + 1.0 / 12)        # the run has 10x the photons of one reference run
+        assert abs(np.mean(z)) < 0.2 and 0.85 < np.std(z) < 1.25 and np.mean(np.abs(z) > 3) < 0.03, (q, np.mean(z), np.std(z))
+        assert r["energytot"] == 10 * n
+    a, b = out["1"][1], out["0"][1]
+    assert abs(a["absorbed"] - b["absorbed"]) < 5 * np.hypot(absorbed_sigma(10 * n, a["absorbed"]), absorbed_sigma(10 * n, b["absorbed"]))
+    assert abs(a["detected"] - b["detected"]) < 5 * np.sqrt(2.0 * b["detected"])
+    assert abs(a["detp"][:, 1].mean() - b["detp"][:, 1].mean()) < 0.03 * b["detp"][:, 1].mean()      # mean partial path of the detected photons
+
+
 def test_generic_source_kernel_equals_specialised():
     """the run-time-dispatch kernel (srcAny, used for the source types without their own instantiation) and a
     compile-time specialisation implement the same sampling: 'line' has no specialisation, 'disk' has one"""
@@ -252,8 +284,8 @@ def test_label_zero_voxels_inside_the_grid(ref, case):
     lab = p.keep["vol"] & 0x7FFFFFFF
     gf, of = raw_field(p, r), o["field"].astype(np.float64)
     assert gf[lab == 0].sum() == 0 and of[lab == 0].sum() == 0
-    for m in (1, 2, 3):
-        np.testing.assert_allclose(gf[lab == m].sum(), of[lab == m].sum(), rtol=0.02)
+    for m, tol in ((1, 0.02), (2, 0.02), (3, 0.06)):       # label 3 holds 1.3 % of the deposits: two 2e5-photon runs differ by ~2 % there
+        np.testing.assert_allclose(gf[lab == m].sum(), of[lab == m].sum(), rtol=tol)
     # the shadow of the pocket: the slab of label-3 voxels right behind it (z 40..59 under the 20x20 opening)
     v3 = p.keep["vol"].reshape(60, 60, 60)          # [z][y][x] view of the x-fastest volume
     sel = np.zeros((60, 60, 60), bool)

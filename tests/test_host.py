@@ -164,3 +164,25 @@ def test_engine_refuses_to_run_without_a_gpu(lib):
         engine.run(benchmarks.get("cube60", 100))
     assert "failed" in str(e.value)
     assert engine.gpuinfo() == []
+
+
+def test_photon_split_of_the_multi_gpu_call_matches_the_host_mirror(lib):
+    """mcxb_split_photons (C ABI, used by mcxb_run_simulation_multi) == multigpu.split_photons (one process per GPU):
+    the reference's workload ratio with the remainder given to the first devices (src/mcx_host.cpp:1011-1012)"""
+    import ctypes as C
+    from mcxcl_b200 import multigpu
+    for nph, wl in ((10, [1, 1, 1]), (1000000000, [1] * 8), (1000, [3, 1]), (7, [0, 1, 1]), (400001, [3, 1]), (0, [1, 1])):
+        share = (C.c_uint64 * len(wl))()
+        lib.mcxb_split_photons(nph, (C.c_float * len(wl))(*wl), len(wl), share)
+        assert list(share) == multigpu.split_photons(nph, wl)
+    share = (C.c_uint64 * 3)()
+    lib.mcxb_split_photons(10, None, 3, share)                  # no weights: equal shares
+    assert list(share) == [4, 3, 3]
+
+
+def test_nccl_is_bound_at_run_time(lib):
+    """no link-time dependency on NCCL: the library loads without it and reports the version it finds by dlopen"""
+    import subprocess
+    out = subprocess.run(["ldd", os.path.join(ROOT, "mcxcl_b200", "libmcxb200.so")], capture_output=True, text=True).stdout
+    assert "nccl" not in out
+    assert lib.mcxb_nccl_version() >= 20000
