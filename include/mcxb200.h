@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCXB_ABI_VERSION 2
+#define MCXB_ABI_VERSION 3
 
 /* error codes returned by every entry point (0 = success).  The reference reports OpenCL errors
  * negated through ocl_assess (src/mcx_host.cpp:213-217); CUDA runtime errors are reported the same
@@ -84,8 +84,11 @@ enum mcxb_sched {
  * MCXB_ACCUM_F32 selects plain fp32 reductions (half the L2 footprint, fine below ~1e7 photons). */
 enum mcxb_accum { MCXB_ACCUM_F64 = 0, MCXB_ACCUM_F32 = 1 };
 
-#define MCXB_DEBUG_RNG   1u
+#define MCXB_DEBUG_RNG       1u      /* MCX_DEBUG_RNG  (src/mcx_const.h:69) */
+#define MCXB_DEBUG_MOVE      2u      /* MCX_DEBUG_MOVE: record photon trajectories (`-D M`, src/mcx_core.cl:929-959) */
+#define MCXB_DEBUG_MOVE_ONLY 8u      /* MCX_DEBUG_MOVE_ONLY: trajectories only; the front-end turns volume and detector output off (src/mcx_utils.c:1552-1555) */
 #define MCXB_DEBUG_STATS 0x10000u
+#define MCXB_TRAJ_RECLEN 6           /* MCX_DEBUG_REC_LEN: {photon id (uint32 bits), x, y, z, weight, source id} */
 
 typedef struct mcxb_config {
     uint32_t abi_version;          /* must be MCXB_ABI_VERSION */
@@ -163,6 +166,18 @@ typedef struct mcxb_config {
     const float*    replay_tof;    /* its time of flight in seconds: selects the time gate of the sensitivity outputs */
     const int32_t*  replay_detid;  /* its detector (low 16 bits, 1-based); needed when replaydet == -1 */
     int32_t         replaydet;     /* -1: one output volume per detector; otherwise one volume */
+
+    /* ---- repetitions: Config.respin (`-r`).  nphoton is split into `respin` batches launched one after the other,
+     *      each with the next slice of the seed stream (the reference reseeds from the continuing rand() stream,
+     *      src/mcx_host.cpp:1319-1332); volumes, energies and detected photons accumulate over the batches and are
+     *      read back and normalised ONCE.  0 and 1 both mean a single batch.  (The reference's own accumulation for
+     *      respin > 1 adds the running device volume into the export buffer once per batch, :1280-1296, which
+     *      over-counts by a factor 2R/(R+1) after normalisation; that arithmetic is not reproduced.) ---- */
+    int32_t  respin;
+    /* ---- trajectories: Config.maxjumpdebug, with MCXB_DEBUG_MOVE / MCXB_DEBUG_MOVE_ONLY in debuglevel.  One record per
+     *      launch, per scattering event and per termination of every packet (src/mcx_core.cl:1497-1503, 2243-2249,
+     *      2625-2632), up to maxjumpdebug records, in arbitrary order (one atomic counter) ---- */
+    uint32_t maxjumpdebug;
 } mcxb_config;
 
 typedef struct mcxb_output {
@@ -184,6 +199,11 @@ typedef struct mcxb_output {
     uint32_t  nthread, nblocksize; /* launch shape actually used */
     uint64_t  kernel_launches;     /* number of CUDA kernels this call launched */
     uint64_t  stats[3];            /* MCXB_DEBUG_STATS: ray segments, fluence deposits, scattering events */
+    /* trajectories (caller-owned, maxjumpdebug * MCXB_TRAJ_RECLEN floats, or NULL); what the reference keeps in
+     * cfg->exportdebugdata / debugdatalen (src/mcx_host.cpp:1173-1193) */
+    float*    debugdata;
+    uint32_t  debugrecorded;       /* positions the kernel wanted to record (may exceed maxjumpdebug) */
+    uint32_t  debugdatalen;        /* records stored = min(debugrecorded, maxjumpdebug) */
 } mcxb_output;
 
 /* subset of GPUInfo (src/mcx_utils.h:143-163) */
@@ -254,6 +274,11 @@ int  mcxb_sim_launch(mcxb_sim* sim, void* cuda_stream);                     /* e
  * gprogress word (src/mcx_host.cpp:1112-1141) */
 int  mcxb_sim_progress(mcxb_sim* sim, uint64_t* claimed, int* finished);
 int  mcxb_sim_set_photons(mcxb_sim* sim, uint64_t nphoton);                 /* change the photon budget of the next launch */
+/* Config.respin on a resident simulation: nphoton in `respin` batches launched back to back WITHOUT a reset in between
+ * (results accumulate on the device); batch k takes the seed-stream slice seed_skip + k * seed_stride (seed_stride = the
+ * threads of all devices of the job).  Returns the summed kernel time.  A second mcxb_sim_launch without mcxb_sim_reset
+ * accumulates in the same way. */
+int  mcxb_sim_run_batches(mcxb_sim* sim, uint64_t nphoton, uint32_t respin, int32_t seed, uint64_t seed_skip, uint64_t seed_stride, float* kernel_ms);
 int  mcxb_sim_reseed(mcxb_sim* sim, int32_t seed, uint64_t seed_skip);      /* new per-thread seed slice (rank r: skip r*nthread) */
 int  mcxb_sim_finalize(mcxb_sim* sim, void* cuda_stream);                   /* accumulators -> float32 volume on the device; asynchronous */
 int  mcxb_sim_fetch(mcxb_sim* sim, void* cuda_stream, mcxb_output* out);    /* finalize if needed, sync, D2H, add into out->field, normalise */
@@ -311,6 +336,11 @@ int mcxb_test_refract(int device, mcxb_f4* v, const float* n1, const float* n2, 
  * launch in ms and the number of reductions per launch. */
 int mcxb_bench_red(int device, int elem_bytes, uint64_t span_elems, uint32_t nblock, uint32_t iters,
                    uint32_t hot_permille, uint32_t repeats, float* ms_out, uint64_t* ops_out);
+
+/* measurement hook (profiles/r2_deposit_variants.md): only the SMs selected by `mode` (0 all, 1/2 lower/upper half of the
+ * SM ids, 3/4 even/odd ids) issue fp64 reductions into one 32-byte sector; run under ncu to see where the L2 "lookup miss"
+ * of a reduction comes from.  Returns the reductions issued and the sum that arrived (they must be equal). */
+int mcxb_bench_red_die(int device, int mode, uint32_t nblock, uint32_t iters, uint64_t* issued_out, double* sum_out);
 
 /* glibc rand()-compatible seed table used by mcxb_sim_create (src/mcx_host.cpp:696-700, 759-768) */
 void mcxb_fill_seeds(int32_t seed, uint64_t skip_records, uint64_t nrecords, uint32_t* out4);

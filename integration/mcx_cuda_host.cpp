@@ -120,7 +120,9 @@ void fill_config(const Config* cfg, mcxb_config* c) {
     c->outputtype = cfg->outputtype;
     c->isnormalized = 0;               /* normalised once, after every device has been summed */
     c->issave2pt = cfg->issave2pt;
-    c->debuglevel = cfg->debuglevel & MCX_DEBUG_RNG;
+    c->debuglevel = cfg->debuglevel & (MCX_DEBUG_RNG | MCX_DEBUG_MOVE | MCX_DEBUG_MOVE_ONLY);
+    c->maxjumpdebug = cfg->maxjumpdebug;
+    c->respin = cfg->respin;
     c->nthread = cfg->autopilot ? 0 : cfg->nthread;
     c->nblocksize = cfg->autopilot ? 0 : cfg->nblocksize;
     c->sched = MCXB_SCHED_DYNAMIC;
@@ -154,12 +156,12 @@ void check_supported(const Config* cfg) {
         mcx_error(-1, "RF replay is outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
     }
 
-    if (cfg->respin != 1) {
-        mcx_error(-1, "respin != 1 is not supported by the CUDA engine", __FILE__, __LINE__);
+    if (cfg->respin < 1) {
+        mcx_error(-1, "negative respin is not supported by the CUDA engine", __FILE__, __LINE__);
     }
 
-    if (cfg->polmedianum || cfg->omega > 0.f || (cfg->debuglevel & (MCX_DEBUG_MOVE | MCX_DEBUG_MOVE_ONLY))) {
-        mcx_error(-1, "polarised, RF and trajectory-saving modes are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
+    if (cfg->polmedianum || cfg->omega > 0.f) {
+        mcx_error(-1, "polarised and RF modes are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
     }
 }
 
@@ -313,7 +315,7 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
     std::vector<mcxb_sim*> sims;
     uint64_t seedskip = 0;
     int rc = MCXB_OK;
-    const bool multi = workdev > 1 && !(cfg->debuglevel & MCX_DEBUG_PROGRESS) && !(cfg->debuglevel & MCX_DEBUG_RNG);
+    const bool multi = workdev > 1 && !(cfg->debuglevel & (MCX_DEBUG_PROGRESS | MCX_DEBUG_RNG | MCX_DEBUG_MOVE | MCX_DEBUG_MOVE_ONLY));
 
     if (multi) {
         /* ---- all selected devices in ONE engine call: shards + NCCL exchange + one read-back ---- */
@@ -338,7 +340,7 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         cfg->his.savedetflag = cfg->savedetflag;
         cfg->his.totalsource = cfg->extrasrclen + 1;
         cfg->his.detected = 0;
-        cfg->his.respin = 1;
+        cfg->his.respin = cfg->respin;
         cfg->detectedcount = 0;
         cfg->energytot = cfg->energyesc = cfg->energyabs = 0.0;
         cfg->runtime = 0;
@@ -439,7 +441,7 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         cfg->his.savedetflag = cfg->savedetflag;
         cfg->his.totalsource = cfg->extrasrclen + 1;
         cfg->his.detected = 0;
-        cfg->his.respin = 1;
+        cfg->his.respin = cfg->respin;
         cfg->detectedcount = 0;
         cfg->energytot = cfg->energyesc = cfg->energyabs = 0.0;
         cfg->runtime = 0;
@@ -454,11 +456,67 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         const unsigned int tic0 = GetTimeMillis();
         MCX_FPRINTF(cfg->flog, "lauching mcx_main_loop for time window [%.1fns %.1fns] ...\n", cfg->tstart * 1e9, cfg->tend * 1e9);
 
-        for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+        /* `-r R`: the budget of every device in R batches, each with the next slice of the seed stream, accumulated on the
+         * device and read back once (mcxb200.h, mcxb_config.respin) */
+        const unsigned int respin = (unsigned int)std::max(1, cfg->respin);
+        const uint64_t seedstride = seedskip;        /* threads of all devices: one slice per device and batch */
+        float kernelms = 0.f;
+
+        for (unsigned int i = 0; i < workdev; i++) {
             MCX_FPRINTF(cfg->flog, "- [device %d(%d): %s] threadph=%d extra=%d np=%.1f nthread=%u nblock=%d repetition=%d\n",
-                        i, gpu[i].id, gpu[i].name, (int)(share[i] / mcxb_sim_nthread(sims[i])), (int)(share[i] % mcxb_sim_nthread(sims[i])),
-                        (double)share[i], mcxb_sim_nthread(sims[i]), (int)gpu[i].autoblock, 1);
-            rc = mcxb_sim_launch(sims[i], NULL);
+                        i, gpu[i].id, gpu[i].name, (int)(share[i] / respin / mcxb_sim_nthread(sims[i])), (int)(share[i] / respin % mcxb_sim_nthread(sims[i])),
+                        (double)share[i], mcxb_sim_nthread(sims[i]), (int)gpu[i].autoblock, (int)respin);
+        }
+
+        for (unsigned int iter = 0; iter + 1 < respin && rc == MCXB_OK; iter++) {      /* all batches but the last */
+            uint64_t skip = (uint64_t)iter * seedstride;
+            float batchms = 0.f;
+            MCX_FPRINTF(cfg->flog, "simulation run#%2d ... \n", iter + 1);
+
+            for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+                rc = mcxb_sim_set_photons(sims[i], share[i] / respin + (iter < share[i] % respin ? 1 : 0));
+
+                if (rc == MCXB_OK && iter > 0) {
+                    rc = mcxb_sim_reseed(sims[i], cfg->seed, skip);
+                }
+
+                if (rc == MCXB_OK) {
+                    rc = mcxb_sim_launch(sims[i], NULL);
+                }
+
+                skip += mcxb_sim_nthread(sims[i]);
+            }
+
+            for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+                batchms = std::max(batchms, mcxb_sim_last_kernel_ms(sims[i]));
+            }
+
+            kernelms += batchms;
+        }
+
+        {
+            const unsigned int iter = respin - 1;
+            uint64_t skip = (uint64_t)iter * seedstride;
+
+            if (respin > 1) {
+                MCX_FPRINTF(cfg->flog, "simulation run#%2d ... \n", iter + 1);
+            }
+
+            for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+                if (respin > 1) {
+                    rc = mcxb_sim_set_photons(sims[i], share[i] / respin + (iter < share[i] % respin ? 1 : 0));
+
+                    if (rc == MCXB_OK) {
+                        rc = mcxb_sim_reseed(sims[i], cfg->seed, skip);
+                    }
+                }
+
+                if (rc == MCXB_OK) {
+                    rc = mcxb_sim_launch(sims[i], NULL);
+                }
+
+                skip += mcxb_sim_nthread(sims[i]);
+            }
         }
 
         if ((cfg->debuglevel & MCX_DEBUG_PROGRESS) && rc == MCXB_OK) {
@@ -472,7 +530,7 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
                 rc = mcxb_sim_progress(sims[0], &claimed, &finished);
 
                 if (rc == MCXB_OK && !finished) {
-                    mcx_progressbar((float)((double)claimed / (double)std::max<uint64_t>(1, share[0])), cfg);
+                    mcx_progressbar((float)((double)claimed / (double)std::max<uint64_t>(1, share[0] / respin)), cfg);
                     sleep_ms(50);
                 }
             }
@@ -481,10 +539,14 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
             MCX_FPRINTF(cfg->flog, "\n");
         }
 
-        float kernelms = 0.f;
+        {
+            float batchms = 0.f;
 
-        for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
-            kernelms = std::max(kernelms, mcxb_sim_last_kernel_ms(sims[i]));     /* waits for device i */
+            for (unsigned int i = 0; i < workdev && rc == MCXB_OK; i++) {
+                batchms = std::max(batchms, mcxb_sim_last_kernel_ms(sims[i]));     /* waits for device i */
+            }
+
+            kernelms += batchms;
         }
 
         const unsigned int toc = GetTimeMillis() - tic0;
@@ -512,7 +574,28 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
                 }
             }
 
+            std::vector<float> trajbuf;
+
+            if (cfg->debuglevel & (MCX_DEBUG_MOVE | MCX_DEBUG_MOVE_ONLY)) {
+                trajbuf.resize(std::max<size_t>(1, (size_t)cfg->maxjumpdebug * MCXB_TRAJ_RECLEN));
+                out.debugdata = trajbuf.data();
+            }
+
             rc = mcxb_sim_fetch(sims[i], NULL, &out);
+
+            if (rc == MCXB_OK && out.debugrecorded) {
+                /* src/mcx_host.cpp:1173-1193 */
+                if (out.debugrecorded > cfg->maxjumpdebug) {
+                    MCX_FPRINTF(cfg->flog, S_RED "WARNING: the saved trajectory positions are more than what your have specified (%u > %d), please use the --maxjumpdebug option to specify a greater number\n" S_RESET,
+                                out.debugrecorded, cfg->maxjumpdebug);
+                } else {
+                    MCX_FPRINTF(cfg->flog, "saved trajectory positions: %u, total: %d\t", out.debugrecorded, cfg->debugdatalen + out.debugrecorded);
+                }
+
+                cfg->exportdebugdata = (float*)realloc(cfg->exportdebugdata, (size_t)(cfg->debugdatalen + out.debugdatalen) * MCXB_TRAJ_RECLEN * sizeof(float));
+                memcpy(cfg->exportdebugdata + (size_t)cfg->debugdatalen * MCXB_TRAJ_RECLEN, trajbuf.data(), (size_t)out.debugdatalen * MCXB_TRAJ_RECLEN * sizeof(float));
+                cfg->debugdatalen += out.debugdatalen;
+            }
 
             if (rc != MCXB_OK) {
                 break;
@@ -665,6 +748,15 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
 
         cfg->his.detected = cfg->detectedcount;
         mcx_savedetphoton(cfg->exportdetected, cfg->seeddata, cfg->detectedcount, 0, cfg);
+    }
+
+    if ((cfg->debuglevel & (MCX_DEBUG_MOVE | MCX_DEBUG_MOVE_ONLY)) && cfg->parentid == mpStandalone && cfg->exportdebugdata) {
+        /* src/mcx_host.cpp:1666-1672: <session>.mct, or the Trajectory block of <session>_detp.jdat */
+        cfg->his.colcount = MCXB_TRAJ_RECLEN;
+        cfg->his.savedphoton = cfg->debugdatalen;
+        cfg->his.totalphoton = cfg->nphoton;
+        cfg->his.detected = 0;
+        mcx_savedetphoton(cfg->exportdebugdata, NULL, cfg->debugdatalen, 0, cfg);
     }
 
 #endif

@@ -6,8 +6,10 @@ or ``python -m mcxcl_b200.build``) every entry point raises, it never reroutes t
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DEBUG_RNG = 1
+DEBUG_MOVE, DEBUG_MOVE_ONLY = 2, 8
+TRAJ_RECLEN = 6
 DEBUG_STATS = 0x10000
 ACCUM_F64, ACCUM_F32 = 0, 1
 SCHED_DYNAMIC, SCHED_STATIC = 0, 1
@@ -80,6 +82,8 @@ class Config(C.Structure):
         ("replay_tof", C.POINTER(C.c_float)),
         ("replay_detid", C.POINTER(C.c_int32)),
         ("replaydet", C.c_int32),
+        ("respin", C.c_int32),
+        ("maxjumpdebug", C.c_uint32),
     ]
 
 
@@ -100,6 +104,9 @@ class Output(C.Structure):
         ("nthread", C.c_uint32), ("nblocksize", C.c_uint32),
         ("kernel_launches", C.c_uint64),
         ("stats", C.c_uint64 * 3),
+        ("debugdata", C.POINTER(C.c_float)),
+        ("debugrecorded", C.c_uint32),
+        ("debugdatalen", C.c_uint32),
     ]
 
 
@@ -155,6 +162,7 @@ SYMBOLS = [
     ("mcxb_sim_progress", C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     ("mcxb_sim_set_photons", C.c_int, [_VP, C.c_uint64]),
     ("mcxb_sim_reseed", C.c_int, [_VP, C.c_int32, C.c_uint64]),
+    ("mcxb_sim_run_batches", C.c_int, [_VP, C.c_uint64, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_float)]),
     ("mcxb_sim_finalize", C.c_int, [_VP, _VP]),
     ("mcxb_sim_fetch", C.c_int, [_VP, _VP, C.POINTER(Output)]),
     ("mcxb_sim_field_devptr", _VP, [_VP]),
@@ -178,6 +186,7 @@ SYMBOLS = [
     ("mcxb_test_refract", C.c_int, [C.c_int, _VP, _VP, _VP, _VP, C.c_uint32]),
     ("mcxb_bench_red", C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                  C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
+    ("mcxb_bench_red_die", C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     ("mcxb_fill_seeds", None, [C.c_int32, C.c_uint64, C.c_uint64, _VP]),
 ]
 

@@ -371,6 +371,9 @@ struct mcxb_sim {
     float* d_pattern = nullptr;
     float* d_invcdf = nullptr;
     unsigned long long* d_stats = nullptr;
+    float* d_traj = nullptr;                     /* trajectory records (-D M) and their counter */
+    uint32_t* d_trajcount = nullptr;
+    uint64_t launched_photons = 0;               /* photons of the batches launched since the last reset (respin) */
     unsigned long long* d_rseed = nullptr;      /* replay inputs */
     float* d_rweight = nullptr;
     float* d_rtof = nullptr;
@@ -429,7 +432,7 @@ static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t npha
     }
 
     const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
-    return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->issaveref == 0 &&
+    return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->issaveref == 0 && !(cfg->debuglevel & (MCXB_DEBUG_MOVE | MCXB_DEBUG_MOVE_ONLY)) &&
            cfg->issave2pt != 0 && cfg->replay_seed == nullptr && cfg->srcnum <= 1 &&
            (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE);
 }
@@ -457,7 +460,7 @@ static bool needs_reflection(const mcxb_config* cfg) {
 }
 
 /* the scattering-queue kernels are chosen when the mean mus per voxel is at most this (see sim_create_impl) */
-static constexpr double kQueueMaxMus = 2.5;
+static constexpr double kQueueMaxMus = 2.25;    /* measured crossover on cube60b with mus swept: gain 1.17 at 0.25, 1.08 at 1, 1.02 at 2, 1.00 at 2.5, 0.93 at 10 (profiles/r2_queue_crossover.log) */
 
 static uint32_t count_gates(const mcxb_config* cfg) {
     return (uint32_t)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);
@@ -534,7 +537,7 @@ static void sim_free(mcxb_sim* s) {
 
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();        /* pooled buffers may be handed out again at once: nothing may still be using them */
-    void* bufs[] = { s->d_media, s->d_field, s->d_field32, s->d_tables, s->d_seeds, s->d_det, s->d_detcount, s->d_seedout,
+    void* bufs[] = { s->d_traj, s->d_trajcount, s->d_media, s->d_field, s->d_field32, s->d_tables, s->d_seeds, s->d_det, s->d_detcount, s->d_seedout,
                      s->d_counter, s->d_energy, s->d_pattern, s->d_invcdf, s->d_stats, s->h_field, s->h_small,
                      s->d_rseed, s->d_rweight, s->d_rtof, s->d_rdetid, s->h_progress
                    };
@@ -581,6 +584,18 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
 
     if (cfg->tstep <= 0.f || cfg->tend <= cfg->tstart) {
         return fail(MCXB_ERR_ARG, "incorrect time gate settings");
+    }
+
+    if (cfg->respin < 0) {
+        return fail(MCXB_ERR_ARG, "negative respin is not supported");
+    }
+
+    if (cfg->respin > 1 && cfg->replay_seed) {
+        return fail(MCXB_ERR_ARG, "respin is disabled in the replay mode");       /* src/mcx_utils.c:1633-1636 */
+    }
+
+    if ((cfg->debuglevel & (MCXB_DEBUG_MOVE | MCXB_DEBUG_MOVE_ONLY)) && cfg->maxjumpdebug == 0) {
+        return fail(MCXB_ERR_ARG, "trajectory capture needs maxjumpdebug > 0");
     }
 
     if (cfg->srcnum > 1) {
@@ -895,7 +910,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         s->fn = ke->fn;
         s->kname = ke->name;
         s->smem = sizeof(float4) * ke->queue * kBlock      /* scattering queue (photon_kernel.cuh) */
-                  + sizeof(float4) * tablen + sizeof(float) * ftablen + (ke->savedet ? sizeof(float) * partialdata * kBlock : 0)
+                  + sizeof(float4) * tablen + ((ke->generic || !MCXB_AUXTAB) ? 0 : 2 * sizeof(float4) * cfg->medianum) + sizeof(float) * ftablen + (ke->savedet ? sizeof(float) * partialdata * kBlock : 0)
                   + ((savedet && cfg->issaveseed) ? 2 * sizeof(unsigned long long) * kBlock : 0)
                   + (cfg->extrasrclen ? sizeof(int) * kBlock : 0);      /* source id per thread (common kernels) */
         const bool fits = s->smem <= (size_t)prop.sharedMemPerBlockOptin;
@@ -970,6 +985,11 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     CU_TRY(dev_alloc(&s->d_counter, device, sizeof(unsigned long long)));
     CU_TRY(dev_alloc(&s->d_detcount, device, sizeof(uint32_t)));
     CU_TRY(dev_alloc(&s->d_stats, device, 3 * sizeof(unsigned long long)));
+
+    if ((cfg->debuglevel & (MCXB_DEBUG_MOVE | MCXB_DEBUG_MOVE_ONLY)) && !s->rngdebug) {
+        CU_TRY(dev_alloc(&s->d_traj, device, sizeof(float) * MCXB_TRAJ_RECLEN * (size_t)cfg->maxjumpdebug));
+        CU_TRY(dev_alloc(&s->d_trajcount, device, sizeof(uint32_t)));
+    }
 
     if (savedet) {
         CU_TRY(dev_alloc(&s->d_det, device, sizeof(float) * std::max<size_t>(1, (size_t)cfg->maxdetphoton * std::max(1u, s->reclen))));
@@ -1069,6 +1089,10 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     P.widedep = (maxgate > 1 ? 1u : 0u) | ((cfg->extrasrclen && cfg->srcid < 0) ? 2u : 0u);
     P.acccopies = s->acccopies;
     P.accstride = s->fieldlen;
+    P.trajdata = s->d_traj;
+    P.trajcount = s->d_trajcount;
+    P.maxjumpdebug = cfg->maxjumpdebug;
+    P.idbase = 0;
 
     if (getenv("MCXB_DEBUG_PTRS")) {
         fprintf(stderr, "mcxb buffers: media %p field %p field32 %p tables %p seeds %p det %p detcount %p counter %p energy %p\n",
@@ -1109,8 +1133,14 @@ extern "C" int mcxb_sim_reset(mcxb_sim* s, void* cuda_stream) {
     CU_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
     CU_TRY(cudaMemsetAsync(s->d_detcount, 0, sizeof(uint32_t), st));
     CU_TRY(cudaMemsetAsync(s->d_stats, 0, 3 * sizeof(unsigned long long), st));
+
+    if (s->d_trajcount) {
+        CU_TRY(cudaMemsetAsync(s->d_trajcount, 0, sizeof(uint32_t), st));
+    }
+
     s->finalized = false;
     s->launched = false;
+    s->launched_photons = 0;
     return MCXB_OK;
 }
 
@@ -1153,6 +1183,15 @@ extern "C" int mcxb_sim_launch(mcxb_sim* s, void* cuda_stream) {
 
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CU_TRY(cudaSetDevice(s->device));
+
+    if (s->launched) {
+        /* another batch on top of the accumulated results (respin): the photon counter starts over, everything else
+         * (volume, energies, detected photons, trajectories) keeps accumulating */
+        CU_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
+        s->finalized = false;
+    }
+
+    s->P.idbase = (uint32_t)s->launched_photons;
     CU_TRY(cudaEventRecord(s->ev0, st));
 
     if (s->rngdebug) {
@@ -1167,6 +1206,7 @@ extern "C" int mcxb_sim_launch(mcxb_sim* s, void* cuda_stream) {
     CU_TRY(cudaEventRecord(s->ev1, st));
     s->launches++;
     s->launched = true;
+    s->launched_photons += s->P.nphoton;
     return MCXB_OK;
 }
 
@@ -1288,6 +1328,19 @@ extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) 
         CU_TRY(cudaMemcpy(out->seeddata, s->d_seedout, 2 * sizeof(unsigned long long) * (size_t)out->saved, cudaMemcpyDeviceToHost));
     }
 
+    out->debugrecorded = out->debugdatalen = 0;
+
+    if (s->d_trajcount) {
+        uint32_t n = 0;
+        CU_TRY(cudaMemcpy(&n, s->d_trajcount, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        out->debugrecorded = n;
+        out->debugdatalen = std::min(n, s->cfg.maxjumpdebug);
+
+        if (out->debugdata && out->debugdatalen) {
+            CU_TRY(cudaMemcpy(out->debugdata, s->d_traj, sizeof(float) * MCXB_TRAJ_RECLEN * (size_t)out->debugdatalen, cudaMemcpyDeviceToHost));
+        }
+    }
+
     out->normalizer = 1.f;
 
     if (wantfield) {
@@ -1404,6 +1457,45 @@ extern "C" float mcxb_sim_last_kernel_ms(mcxb_sim* s) {
     return s->last_ms;
 }
 
+extern "C" int mcxb_sim_run_batches(mcxb_sim* s, uint64_t nphoton, uint32_t respin, int32_t seed, uint64_t seed_skip, uint64_t seed_stride, float* kernel_ms) {
+    /* nphoton split into `respin` batches (remainder to the first ones), batch k seeded from record
+     * seed_skip + k * seed_stride of the seed stream: with seed_stride = the threads of ALL devices of the job every
+     * batch of every device gets its own slice, in the order the reference draws them (src/mcx_host.cpp:1319-1332) */
+    if (!s || respin == 0) {
+        return fail(MCXB_ERR_ARG, "sim is NULL or respin is 0");
+    }
+
+    float total = 0.f;
+
+    for (uint32_t k = 0; k < respin; k++) {
+        const uint64_t batch = nphoton / respin + (k < nphoton % respin ? 1 : 0);
+        int rc = mcxb_sim_set_photons(s, batch);
+
+        if (rc == MCXB_OK && k > 0) {
+            rc = mcxb_sim_reseed(s, seed, seed_skip + (uint64_t)k * seed_stride);
+        }
+
+        if (rc == MCXB_OK) {
+            rc = mcxb_sim_launch(s, nullptr);
+        }
+
+        if (rc != MCXB_OK) {
+            return rc;
+        }
+
+        total += mcxb_sim_last_kernel_ms(s);        /* waits for this batch */
+    }
+
+    s->cfg.nphoton = nphoton;
+    s->P.nphoton = nphoton;
+
+    if (kernel_ms) {
+        *kernel_ms = total;
+    }
+
+    return MCXB_OK;
+}
+
 extern "C" int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_output* out) {
     /* MCXB_TIMING=1 prints where the host time of one call goes (create / reset+launch / fetch / destroy) */
     static const bool timing = getenv("MCXB_TIMING") != nullptr;
@@ -1418,14 +1510,23 @@ extern "C" int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_outp
         rc = mcxb_sim_reset(s, nullptr);
     }
 
-    if (rc == MCXB_OK) {
+    float kernel_ms = 0.f;
+    const uint32_t respin = (uint32_t)std::max(1, cfg->respin);
+
+    if (rc == MCXB_OK && respin == 1) {
         rc = mcxb_sim_launch(s, nullptr);
+    } else if (rc == MCXB_OK) {
+        rc = mcxb_sim_run_batches(s, cfg->nphoton, respin, cfg->seed, cfg->seed_skip, mcxb_sim_nthread(s), &kernel_ms);
     }
 
     t[2] = clk::now();
 
     if (rc == MCXB_OK) {
         rc = mcxb_sim_fetch(s, nullptr, out);
+
+        if (respin > 1 && out) {
+            out->runtime_ms = kernel_ms;        /* the kernel windows of all batches */
+        }
     }
 
     t[3] = clk::now();

@@ -232,6 +232,10 @@ extern "C" int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devi
         return fail(MCXB_ERR_ARG, "replay should only work with a single device");       /* src/mcx_host.cpp:723 */
     }
 
+    if (cfg->debuglevel & (MCXB_DEBUG_MOVE | MCXB_DEBUG_MOVE_ONLY | MCXB_DEBUG_RNG)) {
+        return fail(MCXB_ERR_ARG, "trajectory capture and the RNG debug mode run on one device at a time");
+    }
+
     for (int i = 0; i < ndev; i++) {
         for (int j = 0; j < i; j++) {
             if (devices[i] == devices[j]) {
@@ -313,8 +317,41 @@ extern "C" int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devi
     }
 
     /* ---- launch everywhere, then finalize (accumulators -> float32 volume) on the same streams ---- */
-    for (int i = 0; i < ndev && rc == MCXB_OK; i++) {
-        rc = mcxb_sim_launch(sims[i], nullptr);
+    if (cfg->respin > 1) {
+        /* `-r R`: every device runs its share in R batches; batch k of device i takes slice k * (threads of all devices) +
+         * (threads of devices 0..i-1) of the seed stream.  One host thread per device: a batch waits for the previous one */
+        std::vector<std::thread> th;
+        std::vector<float> bms(ndev, 0.f);
+        uint64_t pre = 0;
+
+        for (int i = 0; i < ndev; i++) {
+            const uint64_t myskip = pre;
+            th.emplace_back([&, i, myskip] {
+                rcs[i] = mcxb_sim_run_batches(sims[i], share[i], (uint32_t)cfg->respin, cfg->seed, myskip, skip, &bms[i]);
+
+                if (rcs[i] != MCXB_OK) {
+                    errs[i] = mcxb_last_error();
+                }
+            });
+            pre += mcxb_sim_nthread(sims[i]);
+        }
+
+        for (auto& t : th) {
+            t.join();
+        }
+
+        for (int i = 0; i < ndev; i++) {
+            if (rcs[i] != MCXB_OK) {
+                rc = fail(rcs[i], "device %d: %s", devs[i], errs[i].c_str());
+                goto done;
+            }
+
+            ms[i] = bms[i];
+        }
+    } else {
+        for (int i = 0; i < ndev && rc == MCXB_OK; i++) {
+            rc = mcxb_sim_launch(sims[i], nullptr);
+        }
     }
 
     for (int i = 0; i < ndev && rc == MCXB_OK; i++) {
@@ -326,7 +363,10 @@ extern "C" int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devi
     }
 
     for (int i = 0; i < ndev; i++) {
-        ms[i] = mcxb_sim_last_kernel_ms(sims[i]);       /* waits for the photon kernel of device i */
+        if (cfg->respin <= 1) {
+            ms[i] = mcxb_sim_last_kernel_ms(sims[i]);   /* waits for the photon kernel of device i */
+        }
+
         CUDA_TRY(cudaSetDevice(devs[i]));
         CUDA_TRY(cudaDeviceSynchronize());               /* finalize done: the exchange streams below are non-blocking ones */
     }

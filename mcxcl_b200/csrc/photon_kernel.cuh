@@ -87,6 +87,11 @@ struct SimParam {
     const int*   replaydetid;
     int32_t      replaydet;
     uint32_t     nrepvol;         /* volumes per source in replay: detnum when replaydet == -1, else 1 */
+    /* trajectory capture (`-D M`, generic kernels): one atomic counter, MCX_DEBUG_REC_LEN = 6 floats per record */
+    float*       trajdata;        /* NULL = off */
+    uint32_t*    trajcount;
+    uint32_t     maxjumpdebug;
+    uint32_t     idbase;          /* photons launched by earlier batches (respin): photon ids continue across batches */
     /* replicated accumulators: CTA b adds into copy (b % acccopies); the copies are summed by finalize_kernel */
     uint32_t     widedep;         /* common kernels: bit 0 = more than one gate, bit 1 = one volume per source */
     uint32_t     acccopies;
@@ -505,6 +510,21 @@ __device__ __forceinline__ void sample_source(const SimParam& P, const float4* _
     }
 }
 
+/* one trajectory record (savedebugdata, src/mcx_core.cl:929-948): {photon id, x, y, z, weight, source id} */
+static __device__ __noinline__ void save_traj(const SimParam& P, uint32_t id, float x, float y, float z, float w, int srcid) {
+    const uint32_t pos = atomicAdd(P.trajcount, 1u);
+
+    if (pos < P.maxjumpdebug) {
+        float* rec = P.trajdata + 6 * (size_t)pos;
+        rec[0] = __uint_as_float(id);
+        rec[1] = x;
+        rec[2] = y;
+        rec[3] = z;
+        rec[4] = w;
+        rec[5] = (float)srcid;
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------------
  * detected-photon record (src/mcx_core.cl:838-926), compacted with one atomic per converged warp
  * ------------------------------------------------------------------------------------------------- */
@@ -623,6 +643,9 @@ constexpr int kBlock = MCXB_BLOCK;
  * scattering event and the block runs every iteration anyway -- engine.cu picks the variant from the mean
  * scattering coefficient per voxel.  Per-thread RNG draw ORDER differs from the reference's, so runs that record
  * seeds for a replay use the kernels without the queue. */
+#ifndef MCXB_AUXTAB
+    #define MCXB_AUXTAB 1
+#endif
 #ifndef MCXB_LAUNCH_IN_TAIL
     #define MCXB_LAUNCH_IN_TAIL 1
 #endif
@@ -641,12 +664,26 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
     float4* tab = smem + QK * kBlock;                     /* optical properties, row 0 = background */
     const float4* srctab = tab + P.medianum;              /* 4 rows per source, main source first  */
     const float4* dettab = srctab + 4 * (1 + P.extrasrclen);
-    float* ftab = reinterpret_cast<float*>(tab + P.tablen);        /* inverse-CDF tables */
+    /* common-configuration kernels: a second copy of the media rows for the segment loop, two float4 per label --
+     * {mua, mus, g, n} and {refined reciprocal of mus, reciprocal of mua, -, -}.  The two reciprocals cost a MUFU each
+     * (and the first one two FMAs of Newton refinement) per segment otherwise; computed here with the very instructions
+     * div_exact uses, so the step length stays bit-identical to the reference's */
+    constexpr bool kAuxTab = !GEN && (MCXB_AUXTAB != 0);
+    float4* const mtab = tab + P.tablen;
+    float* ftab = reinterpret_cast<float*>(mtab + (kAuxTab ? 2 * P.medianum : 0));        /* inverse-CDF tables */
     float* ppath_base = ftab + P.ftablen;                         /* partialdata x blockDim, thread-minor */
     unsigned long long* seed_base = reinterpret_cast<unsigned long long*>(ppath_base + (SAVEDET ? P.partialdata * kBlock : 0));
 
     for (uint32_t i = threadIdx.x; i < P.tablen; i += kBlock) {
         tab[i] = P.tables[i];
+    }
+
+    if (kAuxTab) {
+        for (uint32_t i = threadIdx.x; i < P.medianum; i += kBlock) {
+            const float4 row = P.tables[i];
+            mtab[2 * i] = row;
+            mtab[2 * i + 1] = make_float4(refined_rcp(row.y), mufu_rcp(row.x), 0.f, 0.f);
+        }
     }
 
     for (uint32_t i = threadIdx.x; i < P.nphase; i += kBlock) {
@@ -676,6 +713,25 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
     __syncthreads();
 
+#ifdef MCXB_EXP_SMEMTILE
+    /* measurement only (profiles/r2_deposit_variants.md): a 16^3 fp32 tile of the volume around the source voxel
+     * privatised in shared memory per block, flushed with one global reduction per touched voxel at block exit */
+    __shared__ float exp_tile[4096];
+    int exp_ox, exp_oy, exp_oz;
+    {
+        const float4 sp = srctab[0];
+        exp_ox = max(0, min((int)P.nx - 16, (int)floorf(sp.x) - 8));
+        exp_oy = max(0, min((int)P.ny - 16, (int)floorf(sp.y) - 8));
+        exp_oz = max(0, min((int)P.nz - 16, (int)floorf(sp.z) - 8));
+
+        for (int i = threadIdx.x; i < 4096; i += kBlock) {
+            exp_tile[i] = 0.f;
+        }
+
+        __syncthreads();
+    }
+    int exp_oldtile = -1;
+#endif
     const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
     const MediaT* __restrict__ media = static_cast<const MediaT*>(P.media);
     /* Small volumes are accumulated into several copies (engine.cu picks the count): the few voxels next to the source
@@ -732,6 +788,10 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             /* ------------------------------------------------------------------ retire (:1494-1569) */
             if (!(ph.w != ph.w)) {
                 e_escaped += ph.w;
+
+                if (GEN && P.trajdata) {      /* where the packet ended (:1497-1503) */
+                    save_traj(P, curid + 1u, ph.px, ph.py, ph.pz, ph.w, cursrc);
+                }
 
                 if (GEN && P.issaveref == 1 && ph.label == 0 && ph.idx1d != kOutsideMin && ph.idx1d != kOutsideMax && ph.w > 0.f) {
                     int tshift = max(0, min((int)P.maxgate - 1, (int)floorf((ph.tof - P.twin0) * P.Rtstep)));
@@ -793,6 +853,8 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 curid = nextid++;
                 rng.a = __ldg(P.replayseed + 2 * (size_t)curid);
                 rng.b = __ldg(P.replayseed + 2 * (size_t)curid + 1);
+            } else if (GEN && P.trajdata) {
+                curid = P.idbase + nextid++;      /* the number of this packet in the whole run */
             }
 
             /* ------------------------------------------------------------------ launch (:1598-2255) */
@@ -937,6 +999,10 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             ph.face = -1;
             pacc = 0.f;
             qs &= ~0xFFu;        /* queued directions belonged to the previous packet */
+
+            if (GEN && P.trajdata) {          /* where the packet starts (:2243-2249) */
+                save_traj(P, curid + 1u, ph.px, ph.py, ph.pz, ph.w, cursrc);
+            }
         }
         return false;
     };
@@ -1070,6 +1136,10 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
                 ph.nscat++;
 
+                if (GEN && P.trajdata) {      /* every scattering site (:2625-2632) */
+                    save_traj(P, curid + 1u, ph.px, ph.py, ph.pz, ph.w, cursrc);
+                }
+
                 /* scattering-site sensitivities of a replayed packet (:2567-2592): WP counts the events, DCS sums the
                  * momentum transfer 1-cos(theta), WPTOF weights the count by the time of flight; each scaled by the
                  * detected weight and binned by the DETECTED time of flight */
@@ -1104,17 +1174,24 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
         /* ------------------------------------------------------------------ one ray segment (:2652-2765) */
         ph.n1 = nmed;
+        float rmus = 0.f, rmua = 0.f;
         {
-            const float4 pr = tab[ph.label];
+            const float4 pr = kAuxTab ? mtab[2 * ph.label] : tab[ph.label];
             mua = pr.x;
             mus = pr.y;
             g = pr.z;
             nmed = pr.w;
+
+            if (kAuxTab) {
+                const float2 ax = *reinterpret_cast<const float2*>(mtab + 2 * ph.label + 1);
+                rmus = ax.x;
+                rmua = ax.y;
+            }
         }
         const float dist = face_distance(ph.px, ph.py, ph.pz, ph.vx, ph.vy, ph.vz, ph.ix, ph.iy, ph.iz, ph.face);
         const float musp = (GEN && (uint32_t)(ph.nscat + 1) > P.gscatter) ? __fmul_rn(mus, __fsub_rn(1.f, g)) : mus;
         float slen;
-        const float len = step_length(dist, musp, ph.slen, slen);
+        const float len = kAuxTab ? step_length_r(dist, musp, rmus, ph.slen, slen) : step_length(dist, musp, ph.slen, slen);
         ph.pathlen += len;
         ph.px = advance(ph.px, len, ph.vx);
         ph.py = advance(ph.py, len, ph.vy);
@@ -1170,7 +1247,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             /* common configuration (flux / fluence, one volume per gate): ONE divergent region instead of three nested
              * ones -- every level of nesting costs a BSSY / BRA / BSYNC triple per warp-iteration */
             const bool moved = ph.idx1d != oldidx;
-            const float weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * mufu_rcp(mua));
+            const float weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * (kAuxTab ? rmua : mufu_rcp(mua)));
 
             /* nothing is deposited into a label-0 voxel (:2816: "&& mediaidold") */
             if (moved && oldlabel && ph.tof >= P.twin0 && ph.tof < P.twin1 && fabsf(weight) > 0.f) {
@@ -1189,7 +1266,41 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
                         red_add(static_cast<AccT*>(P.field) + ((size_t)gate * P.dimxyz + (oldidx + copyoff)), weight);
                     } else {
+#if defined(MCXB_EXP_MATCHANY)
+                        /* measurement only: lanes of this warp that deposit into the SAME voxel in this iteration are summed
+                         * first (match.any + shuffles), one reduction per distinct voxel */
+                        const uint32_t act = __activemask();
+                        const uint32_t peers = __match_any_sync(act, oldidx);
+                        const uint32_t lead = __ffs(peers) - 1u;
+                        uint32_t rest = peers & ~(1u << lead);
+                        float sum = weight;
+
+                        while (__any_sync(act, rest != 0u)) {
+                            const int src = rest ? (__ffs(rest) - 1) : (int)lane_id();
+                            const float v = __shfl_sync(act, weight, src);
+
+                            if (lane_id() == lead && rest) {
+                                sum += v;
+                            }
+
+                            rest &= rest - 1u;
+                        }
+
+                        if (lane_id() == lead) {
+                            red_add(static_cast<AccT*>(P.field) + (oldidx + copyoff), sum);
+                        }
+
+#elif defined(MCXB_EXP_SMEMTILE)
+
+                        if (exp_oldtile >= 0) {
+                            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(exp_tile + exp_oldtile)), "f"(weight) : "memory");
+                        } else {
+                            red_add(static_cast<AccT*>(P.field) + (oldidx + copyoff), weight);
+                        }
+
+#else
                         red_add(static_cast<AccT*>(P.field) + (oldidx + copyoff), weight);
+#endif
                     }
                 }
 
@@ -1198,6 +1309,12 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 }
             }
 
+#ifdef MCXB_EXP_SMEMTILE
+            {
+                const uint32_t tx = (uint32_t)(ph.ix - exp_ox), ty = (uint32_t)(ph.iy - exp_oy), tz = (uint32_t)(ph.iz - exp_oz);
+                exp_oldtile = (tx < 16u && ty < 16u && tz < 16u && ph.label) ? (int)(tz * 256u + ty * 16u + tx) : -1;
+            }
+#endif
             ph.w0 = moved ? ph.w : ph.w0;
             ph.pathlen = moved ? 0.f : ph.pathlen;
         } else
@@ -1418,6 +1535,19 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
         }
     }
 
+#ifdef MCXB_EXP_SMEMTILE
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < 4096; i += kBlock) {
+        const float v = exp_tile[i];
+
+        if (v != 0.f) {
+            const uint32_t gi = (uint32_t)(((i >> 8) + exp_oz) * (int)P.dimxy + (((i >> 4) & 15) + exp_oy) * (int)P.nx + ((i & 15) + exp_ox));
+            red_add(field + gi, v);
+        }
+    }
+
+#endif
     /* ---------------------------------------------------------------------- energy bookkeeping (:3301-3302) */
     double esc = (double)e_escaped, lau = (double)e_launched;
 

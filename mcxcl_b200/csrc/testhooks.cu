@@ -313,3 +313,51 @@ done:
 
     return rc;
 }
+
+
+/* ---------------------------------------------------------------------------------------------------
+ * Where does a reduction execute?  (profiles/r2_deposit_variants.md: "50 % of the RED sectors miss in the L2 lookup with
+ * no DRAM traffic".)  Only the SMs selected by `mode` issue `iters` fp64 reductions per thread, all of them into ONE
+ * 32-byte sector: mode 0 = every SM, 1 / 2 = lower / upper half of the SM ids, 3 / 4 = even / odd SM ids.  Run under
+ * `ncu --metrics lts__t_sectors_srcunit_tex_op_red_lookup_{hit,miss}.sum`: if the lookup-miss count follows WHICH SMs
+ * issue the reductions, the "miss" is the hop from the issuing die's L2 to the L2 partition that owns the line, not a
+ * cache miss.
+ * ------------------------------------------------------------------------------------------------- */
+__global__ void hook_red_die(double* buf, uint32_t iters, int mode, uint32_t nsm, unsigned long long* issued) {
+    uint32_t smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    const bool on = mode == 0 || (mode == 1 && smid < nsm / 2) || (mode == 2 && smid >= nsm / 2) || (mode == 3 && (smid & 1u) == 0) || (mode == 4 && (smid & 1u) == 1);
+
+    if (!on) {
+        return;
+    }
+
+    for (uint32_t i = 0; i < iters; i++) {
+        red_add(buf + (threadIdx.x & 3u), 1.f);
+    }
+
+    if (threadIdx.x == 0) {
+        atomicAdd(issued, (unsigned long long)blockDim.x * iters);
+    }
+}
+
+extern "C" int mcxb_bench_red_die(int device, int mode, uint32_t nblock, uint32_t iters, uint64_t* issued_out, double* sum_out) {
+    int rc = MCXB_OK;
+    DevBuf buf, cnt;
+    int nsm = 0;
+    double h[4] = {0, 0, 0, 0};
+    HOOK_TRY(cudaSetDevice(device));
+    HOOK_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    HOOK_TRY(buf.alloc(256));
+    HOOK_TRY(cnt.alloc(8));
+    HOOK_TRY(cudaMemset(buf.p, 0, 256));
+    HOOK_TRY(cudaMemset(cnt.p, 0, 8));
+    hook_red_die <<< nblock, 256>>>((double*)buf.p, iters, mode, (uint32_t)nsm, (unsigned long long*)cnt.p);
+    HOOK_TRY(cudaGetLastError());
+    HOOK_TRY(cudaDeviceSynchronize());
+    HOOK_TRY(cudaMemcpy(issued_out, cnt.p, 8, cudaMemcpyDeviceToHost));
+    HOOK_TRY(cudaMemcpy(h, buf.p, 32, cudaMemcpyDeviceToHost));
+    *sum_out = h[0] + h[1] + h[2] + h[3];
+done:
+    return rc;
+}

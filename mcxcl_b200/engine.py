@@ -76,6 +76,13 @@ class Simulation:
     def reseed(self, seed, seed_skip=0):
         abi.check(self.lib.mcxb_sim_reseed(self.h, int(seed), int(seed_skip)), "mcxb_sim_reseed")
 
+    def run_batches(self, nphoton, respin, seed, seed_skip=0, seed_stride=None):
+        """Config.respin on this resident simulation (mcxb_sim_run_batches); returns the summed kernel time in ms"""
+        ms = C.c_float(0)
+        abi.check(self.lib.mcxb_sim_run_batches(self.h, int(nphoton), int(respin), int(seed), int(seed_skip),
+                                                int(self.nthread if seed_stride is None else seed_stride), C.byref(ms)), "mcxb_sim_run_batches")
+        return float(ms.value)
+
     def reset(self, stream=None):
         abi.check(self.lib.mcxb_sim_reset(self.h, C.c_void_p(stream or 0)), "mcxb_sim_reset")
 
@@ -105,8 +112,9 @@ class Simulation:
             if c.issaveseed:
                 seeds = np.zeros((c.maxdetphoton, 2), dtype=np.uint64)
                 out.seeddata = seeds.ctypes.data_as(C.POINTER(C.c_uint64))
+        traj = _traj_buffer(c, out)
         abi.check(self.lib.mcxb_sim_fetch(self.h, C.c_void_p(stream or 0), C.byref(out)), "mcxb_sim_fetch")
-        return _result(self.p, out, field if want_field else None, det, seeds)
+        return _result(self.p, out, field if want_field else None, det, seeds, traj)
 
     # raw device pointers for the multi-GPU reducer
     def devptrs(self):
@@ -116,7 +124,16 @@ class Simulation:
                     seeddata=L.mcxb_sim_seeddata_devptr(h))
 
 
-def _result(p, out, field, det, seeds):
+def _traj_buffer(c, out):
+    """caller-owned trajectory buffer when `-D M` / `-D T` is on (cfg->exportdebugdata, src/pmcxcl.cpp:1229-1231)"""
+    if not (c.debuglevel & (abi.DEBUG_MOVE | abi.DEBUG_MOVE_ONLY)) or (c.debuglevel & abi.DEBUG_RNG):
+        return None
+    traj = np.zeros((max(1, c.maxjumpdebug), abi.TRAJ_RECLEN), dtype=np.float32)
+    out.debugdata = traj.ctypes.data_as(C.POINTER(C.c_float))
+    return traj
+
+
+def _result(p, out, field, det, seeds, traj=None):
     c = p.c
     res = dict(
         energytot=out.energytot, energyesc=out.energyesc, energyabs=out.energyabs,
@@ -130,6 +147,9 @@ def _result(p, out, field, det, seeds):
         res["detp"] = det[:out.saved]
         if seeds is not None:
             res["seeds"] = seeds[:out.saved]
+    if traj is not None:
+        res["traj"] = traj[:out.debugdatalen]          # rows: {photon id (uint32 bits), x, y, z, weight, source id}
+        res["traj_recorded"] = int(out.debugrecorded)
     return res
 
 
@@ -150,8 +170,9 @@ def run_prepared(prepared, device=0, field=None):
         if c.issaveseed:
             seeds = np.zeros((c.maxdetphoton, 2), dtype=np.uint64)
             out.seeddata = seeds.ctypes.data_as(C.POINTER(C.c_uint64))
+    traj = _traj_buffer(c, out)
     abi.check(lib.mcxb_run_simulation(C.byref(c), int(device), C.byref(out)), "mcxb_run_simulation")
-    return _result(p, out, field, det, seeds)
+    return _result(p, out, field, det, seeds, traj)
 
 
 def run_prepared_multi(prepared, devices, workload=None, field=None):
@@ -212,6 +233,8 @@ def run(cfg=None, device=0, **kw):
         out["detp"] = np.ascontiguousarray(r["detp"].T)
         if r["seeds"] is not None:
             out["seeds"] = r["seeds"].view(np.uint8).reshape(-1, 16).T.copy()
+    if r.get("traj") is not None:
+        out["traj"] = np.asfortranarray(r["traj"].T)            # (6, N) like pmcxcl (src/pmcxcl.cpp:1266-1282)
     out["stat"] = dict(runtime=r["runtime_ms"], nphoton=int(p.c.nphoton), energytot=r["energytot"],
                        energyabs=r["energyabs"], normalizer=r["normalizer"], unitinmm=p.c.unitinmm,
                        workload=[1.0], detected=r["detected"], absorbed=r["absorbed"])

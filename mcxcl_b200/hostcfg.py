@@ -290,8 +290,15 @@ def prepare(cfg):
             raise ConfigError(-6, "the specified source type is not supported")
         st = SRCTYPES.index(st)
     c.srctype = int(st)
-    if int(cfg.get("respin", 1)) != 1:
-        raise ConfigError(-1, "respin != 1 is not supported by this build (see DESIGN.md, reference quirk C)")
+    respin = int(cfg.get("respin", 1))
+    if respin == 0:
+        raise ConfigError(-1, "respin number can not be 0, check your -r/--repeat input or cfg.respin value")       # src/mcx_utils.c:1628-1630
+    if respin < 0:
+        raise ConfigError(-1, "negative respin is not supported by this build")
+    if replayseed is not None and respin > 1:
+        respin = 1                           # "respin is disabled in the replay mode" (src/mcx_utils.c:1633-1636)
+    c.respin = respin
+    c.maxjumpdebug = int(cfg.get("maxjumpdebug", 10000000))                  # src/mcx_utils.c:288
 
     # --- sources: N x 4 arrays define extra sources (src/pmcxcl.cpp:477-660) -------------------
     def rows(key, default, wdef):
@@ -325,6 +332,9 @@ def prepare(cfg):
         raise ConfigError(-4, "source initial direction vector can not have a length of 0")
     srcdir[0, :3] = (d * (1.0 / n)).astype(np.float32)
 
+    if c.debuglevel & abi.DEBUG_MOVE_ONLY:  # src/mcx_utils.c:1552-1555
+        c.issave2pt = 0
+        c.issavedet = 0
     if c.debuglevel & 1:                    # MCX_DEBUG_RNG
         c.isnormalized = 0
         c.issavedet = 0

@@ -27,6 +27,7 @@ class Result(C.Structure):
         ("energytot", C.c_double), ("energyesc", C.c_double),
         ("n_segment", C.c_uint64), ("n_deposit", C.c_uint64), ("n_scatter", C.c_uint64), ("n_launch", C.c_uint64),
         ("runtime_ms", C.c_double),
+        ("traj", C.POINTER(C.c_float)), ("trajcap", C.c_uint32), ("trajcount", C.c_uint32),
     ]
 
 
@@ -86,6 +87,11 @@ class Checker:
             if p.c.issaveseed:
                 seeds = np.zeros((p.c.maxdetphoton, 2), dtype=np.uint64)
                 res.seeddata = seeds.ctypes.data_as(C.POINTER(C.c_uint64))
+        traj = None
+        if (p.c.debuglevel & 0xA) and self.kind == "reference":          # MCX_DEBUG_MOVE / MCX_DEBUG_MOVE_ONLY
+            traj = np.zeros((p.c.maxjumpdebug, 6), dtype=np.float32)
+            res.traj = traj.ctypes.data_as(C.POINTER(C.c_float))
+            res.trajcap = p.c.maxjumpdebug
         rc = self._fn("run")(C.byref(p.c), int(nthread), int(hostthreads), C.byref(res))
         if rc != 0:
             raise RuntimeError("%s run failed: %d" % (self.kind, rc))
@@ -95,7 +101,7 @@ class Checker:
                     detected=res.detected, detp=None if det is None else det[:nsaved],
                     seeds=None if seeds is None else seeds[:nsaved], reclen=res.reclen,
                     n_segment=res.n_segment, n_deposit=res.n_deposit, n_scatter=res.n_scatter,
-                    n_launch=res.n_launch, runtime_ms=res.runtime_ms)
+                    n_launch=res.n_launch, runtime_ms=res.runtime_ms, traj=None if traj is None else traj[:res.trajcount])
 
     def seeds(self, seed, nrecords, skip=0):
         out = np.zeros(4 * nrecords, dtype=np.uint32)

@@ -29,6 +29,9 @@ typedef void (*ref_kernel_fn)(const unsigned int*, float*, float*, unsigned int*
                               const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*,
                               void*, const void*, float*, float*, int*);
 
+thread_local unsigned int* mcxref_jumpdebug = NULL;
+thread_local float* mcxref_debugdata = NULL;
+
 #define REF_DECL(name) \
     extern "C" void mcxref_kernel_##name##_r0_d0(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*); \
     extern "C" void mcxref_kernel_##name##_r1_d0(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*); \
@@ -159,7 +162,8 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     param.outputtype = (uint)cfg->outputtype;
     param.threadphoton = (uint)(cfg->nphoton / nthread);
     param.oddphoton = (int)(cfg->nphoton - (uint64_t)param.threadphoton * nthread);
-    param.debuglevel = cfg->debuglevel & 1u;
+    param.debuglevel = cfg->debuglevel & (1u | 2u | 8u);        /* MCX_DEBUG_RNG, MCX_DEBUG_MOVE, MCX_DEBUG_MOVE_ONLY */
+    param.maxjumpdebug = cfg->maxjumpdebug;
     param.savedetflag = flag;
     param.reclen = reclen;
     param.partialdata = partialdata;
@@ -220,11 +224,25 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     std::vector<float> genergy((size_t)nthread * 2, 0.f);
     const size_t sharedbytes = 4 * (size_t)(param.nphaselen + param.nanglelen) + 4 * (size_t)(w0offset + param.srcnum + 2) + 16 * param.issaveseed + 64;
 
+    const bool wanttraj = (param.debuglevel & (2u | 8u)) != 0 && res->traj != NULL;
+    std::vector<std::vector<float> > ttraj(hostthreads);
+    std::vector<unsigned int> ttrajcount(hostthreads, 0);
+
     auto t0 = std::chrono::steady_clock::now();
     #pragma omp parallel num_threads(hostthreads)
     {
         const int tid = omp_get_thread_num();
         tfield[tid].assign(fieldlen * 2, 0.f);
+
+        if (wanttraj) {
+            /* every host thread records into its own buffer with its own counter (the kernel's atomic_inc, :930) */
+            ttraj[tid].assign((size_t)param.maxjumpdebug * 6, 0.f);
+            mcxref_jumpdebug = &ttrajcount[tid];
+            mcxref_debugdata = ttraj[tid].data();
+        } else {
+            mcxref_jumpdebug = NULL;
+            mcxref_debugdata = NULL;
+        }
 
         if (cfg->issavedet) {
             tdet[tid].assign((size_t)detcap * (reclen ? reclen : 1), 0.f);
@@ -316,6 +334,16 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
                 res->seeddata[2 * (size_t)saved] = tseed[t][2 * (size_t)k];
                 res->seeddata[2 * (size_t)saved + 1] = tseed[t][2 * (size_t)k + 1];
             }
+        }
+    }
+
+    res->trajcount = 0;
+
+    for (int t = 0; wanttraj && t < hostthreads; t++) {
+        const unsigned int n = std::min(ttrajcount[t], param.maxjumpdebug);
+
+        for (unsigned int k = 0; k < n && res->trajcount < res->trajcap; k++, res->trajcount++) {
+            memcpy(res->traj + (size_t)res->trajcount * 6, ttraj[t].data() + (size_t)k * 6, sizeof(float) * 6);
         }
     }
 

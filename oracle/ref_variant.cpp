@@ -20,6 +20,11 @@ namespace REF_CAT(refk_, REF_SUFFIX) {
 #include "mcx_core_patched.cl"
 }
 
+/* trajectory buffers of the calling host thread (set by ref_driver.cpp when MCX_DEBUG_MOVE is requested): passed this
+ * way so that the kernel wrappers keep one signature */
+extern thread_local unsigned int* mcxref_jumpdebug;
+extern thread_local float* mcxref_debugdata;
+
 extern "C" void REF_CAT(mcxref_kernel_, REF_SUFFIX)(
     const unsigned int* media, float* field, float* genergy, unsigned int* n_seed,
     float* n_det, const void* gproperty, float* srcpattern, const void* gdetpos,
@@ -30,7 +35,7 @@ extern "C" void REF_CAT(mcxref_kernel_, REF_SUFFIX)(
     mcx_main_loop(media, field, genergy, n_seed, n_det, (const float4*)gproperty, srcpattern,
                   (const float4*)gdetpos, gprogress, detectedphoton,
                   replayweight, photontof, photondetid,
-                  (RandType*)gseeddata, /*gjumpdebug*/ NULL, /*gdebugdata*/ NULL,
+                  (RandType*)gseeddata, mcxref_jumpdebug, mcxref_debugdata,
                   ginvcdf, gangleinvcdf, (RandType*)sharedmem, /*gsmatrix*/ NULL,
                   (const MCXParam*)gcfg);
 }

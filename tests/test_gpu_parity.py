@@ -369,6 +369,77 @@ def test_russian_roulette_matches_reference(ref):
     np.testing.assert_allclose(tot_g, tot_o, rtol=0.03)
 
 
+def test_repetitions_accumulate_like_one_batch():
+    """Config.respin: R batches with consecutive seed-stream slices, accumulated on the device, read back and
+    normalised once -- statistically the single-batch answer, every packet launched exactly once, no RNG stream
+    used twice"""
+    n = 300001
+    cfg = dict(benchmarks.get("cube60b", n), issaveseed=1)
+    p1, one = run_gpu(cfg)
+    p3, rep = run_gpu(cfg, respin=3)
+    assert rep["energytot"] == n and one["energytot"] == n
+    assert rep["normalizer"] == pytest.approx(one["normalizer"], rel=1e-6)
+    sig = absorbed_sigma(n, one["absorbed"])
+    assert abs(rep["absorbed"] - one["absorbed"]) < 5 * np.sqrt(2.0) * sig
+    assert abs(rep["detected"] - one["detected"]) < 5 * np.sqrt(2.0 * one["detected"])
+    np.testing.assert_allclose(raw_field(p3, rep).sum(), raw_field(p1, one).sum(), rtol=0.01)
+    assert rep["saved"] == rep["detected"] == rep["seeds"].shape[0]
+    assert len({tuple(x) for x in rep["seeds"].tolist()}) == rep["saved"]
+    # the first batch of a repeated run IS the head of the seed stream: same streams as a single run of n/3 photons
+    # (static scheduling makes the packet -> stream map reproducible)
+    a = run_gpu(dict(cfg, nphoton=100000, sched=1))[1]
+    with engine.Simulation(hostcfg.prepare(dict(cfg, nphoton=100000, sched=1))) as sim:
+        sim.reset()
+        sim.run_batches(100000, 1, cfg["seed"])
+        b = sim.fetch()
+    assert a["detected"] == b["detected"] and {tuple(x) for x in a["seeds"].tolist()} == {tuple(x) for x in b["seeds"].tolist()}
+    # respin with a replay is switched off like the reference does (src/mcx_utils.c:1633-1636)
+    seeds8 = np.ascontiguousarray(one["seeds"]).view(np.uint8).reshape(-1, 16).T.copy()
+    rp = hostcfg.prepare(dict(benchmarks.get("cube60b", n), seed=seeds8, detphotons=np.ascontiguousarray(one["detp"].T), respin=4))
+    assert rp.c.respin == 1
+
+
+def test_trajectories_match_reference(ref):
+    """`-D M` (MCX_DEBUG_MOVE): one record {photon id, x, y, z, weight, source id} at the launch, at every scattering site
+    and at the end of every packet (src/mcx_core.cl:929-948, 1497-1503, 2243-2249, 2625-2632), compared with the
+    reference source run on the host: exact launch records, the same number of records per packet and the same
+    distribution of scattering sites; `-D T` (MOVE_ONLY) switches volume and detector output off."""
+    n = 6000
+    cfg = dict(benchmarks.get("cube60b", n), debuglevel="M", maxjumpdebug=2000000)
+    p, r = run_gpu(cfg)
+    _, o = run_ref(ref, cfg, work=512)
+    out = {}
+    for name, t in (("gpu", r["traj"]), ("ref", o["traj"])):
+        ids = t[:, 0].copy().view(np.uint32).astype(np.int64)
+        assert len(np.unique(ids)) == n and ids.min() == 1 and ids.max() == n
+        order = np.argsort(ids, kind="stable")              # records of one packet keep their order of creation
+        t, ids = t[order], ids[order]
+        first = np.r_[True, ids[1:] != ids[:-1]]
+        last = np.r_[ids[1:] != ids[:-1], True]
+        assert (t[first, 1:5] == np.array([29.0, 29.0, 0.0, 1.0], np.float32)).all()      # launch records are exact
+        assert (t[:, 5] == 0).all()                                                         # single source
+        dw = np.diff(t[:, 4])
+        assert (dw[~first[1:]] <= 1e-6).all()                                              # weight never grows inside a packet
+        counts = np.bincount(ids)[1:]
+        out[name] = dict(counts=counts, z=t[~first & ~last, 3], w_end=t[last, 4], n=t.shape[0])
+    g, w = out["gpu"], out["ref"]
+    assert r["traj_recorded"] == g["n"]
+    se = np.hypot(g["counts"].std() / np.sqrt(n), w["counts"].std() / np.sqrt(n))
+    assert abs(g["counts"].mean() - w["counts"].mean()) < 5 * se, (g["counts"].mean(), w["counts"].mean())
+    assert g["counts"].min() >= 2
+    assert abs(g["z"].mean() - w["z"].mean()) < 0.05 * w["z"].mean()                       # depth of the scattering sites
+    assert abs(np.median(g["z"]) - np.median(w["z"])) < 0.05 * np.median(w["z"])
+    assert abs(g["w_end"].mean() - w["w_end"].mean()) < 5 * np.hypot(g["w_end"].std(), w["w_end"].std()) / np.sqrt(n)
+    # the volume is still produced with -D M ...
+    assert abs(r["absorbed"] - o["absorbed"]) < 0.03 and r["field"].sum() > 0
+    # ... and not with -D T; the buffer limit is honoured and the overflow reported
+    p2, r2 = run_gpu(dict(cfg, debuglevel="T", maxjumpdebug=1000))
+    assert r2["traj"].shape == (1000, 6) and r2["traj_recorded"] > 1000
+    assert r2["field"].sum() == 0 and r2["detp"] is None
+    out1 = engine.run(dict(cfg, nphoton=50))
+    assert out1["traj"].shape[0] == 6 and out1["traj"].shape[1] > 100                      # pmcxcl layout: (6, N)
+
+
 def test_gscatter_similarity_switch(ref):
     cfg = decks.cube(nphoton=100000, gscatter=5, prop=[[0, 0, 1, 1], [0.005, 2.0, 0.8, 1.37], [0.002, 5.0, 0.9, 1.0]])
     p, r = run_gpu(cfg)

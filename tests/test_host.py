@@ -126,7 +126,7 @@ def test_prepare_direction_normalised():
     (lambda c: c.update(tend=0.0), -6),
     (lambda c: c.update(srctype="laser"), -6),
     (lambda c: c.update(bc="xyzabc"), -4),
-    (lambda c: c.update(respin=2), -1),
+    (lambda c: c.update(respin=0), -1),              # src/mcx_utils.c:1628-1630
 ])
 def test_prepare_rejects_like_reference(mutate, code):
     cfg = benchmarks.get("cube60", 10)

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2_pytest_gpu.log
+tail -4 gpurun_out/r2_pytest_gpu.log
+: > gpurun_out/r2_sweep_tail.log
+for v in default tail0; do
+  if [ $v = default ]; then unset MCXB200_LIB; else export MCXB200_LIB=$PWD/mcxcl_b200/build/variants/$v/libmcxb200.so; fi
+  echo "== $v" >> gpurun_out/r2_sweep_tail.log
+  timeout 600 python tools/perf_sweep.py cube60:1e8 cube60b:1e8 skinvessel:1e8 colin27:3e7 digimouse:3e7 digimouse_tg:3e7 >> gpurun_out/r2_sweep_tail.log 2>&1
+done
+unset MCXB200_LIB
+cut -c1-220 gpurun_out/r2_sweep_tail.log
+timeout 900 python tools/queue_crossover.py 3e7 > gpurun_out/r2_queue_crossover.log 2>&1
+cat gpurun_out/r2_queue_crossover.log
