@@ -67,6 +67,10 @@ enum mcxb_outputtype { MCXB_OT_FLUX = 0, MCXB_OT_FLUENCE = 1, MCXB_OT_ENERGY = 2
                      };
 
 /* boundary codes: TBoundary (src/mcx_utils.h:65) */
+enum mcxb_mediaformat { MCXB_MEDIA_LABEL_HALF = 99, MCXB_MEDIA_AS_F2H = 100, MCXB_MEDIA_MUA_FLOAT = 101, MCXB_MEDIA_AS_HALF = 102,
+                        MCXB_MEDIA_ASGN_BYTE = 103, MCXB_MEDIA_AS_SHORT = 104
+                      };
+
 enum mcxb_boundary { MCXB_BC_UNKNOWN = 0, MCXB_BC_REFLECT, MCXB_BC_ABSORB, MCXB_BC_MIRROR, MCXB_BC_CYCLIC };
 
 /* photon -> thread scheduling */
@@ -97,6 +101,13 @@ typedef struct mcxb_config {
     uint32_t dimx, dimy, dimz;
     const uint32_t* vol;           /* dimx*dimy*dimz words, x fastest; bits 0..30 label, bit 31 detector mask */
     float    unitinmm;
+    /* Config.mediabyte (src/mcx_const.h:56-64): <= 4 = label media (the volume holds labels); otherwise one of the
+     * continuous formats, where the 31 low bits of every word ENCODE the optical properties of the voxel, decoded per
+     * segment like updateproperty (src/mcx_core.cl:1079-1193): 99 MEDIA_LABEL_HALF {half value, 2-bit slot, 14-bit
+     * label}, 100 MEDIA_AS_F2H / 102 MEDIA_AS_HALF {half mua, half mus}, 101 MEDIA_MUA_FLOAT {float mua},
+     * 103 MEDIA_ASGN_BYTE {mua, mus, g, n as bytes between prop[1] and prop[2]}, 104 MEDIA_AS_SHORT {mua, mus as
+     * shorts between prop[1] and prop[2]}.  (96 two-word, 97 SVMC and 98 mixed-label media are not part of this build.) */
+    uint32_t mediaformat;
 
     /* ---- media table: Config.prop / medianum ({mua,mus,g,n}, row 0 = background) ---- */
     uint32_t medianum;
@@ -160,7 +171,13 @@ typedef struct mcxb_config {
     /* ---- photon replay: Config.replay / replaydet with Config.seed == SEED_FROM_FILE (src/mcx_utils.h:133-142,
      *      src/mcx_host.cpp:722-737; kernel src/mcx_core.cl:1590-1596, 2567-2592, 2845-2858).  When replay_seed is
      *      set, photon i restarts its RNG stream from replay_seed[2i..2i+1] (the state mcxb_output.seeddata recorded
-     *      for a detected photon) and nphoton is the number of records. ---- */
+     *      for a detected photon) and nphoton is the number of records.
+     *      Two defects of the reference's replay are NOT reproduced (tests/test_replay.py documents both): (i) its OpenCL
+     *      kernel maps work-item t to record t*threadphoton + min(t, oddphoton-1) + k (src/mcx_core.cl:1591), which skips
+     *      or repeats records whenever a work-item owns more than one photon -- here record i is photon i; (ii) at
+     *      scattering sites it indexes replay_weight / replay_tof / replay_detid with f.w instead of f.w-1
+     *      (src/mcx_core.cl:2569-2586 vs :2847), i.e. the WP / DCS / WPTOF deposits of photon i carry the weight of record
+     *      i+1 -- here every output type uses record i. ---- */
     const uint64_t* replay_seed;   /* 2 words per photon, or NULL = forward simulation */
     const float*    replay_weight; /* detected weight of photon i (mcx_replayprep, src/mcx_utils.c:1355-1430) */
     const float*    replay_tof;    /* its time of flight in seconds: selects the time gate of the sensitivity outputs */

@@ -38,6 +38,7 @@ class Config(C.Structure):
         ("dimx", C.c_uint32), ("dimy", C.c_uint32), ("dimz", C.c_uint32),
         ("vol", C.POINTER(C.c_uint32)),
         ("unitinmm", C.c_float),
+        ("mediaformat", C.c_uint32),
         ("medianum", C.c_uint32),
         ("prop", C.POINTER(F4)),
         ("srctype", C.c_int32),

@@ -352,7 +352,7 @@ struct mcxb_sim {
     SimParam P;
     PhotonKernelFn fn = nullptr;
     const char* kname = "";
-    bool acc64 = true, media16 = false, rngdebug = false;
+    bool acc64 = true, media16 = false, media32 = false, rngdebug = false;
     uint32_t nblock = 0, nthread = 0;
     size_t smem = 0;
     uint64_t fieldlen = 0;
@@ -395,11 +395,12 @@ struct mcxb_sim {
 };
 
 /* det: 0 = no detector capture, 1 = the default record, 2 = any record flags (generic kernels take 1 and 2 alike) */
-static const KernelEntry* find_kernel(int src, bool refl, int det, bool m16, bool acc64, bool stats, bool common, bool queue = false) {
+static const KernelEntry* find_kernel(int src, bool refl, int det, int mediabits, bool acc64, bool stats, bool common, bool queue = false) {
     typedef const KernelEntry* (*GroupFn)(int*);
     static const GroupFn groups[kNumGroups] = { mcxb_kernel_group_0, mcxb_kernel_group_1, mcxb_kernel_group_2, mcxb_kernel_group_3,
-                                                mcxb_kernel_group_4, mcxb_kernel_group_5, mcxb_kernel_group_6
+                                                mcxb_kernel_group_4, mcxb_kernel_group_5, mcxb_kernel_group_6, mcxb_kernel_group_7
                                               };
+    const bool m16 = mediabits == 16, m32 = mediabits == 32;
     /* most specialised first: {source, common} -> {any source, common} -> {any source, generic} */
     const int wantsrc[3] = { src, (int)srcAny, (int)srcAny };
     const bool wantgen[3] = { false, false, true };
@@ -413,7 +414,7 @@ static const KernelEntry* find_kernel(int src, bool refl, int det, bool m16, boo
                 const bool detok = wantgen[pass] ? ((e[i].savedet != 0) == (det != 0)) : (e[i].savedet == det);
 
                 if (e[i].src == wantsrc[pass] && e[i].generic == wantgen[pass] && e[i].reflect == refl && detok &&
-                        e[i].media16 == m16 && e[i].acc64 == acc64 && e[i].stats == stats && (e[i].queue != 0) == (queue && !wantgen[pass])) {
+                        e[i].media16 == m16 && e[i].media32 == m32 && e[i].acc64 == acc64 && e[i].stats == stats && (e[i].queue != 0) == (queue && !wantgen[pass])) {
                     return e + i;
                 }
             }
@@ -716,10 +717,43 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     const uint32_t partialdata = nmed * ((flag >> 1 & 1u) + (flag >> 2 & 1u) + (flag >> 3 & 1u));
     s->reclen = partialdata + (flag & 1u) + 3 * ((flag >> 4 & 1u) + (flag >> 5 & 1u)) + (flag >> 6 & 1u);
 
+    /* ---- continuous media: the words go to the device as they are (src/mcx_host.cpp:739-745) ---- */
+    const bool continuous = cfg->mediaformat > 4;
+
+    if (continuous) {
+        const uint32_t f = cfg->mediaformat;
+
+        if (f < MCXB_MEDIA_LABEL_HALF || f > MCXB_MEDIA_AS_SHORT) {
+            return fail(MCXB_ERR_ARG, "media format %u (two-word, SVMC or mixed-label media) is outside this build's hot path", f);
+        }
+
+        /* src/mcx_utils.c:1760-1766 */
+        if ((f == MCXB_MEDIA_AS_F2H || f == MCXB_MEDIA_MUA_FLOAT || f == MCXB_MEDIA_AS_HALF) && cfg->medianum < 2) {
+            return fail(MCXB_ERR_ARG, "the 'prop' field must contain at least 2 rows for the requested media format");
+        }
+
+        if ((f == MCXB_MEDIA_ASGN_BYTE || f == MCXB_MEDIA_AS_SHORT) && cfg->medianum < 3) {
+            return fail(MCXB_ERR_ARG, "the 'prop' field must contain at least 3 rows for the requested media format");
+        }
+
+        if (cfg->issavedet && (cfg->savedetflag & 0x0Eu) && !(cfg->debuglevel & 1u)) {
+            /* the reference indexes its per-medium rows with the media word itself there (src/mcx_core.cl:2515, 2787) */
+            return fail(MCXB_ERR_ARG, "per-medium detector records (savedetflag S, P, M) need label media; use savedetflag 'dxvw' or issavedet=0 with continuous media");
+        }
+
+        if (cfg->srcnum > 1 || cfg->replay_seed) {
+            return fail(MCXB_ERR_ARG, "photon sharing and replay are not available with continuous media in this build");
+        }
+
+        s->media32 = true;
+        CU_TRY(dev_alloc(&s->d_media, device, 4 * dimxyz));
+        CU_TRY(cudaMemcpy(s->d_media, cfg->vol, 4 * dimxyz, cudaMemcpyHostToDevice));
+    }
+
     /* ---- media volume: labels packed to 8 (or 16) bits with the detector flag in the top bit ---- */
     uint32_t maxlabel = 0;
 
-    for (uint64_t i = 0; i < dimxyz; i++) {
+    for (uint64_t i = 0; i < dimxyz && !continuous; i++) {
         maxlabel = std::max(maxlabel, cfg->vol[i] & 0x7FFFFFFFu);
     }
 
@@ -734,7 +768,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     {
         std::vector<uint64_t> hist(cfg->medianum, 0);
 
-        for (uint64_t i = 0; i < dimxyz; i++) {
+        for (uint64_t i = 0; i < dimxyz && !continuous; i++) {
             hist[cfg->vol[i] & 0x7FFFFFFFu]++;
         }
 
@@ -752,7 +786,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         return fail(MCXB_ERR_ARG, "more than 32767 media labels are not supported");
     }
 
-    {
+    if (!continuous) {
         std::vector<uint8_t> packed(dimxyz * (s->media16 ? 2 : 1));
 
         if (s->media16) {
@@ -869,7 +903,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->acc64 = cfg->accum != MCXB_ACCUM_F32;
     const bool refl = needs_reflection(cfg);
     const bool stats = (cfg->debuglevel & MCXB_DEBUG_STATS) != 0;
-    const bool common = is_common_config(cfg, savedet, nphase);
+    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32;
     const int detmode = savedet ? (flag == 0x5u ? 1 : 2) : 0;
     /* Scattering queue (photon_kernel.cuh): pays where a packet crosses several voxels per scattering event.  Measured on
      * B200: +8..10 % at mus = 1 per voxel (cube60 / cube60b), +20 % at mus <= 0.2 (skinvessel), -9..-12 % at mus = 8..40
@@ -882,16 +916,21 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     }
 
     const KernelEntry* ke = nullptr;
+    const int mediabits = s->media32 ? 32 : (s->media16 ? 16 : 8);
+
+    if (stats && s->media32) {
+        return fail(MCXB_ERR_ARG, "the instrumented (stats) kernel exists for label media only");
+    }
 
     if (stats) {
-        ke = find_kernel(srcAny, true, 1, s->media16, true, true, false);
+        ke = find_kernel(srcAny, true, 1, mediabits, true, true, false);
     } else {
         if (queue) {
-            ke = find_kernel(cfg->srctype, refl, detmode, s->media16, s->acc64, false, common, true);
+            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, true);
         }
 
         if (!ke) {
-            ke = find_kernel(cfg->srctype, refl, detmode, s->media16, s->acc64, false, common, false);
+            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, false);
         }
     }
 
@@ -910,7 +949,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         s->fn = ke->fn;
         s->kname = ke->name;
         s->smem = sizeof(float4) * ke->queue * kBlock      /* scattering queue (photon_kernel.cuh) */
-                  + sizeof(float4) * tablen + ((ke->generic || !MCXB_AUXTAB) ? 0 : 2 * sizeof(float4) * cfg->medianum) + sizeof(float) * ftablen + (ke->savedet ? sizeof(float) * partialdata * kBlock : 0)
+                  + sizeof(float4) * tablen + sizeof(float) * ftablen + (ke->savedet ? sizeof(float) * partialdata * kBlock : 0)
                   + ((savedet && cfg->issaveseed) ? 2 * sizeof(unsigned long long) * kBlock : 0)
                   + (cfg->extrasrclen ? sizeof(int) * kBlock : 0);      /* source id per thread (common kernels) */
         const bool fits = s->smem <= (size_t)prop.sharedMemPerBlockOptin;
@@ -925,7 +964,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
 
         if (ke->queue && (!fits || perSM < MCXB_MINBLOCKS)) {
             /* the queue's shared memory would cost resident blocks (many partial-path rows): scatter in place instead */
-            ke = find_kernel(cfg->srctype, refl, detmode, s->media16, s->acc64, false, common, false);
+            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, false);
 
             if (!ke) {
                 return fail(MCXB_ERR_ARG, "no kernel specialisation for this configuration");
@@ -1051,6 +1090,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     P.detnum = cfg->detnum;
     P.tablen = tablen;
     P.tables = s->d_tables;
+    P.mediaformat = s->media32 ? cfg->mediaformat : 0u;
     P.srcpattern = s->d_pattern;
     P.nphase = nphase;
     P.nangle = nangle;

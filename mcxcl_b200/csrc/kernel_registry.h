@@ -17,13 +17,13 @@ struct KernelEntry {
     int  src;          /* SrcType or srcAny */
     bool reflect;
     int  savedet;      /* 0 none, 1 default record folded at compile time, 2 record flags at run time */
-    bool media16, acc64, stats, generic;
+    bool media16, media32, acc64, stats, generic;     /* media word: 8 bits, 16 bits, or 32 bits (continuous media) */
     int  queue;        /* depth of the scattering queue (shared memory, 16 bytes x depth per thread), 0 = none */
     PhotonKernelFn fn;
     const char* name;
 };
 
-constexpr int kNumGroups = 7;
+constexpr int kNumGroups = 8;
 
 } // namespace mcxb
 
@@ -34,3 +34,4 @@ extern "C" const mcxb::KernelEntry* mcxb_kernel_group_3(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_4(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_5(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_6(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_7(int* n);

@@ -20,6 +20,7 @@
  *     specialisations, the same axes the reference JIT-specialises on (src/mcx_host.cpp:857-971).
  */
 #pragma once
+#include <cuda_fp16.h>
 #include "photon_device.cuh"
 
 namespace mcxb {
@@ -56,6 +57,7 @@ struct SimParam {
     /* tables in shared memory: [medianum] media, then 4*(1+extrasrclen) source rows, then detnum detectors */
     uint32_t medianum, detnum, tablen;
     const float4* tables;
+    uint32_t mediaformat;         /* continuous media (32-bit media words): format code 99..104, else 0 */
     const float*  srcpattern;
     /* launch-angle / phase-function inverse CDF tables (src/mcx_core.cl:2102-2118, 2475-2482) */
     uint32_t nphase, nangle, ftablen;   /* ftablen = nphase+nangle rounded up to an even count */
@@ -122,6 +124,55 @@ template <> struct MediaTraits<uint8_t> {
 template <> struct MediaTraits<uint16_t> {
     static constexpr uint32_t det = 0x8000u, lab = 0x7FFFu;
 };
+
+template <> struct MediaTraits<uint32_t> {        /* continuous media: the word IS the medium (src/mcx_core.cl:509-514) */
+    static constexpr uint32_t det = 0x80000000u, lab = 0x7FFFFFFFu;
+};
+
+/* optical properties {mua, mus, g, n} of a voxel.  Label media: row `word` of the table.  Continuous media
+ * (MediaT = uint32_t): decoded from the word like updateproperty (src/mcx_core.cl:1079-1193); the fields a format
+ * does not carry come from row 1 (the reference leaves them at what launchnewphoton loaded from gproperty[1], :2210)
+ * and n from row 0 / row 1 for an empty / non-empty word. */
+template <typename MediaT>
+__device__ __forceinline__ float4 medium(const SimParam& P, const float4* __restrict__ tab, uint32_t word) {
+    if (sizeof(MediaT) < 4) {
+        return tab[word];
+    }
+
+    const uint32_t fmt = P.mediaformat;
+    float4 pr = tab[1];
+    const float nfill = tab[word != 0u].w;
+
+    if (fmt == 101u) {                                     /* MEDIA_MUA_FLOAT */
+        pr.x = fabsf(__uint_as_float(word));
+        pr.w = nfill;
+    } else if (fmt == 100u || fmt == 102u) {               /* MEDIA_AS_F2H, MEDIA_AS_HALF */
+        pr.x = fabsf(__half2float(__ushort_as_half((unsigned short)(word & 0xFFFFu))));
+        pr.y = fabsf(__half2float(__ushort_as_half((unsigned short)(word >> 16))));
+        pr.w = nfill;
+    } else if (fmt == 99u) {                               /* MEDIA_LABEL_HALF */
+        pr = tab[word & 0x3FFFu];
+        const float v = fabsf(__half2float(__ushort_as_half((unsigned short)(word >> 16))));
+        const uint32_t slot = (word & 0xC000u) >> 14;
+        pr.x = (slot == 0u) ? v : pr.x;
+        pr.y = (slot == 1u) ? v : pr.y;
+        pr.z = (slot == 2u) ? v : pr.z;
+        pr.w = (slot == 3u) ? v : pr.w;
+    } else if (fmt == 103u) {                              /* MEDIA_ASGN_BYTE */
+        const float4 lo = tab[1], hi = tab[2];
+        pr.x = (float)(word & 0xFFu) * (1.f / 255.f) * (hi.x - lo.x) + lo.x;
+        pr.y = (float)((word >> 8) & 0xFFu) * (1.f / 255.f) * (hi.y - lo.y) + lo.y;
+        pr.z = (float)((word >> 16) & 0xFFu) * (1.f / 255.f) * (hi.z - lo.z) + lo.z;
+        pr.w = (float)((word >> 24) & 0xFFu) * (1.f / 127.f) * (hi.w - lo.w) + lo.w;
+    } else if (fmt == 104u) {                              /* MEDIA_AS_SHORT */
+        const float4 lo = tab[1], hi = tab[2];
+        pr.x = (float)(word & 0xFFFFu) * (1.f / 65535.f) * (hi.x - lo.x) + lo.x;
+        pr.y = (float)(word >> 16) * (1.f / 65535.f) * (hi.y - lo.y) + lo.y;
+        pr.w = nfill;
+    }
+
+    return pr;
+}
 
 template <typename MediaT>
 __device__ __forceinline__ void fetch_voxel(const MediaT* __restrict__ media, uint32_t idx, uint32_t& label, uint32_t& det) {
@@ -221,7 +272,7 @@ __device__ MCXB_ENTER_INLINE int enter_volume(const SimParam& P, const float4* _
                     fetch_voxel(media, (uint32_t)idx, elab, det);
                 }
 
-                const float nin = tab[elab].w, nout = tab[0].w;
+                const float nin = medium<MediaT>(P, tab, elab).w, nout = tab[0].w;
 
                 if (P.isspecular && nin != nout) {
                     ph.w *= 1.f - fresnel(ph.vx, ph.vy, ph.vz, nout, nin, ph.face);
@@ -643,9 +694,6 @@ constexpr int kBlock = MCXB_BLOCK;
  * scattering event and the block runs every iteration anyway -- engine.cu picks the variant from the mean
  * scattering coefficient per voxel.  Per-thread RNG draw ORDER differs from the reference's, so runs that record
  * seeds for a replay use the kernels without the queue. */
-#ifndef MCXB_AUXTAB
-    #define MCXB_AUXTAB 1
-#endif
 #ifndef MCXB_LAUNCH_IN_TAIL
     #define MCXB_LAUNCH_IN_TAIL 1
 #endif
@@ -664,26 +712,12 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
     float4* tab = smem + QK * kBlock;                     /* optical properties, row 0 = background */
     const float4* srctab = tab + P.medianum;              /* 4 rows per source, main source first  */
     const float4* dettab = srctab + 4 * (1 + P.extrasrclen);
-    /* common-configuration kernels: a second copy of the media rows for the segment loop, two float4 per label --
-     * {mua, mus, g, n} and {refined reciprocal of mus, reciprocal of mua, -, -}.  The two reciprocals cost a MUFU each
-     * (and the first one two FMAs of Newton refinement) per segment otherwise; computed here with the very instructions
-     * div_exact uses, so the step length stays bit-identical to the reference's */
-    constexpr bool kAuxTab = !GEN && (MCXB_AUXTAB != 0);
-    float4* const mtab = tab + P.tablen;
-    float* ftab = reinterpret_cast<float*>(mtab + (kAuxTab ? 2 * P.medianum : 0));        /* inverse-CDF tables */
+    float* ftab = reinterpret_cast<float*>(tab + P.tablen);        /* inverse-CDF tables */
     float* ppath_base = ftab + P.ftablen;                         /* partialdata x blockDim, thread-minor */
     unsigned long long* seed_base = reinterpret_cast<unsigned long long*>(ppath_base + (SAVEDET ? P.partialdata * kBlock : 0));
 
     for (uint32_t i = threadIdx.x; i < P.tablen; i += kBlock) {
         tab[i] = P.tables[i];
-    }
-
-    if (kAuxTab) {
-        for (uint32_t i = threadIdx.x; i < P.medianum; i += kBlock) {
-            const float4 row = P.tables[i];
-            mtab[2 * i] = row;
-            mtab[2 * i + 1] = make_float4(refined_rcp(row.y), mufu_rcp(row.x), 0.f, 0.f);
-        }
     }
 
     for (uint32_t i = threadIdx.x; i < P.nphase; i += kBlock) {
@@ -987,7 +1021,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             budget--;
             ph.label = rawlabel;
             ph.detflag = rawdet;
-            nmed = tab[ph.label].w;
+            nmed = medium<MediaT>(P, tab, ph.label).w;
             e_launched += ph.w;
             ph.w0 = ph.w;
             w0init = ph.w;
@@ -1020,6 +1054,10 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
         ph.slen = 1.f;
         relaunch = false;
     }
+
+#ifdef MCXB_EXP_UNROLL2
+    #pragma unroll 2
+#endif
 
     while (true) {
         if (!kLaunchInTail && relaunch) {
@@ -1174,24 +1212,17 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
         /* ------------------------------------------------------------------ one ray segment (:2652-2765) */
         ph.n1 = nmed;
-        float rmus = 0.f, rmua = 0.f;
         {
-            const float4 pr = kAuxTab ? mtab[2 * ph.label] : tab[ph.label];
+            const float4 pr = medium<MediaT>(P, tab, ph.label);
             mua = pr.x;
             mus = pr.y;
             g = pr.z;
             nmed = pr.w;
-
-            if (kAuxTab) {
-                const float2 ax = *reinterpret_cast<const float2*>(mtab + 2 * ph.label + 1);
-                rmus = ax.x;
-                rmua = ax.y;
-            }
         }
         const float dist = face_distance(ph.px, ph.py, ph.pz, ph.vx, ph.vy, ph.vz, ph.ix, ph.iy, ph.iz, ph.face);
         const float musp = (GEN && (uint32_t)(ph.nscat + 1) > P.gscatter) ? __fmul_rn(mus, __fsub_rn(1.f, g)) : mus;
         float slen;
-        const float len = kAuxTab ? step_length_r(dist, musp, rmus, ph.slen, slen) : step_length(dist, musp, ph.slen, slen);
+        const float len = step_length(dist, musp, ph.slen, slen);
         ph.pathlen += len;
         ph.px = advance(ph.px, len, ph.vx);
         ph.py = advance(ph.py, len, ph.vy);
@@ -1247,7 +1278,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             /* common configuration (flux / fluence, one volume per gate): ONE divergent region instead of three nested
              * ones -- every level of nesting costs a BSSY / BRA / BSYNC triple per warp-iteration */
             const bool moved = ph.idx1d != oldidx;
-            const float weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * (kAuxTab ? rmua : mufu_rcp(mua)));
+            const float weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * mufu_rcp(mua));
 
             /* nothing is deposited into a label-0 voxel (:2816: "&& mediaidold") */
             if (moved && oldlabel && ph.tof >= P.twin0 && ph.tof < P.twin1 && fabsf(weight) > 0.f) {
@@ -1472,7 +1503,7 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
                 /* -------------------------------------------------------------- index mismatch (:3063-3297) */
                 if (REFLECT && !relaunch) {
-                    const float n2 = (ph.label == oldlabel) ? nmed : tab[ph.label].w;
+                    const float n2 = (ph.label == oldlabel) ? nmed : medium<MediaT>(P, tab, ph.label).w;
                     const bool mirror = GEN && bcode == bcMirror;
                     bool handle = false;
 

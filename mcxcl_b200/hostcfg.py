@@ -205,6 +205,68 @@ class Prepared:
         return other
 
 
+MEDIA_LABEL_HALF, MEDIA_AS_F2H, MEDIA_MUA_FLOAT, MEDIA_AS_HALF, MEDIA_ASGN_BYTE, MEDIA_AS_SHORT = 99, 100, 101, 102, 103, 104
+
+
+def _float_to_half_bits(f):
+    """float32 -> IEEE half bit patterns the way pmcxcl packs continuous media (src/pmcxcl.cpp:286-318): mantissa
+    TRUNCATED to 10 bits, exponent re-biased and clamped, denormals (2^-24 .. 2^-14) rounded from an 11-bit mantissa"""
+    i = np.ascontiguousarray(f, dtype=np.float32).view(np.uint32).astype(np.int64)
+    m = (i >> 13) & 0x3FF
+    e = (i >> 23) & 0xFF
+    tmp = np.where(e > 0x70, (e - 0x70) & 0x1F, 0)
+    normal = (((i >> 31) << 5 | tmp) << 10) | m
+    sign = (i >> 16) & 0x8000
+    m11 = ((i >> 12) & 0x7FF) | 0x800
+    sh = (114 - e) & 31                         # the C code shifts an int by this count: taken mod 32 on x86
+    den = sign | ((m11 >> sh) + ((m11 >> ((113 - e) & 31)) & 1))
+    return np.where((m < 0x10) & (tmp == 0), den, normal).astype(np.uint32) & 0xFFFF
+
+
+def pack_continuous_volume(vol, unitinmm=1.0):
+    """4-D `vol` of pmcxcl (component, x, y, z) -> (uint32 words shaped (x, y, z), media format), mirroring the packing of
+    src/pmcxcl.cpp:108-400: float32 x1 = mua (MEDIA_MUA_FLOAT), float32 x2 = mua, mus as halves (MEDIA_AS_F2H), float32 x3 =
+    {value, slot 0..3, label} (MEDIA_LABEL_HALF), int8/uint8 x4 = mua, mus, g, n bytes (MEDIA_ASGN_BYTE), int16/uint16 x2 =
+    mua, mus shorts (MEDIA_AS_SHORT).  mua and mus are scaled by unitinmm where pmcxcl does."""
+    v = np.asarray(vol)
+    if v.ndim != 4:
+        raise ConfigError(-4, "a continuous-media volume is 4-D: (component, x, y, z)")
+    ch = v.shape[0]
+    u = np.float32(unitinmm)
+    if v.dtype in (np.int8, np.uint8) and ch == 4:
+        b = v.astype(np.uint8).astype(np.uint32)
+        return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24), MEDIA_ASGN_BYTE
+    if v.dtype in (np.int16, np.uint16) and ch == 2:
+        h = v.astype(np.uint16).astype(np.uint32)
+        return h[0] | (h[1] << 16), MEDIA_AS_SHORT
+    if v.dtype in (np.float32, np.float64):
+        f = v.astype(np.float32)
+        if ch == 1:
+            mua = f[0] * u
+            w = mua.view(np.uint32).copy()
+            w[w == 0] = np.float32(1.19209290e-07).view(np.uint32)      # avoid being taken for a 0-label voxel
+            w[np.isnan(f[0])] = 0
+            return w, MEDIA_MUA_FLOAT
+        if ch == 2:
+            mua, mus = f[0] * u, f[1] * u
+            w = _float_to_half_bits(mua) | (_float_to_half_bits(mus) << 16)
+            w[w == 0] = 0x00010000
+            w[np.isnan(mua) | np.isnan(mus)] = 0
+            return w.astype(np.uint32), MEDIA_AS_F2H
+        if ch == 3:
+            val, slot, lab = f[0].copy(), f[1], f[2]
+            if (slot < 0).any() or (slot >= 4).any() or (lab < 0).any():
+                raise ConfigError(-4, "the 2nd volume must have an integer value between 0 and 3")
+            val[(slot >= 1) & (slot <= 2)] *= u
+            i = val.view(np.uint32).astype(np.int64)
+            e = (i >> 23) & 0xFF
+            tmp = np.where(e > 0x70, (e - 0x70) & 0x1F, 0)
+            hval = ((((i >> 31) << 5) | tmp) << 10) | ((i >> 13) & 0x3FF)
+            low = ((slot.astype(np.int64) & 0x3) << 14) | lab.astype(np.int64)
+            return ((hval << 16) | low).astype(np.uint32), MEDIA_LABEL_HALF
+    raise ConfigError(-4, "Invalid array for vol array.")
+
+
 def prepare(cfg):
     """dict -> Prepared.  Mirrors parse_config + mcx_validatecfg + mcx_preprocess for the hot path."""
     if "vol" not in cfg or "prop" not in cfg:
@@ -215,8 +277,11 @@ def prepare(cfg):
     p.session = str(cfg.get("session", ""))
 
     vol = np.asarray(cfg["vol"])
+    c.mediaformat = int(cfg.get("mediaformat", 0))          # explicit format code with already packed uint32 words
+    if vol.ndim == 4:
+        vol, c.mediaformat = pack_continuous_volume(vol, float(cfg.get("unitinmm", 1.0)))
     if vol.ndim != 3:
-        raise ConfigError(-4, "the 'vol' field must be a 3D array (label-based media only)")
+        raise ConfigError(-4, "the 'vol' field must be a 3D array of labels or a 4D array of optical properties")
     if vol.size == 0:
         raise ConfigError(-4, "the 'vol' field in the input structure can not be empty")
     nx, ny, nz = vol.shape
@@ -366,7 +431,14 @@ def prepare(cfg):
     if c.srcnum > 1 and c.srctype != 5:
         raise ConfigError(-4, "photon sharing (srcnum>1) needs the 'pattern' source type")
 
-    maxlabel = int((flat & MED_MASK).max())
+    continuous = c.mediaformat > 4
+    if continuous:
+        # src/mcx_utils.c:1760-1766
+        if c.mediaformat in (MEDIA_AS_F2H, MEDIA_MUA_FLOAT, MEDIA_AS_HALF) and c.medianum < 2:
+            raise ConfigError(-4, "the 'prop' field must contain at least 2 rows for the requested media format")
+        if c.mediaformat in (MEDIA_ASGN_BYTE, MEDIA_AS_SHORT) and c.medianum < 3:
+            raise ConfigError(-4, "the 'prop' field must contain at least 3 rows for the requested media format")
+    maxlabel = 0 if continuous else int((flat & MED_MASK).max())
     if c.medianum <= maxlabel:
         raise ConfigError(-4, "input media optical properties are less than the labels in the volume")
     if c.srctype in (5, 15) and cfg.get("srcpattern") is None:

@@ -32,6 +32,7 @@ SOURCES = [
 # what the reference passes at its default optlevel for label media with atomics on
 # (src/mcx_host.cpp:857-891), minus USE_MACRO_CONST so gcfg-> fields are read from the struct
 BASEFLAGS = ["-DMED_TYPE=1", "-DUSE_ATOMIC", "-DMCX_USE_NATIVE"]
+MEDIA_FORMATS = [99, 100, 101, 102, 103, 104]        # MEDIA_LABEL_HALF .. MEDIA_AS_SHORT (src/mcx_const.h:59-64)
 CXX = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fpermissive", "-w", "-fPIC", "-fopenmp", "-x", "c++"]
 
 PATCHES = [
@@ -89,6 +90,19 @@ def main():
                 suffix = "%s_r%d_d%d" % (name, refl, det)
                 obj = os.path.join(OUT, "k_%s.o" % suffix)
                 flags = BASEFLAGS + ["-D" + macro, "-DREF_SUFFIX=" + suffix]
+                if refl:
+                    flags.append("-DMCX_DO_REFLECTION")
+                if det:
+                    flags.append("-DMCX_SAVE_DETECTORS")
+                jobs.append(CXX + flags + inc + ["-c", os.path.join(HERE, "ref_variant.cpp"), "-o", obj])
+                objs.append(obj)
+    # continuous media: the reference JIT passes -DMED_TYPE=<cfg->mediabyte> (src/mcx_host.cpp:882); pencil source only
+    for med in MEDIA_FORMATS:
+        for refl in (0, 1):
+            for det in (0, 1):
+                suffix = "pencil_m%d_r%d_d%d" % (med, refl, det)
+                obj = os.path.join(OUT, "k_%s.o" % suffix)
+                flags = [f for f in BASEFLAGS if not f.startswith("-DMED_TYPE")] + ["-DMED_TYPE=%d" % med, "-DMCX_SRC_PENCIL", "-DREF_SUFFIX=" + suffix]
                 if refl:
                     flags.append("-DMCX_DO_REFLECTION")
                 if det:

@@ -43,6 +43,41 @@ using std::sqrt;
 #define __kernel
 #define __constant const
 
+/* ---- cl_khr_fp16 as far as updateproperty needs it (MED_TYPE 99 / 100 / 102, src/mcx_core.cl:1103-1152): a `half`
+ *      is its 16 storage bits, vload_half widens them exactly to binary32, convert_float is the identity ---- */
+typedef unsigned short half;
+static inline float vload_half(size_t offset, const half* p) {
+    const unsigned int h = p[offset];
+    const unsigned int sign = (h & 0x8000u) << 16;
+    unsigned int e = (h >> 10) & 0x1Fu, m = h & 0x3FFu, bits;
+
+    if (e == 0) {
+        if (m == 0) {
+            bits = sign;
+        } else {                /* subnormal half: normalise */
+            e = 113;
+
+            while (!(m & 0x400u)) {
+                m <<= 1;
+                e--;
+            }
+
+            bits = sign | (e << 23) | ((m & 0x3FFu) << 13);
+        }
+    } else if (e == 31) {
+        bits = sign | 0x7F800000u | (m << 13);
+    } else {
+        bits = sign | ((e + 112) << 23) | (m << 13);
+    }
+
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+static inline float convert_float(float v) {
+    return v;
+}
+
 /* ---- vector types (only the members/operators mcx_core.cl actually uses) ---- */
 struct alignas(16) float4 {
     float x, y, z, w;
