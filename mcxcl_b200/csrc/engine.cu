@@ -1091,6 +1091,17 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     P.tablen = tablen;
     P.tables = s->d_tables;
     P.mediaformat = s->media32 ? cfg->mediaformat : 0u;
+    {
+        /* the launch of the usual pencil beam is a copy of the source record (photon_kernel.cuh, next_packet) */
+        uint32_t labelbits = 0;
+        memcpy(&labelbits, &cfg->src.param2.w, 4);
+        P.plainlaunch = (cfg->srctype == MCXB_SRC_PENCIL && cfg->extrasrclen == 0 && nangle == 0 && cfg->src.dir.w == 0.f &&
+                         (labelbits & 0x7FFFFFFFu) != 0u && fabsf(cfg->src.pos.w) > cfg->minenergy && !cfg->replay_seed) ? 1u : 0u;
+
+        if (getenv("MCXB_NO_PLAINLAUNCH")) {       /* tuning / A-B only */
+            P.plainlaunch = 0;
+        }
+    }
     P.srcpattern = s->d_pattern;
     P.nphase = nphase;
     P.nangle = nangle;
