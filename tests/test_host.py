@@ -186,3 +186,44 @@ def test_nccl_is_bound_at_run_time(lib):
     out = subprocess.run(["ldd", os.path.join(ROOT, "mcxcl_b200", "libmcxb200.so")], capture_output=True, text=True).stdout
     assert "nccl" not in out
     assert lib.mcxb_nccl_version() >= 20000
+
+
+def test_continuous_media_packing_follows_pmcxcl():
+    """hostcfg.pack_continuous_volume mirrors the packing of src/pmcxcl.cpp:108-400 (what reaches the boundary in
+    Config.vol / Config.mediabyte)"""
+    mua = np.full((3, 4, 5), 0.005, np.float32)
+    mus = np.full((3, 4, 5), 1.5, np.float32)
+    w, fmt = hostcfg.pack_continuous_volume(mua[None], 2.0)
+    assert fmt == hostcfg.MEDIA_MUA_FLOAT and w.dtype == np.uint32 and (w.view(np.float32) == np.float32(0.01)).all()
+    z = mua.copy()
+    z[0, 0, 0] = 0.0
+    z[1, 1, 1] = np.nan
+    w, _ = hostcfg.pack_continuous_volume(z[None], 1.0)
+    assert w[0, 0, 0] == np.float32(1.19209290e-07).view(np.uint32) and w[1, 1, 1] == 0         # zero mua is not a 0-label voxel; NaN is
+    w, fmt = hostcfg.pack_continuous_volume(np.stack([mua, mus]), 1.0)
+    assert fmt == hostcfg.MEDIA_AS_F2H
+    lo = (w & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float32)
+    hi = (w >> 16).astype(np.uint16).view(np.float16).astype(np.float32)
+    assert (hi == 1.5).all() and (np.abs(lo - 0.005) < 0.005 * 2.0 ** -10).all() and (lo <= 0.005).all()   # mantissa truncated, not rounded
+    # exactly representable halves survive unchanged; the conversion never rounds up
+    vals = np.array([1.0, 0.5, 0.375, 2.0, 1000.0, 6.1035156e-05, 65504.0], np.float32)
+    assert (hostcfg._float_to_half_bits(vals).astype(np.uint16).view(np.float16).astype(np.float32) == vals).all()
+    rs = np.random.RandomState(5)
+    f = rs.uniform(1e-3, 50, 2000).astype(np.float32)
+    h = hostcfg._float_to_half_bits(f).astype(np.uint16).view(np.float16).astype(np.float32)
+    assert (h <= f).all() and (f - h < f * 2.0 ** -10).all()
+    b = (np.arange(4 * 3 * 4 * 5) % 251).astype(np.uint8).reshape(4, 3, 4, 5)
+    w, fmt = hostcfg.pack_continuous_volume(b)
+    assert fmt == hostcfg.MEDIA_ASGN_BYTE and (w.view(np.uint8).reshape(3, 4, 5, 4) == np.moveaxis(b, 0, -1)).all()
+    s16 = (np.arange(2 * 3 * 4 * 5) * 1021 % 65521).astype(np.uint16).reshape(2, 3, 4, 5)
+    w, fmt = hostcfg.pack_continuous_volume(s16)
+    assert fmt == hostcfg.MEDIA_AS_SHORT and ((w & 0xFFFF) == s16[0]).all() and ((w >> 16) == s16[1]).all()
+    lh = np.zeros((3, 3, 4, 5), np.float32)
+    lh[0], lh[1], lh[2] = 0.5, 1, 7                       # value 0.5 replaces slot 1 (mus, scaled by unitinmm) of label 7
+    w, fmt = hostcfg.pack_continuous_volume(lh, 2.0)
+    assert fmt == hostcfg.MEDIA_LABEL_HALF and ((w & 0x3FFF) == 7).all() and (((w >> 14) & 3) == 1).all()
+    assert ((w >> 16).astype(np.uint16).view(np.float16) == np.float16(1.0)).all()
+    p = hostcfg.prepare(dict(benchmarks.get("cube60", 10), vol=np.full((1, 60, 60, 60), 0.005, np.float32), issavedet=0))
+    assert p.c.mediaformat == 101 and p.dims == (60, 60, 60)
+    with pytest.raises(hostcfg.ConfigError):
+        hostcfg.prepare(dict(benchmarks.get("cube60", 10), vol=np.zeros((4, 6, 6, 6), np.uint8), prop=[[0, 0, 1, 1], [0.005, 1, 0, 1.37]]))

@@ -109,3 +109,27 @@ def test_golden_fixture_consistency(ref):
     o = ref.run(hostcfg.prepare(cfg), int(g["work"]), hostthreads=0)
     assert o["absorbed"] == pytest.approx(float(g["absorbed"][0]), abs=1e-12)
     assert o["detected"] == int(g["detected"][0])
+
+
+def test_continuous_media_builds_of_the_reference_reproduce_the_label_run(ref):
+    """the -DMED_TYPE=99..104 builds of the reference source (oracle/build_ref.py): a volume that encodes the properties of
+    label 1 in every voxel walks the SAME trajectories (equal segment counts, weights equal to rounding) as the label run when the encoding is exact (float mua, label +
+    half override of an exactly representable value) and statistically the same ones when it is quantised"""
+    from mcxcl_b200 import hostcfg
+    n = 5000
+    base = dict(benchmarks.get("cube60b", n), issavedet=0, prop=[[0, 0, 1, 1], [0.0078125, 1.0, 0.01, 1.37]])   # mua = 2^-7: exact as a half
+    want = ref.run(hostcfg.prepare(base), 64, hostthreads=1)
+    mua = np.full((60, 60, 60), 0.0078125, np.float32)
+    exact = {"mua_float": mua[None], "as_f2h": np.stack([mua, np.ones_like(mua)])}
+    lh = np.zeros((3, 60, 60, 60), np.float32)
+    lh[0], lh[1], lh[2] = mua, 0, 1
+    exact["label_half"] = lh
+    for name, vol in exact.items():
+        got = ref.run(hostcfg.prepare(dict(base, vol=vol)), 64, hostthreads=1)
+        assert got["n_segment"] == want["n_segment"], name                           # the same walk, segment for segment
+        assert got["energyesc"] == pytest.approx(want["energyesc"], rel=1e-5), name  # weights agree to rounding (exp argument order)
+        assert np.allclose(got["field"], want["field"], rtol=1e-3, atol=1e-6 * float(want["field"].max())), name
+    b = np.zeros((4, 60, 60, 60), np.uint8)
+    b[0], b[1], b[2], b[3] = 100, 51, 0, 127               # mua 100/255*0.02, mus 51/255*5 = 1, g 0.01, n 1.37
+    got = ref.run(hostcfg.prepare(dict(base, vol=b, prop=[[0, 0, 1, 1], [0.0, 0.0, 0.01, 1.0], [0.02, 5.0, 0.9, 1.37]])), 64, hostthreads=1)
+    assert abs(got["absorbed"] - want["absorbed"]) < 0.02
