@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCXB_ABI_VERSION 3
+#define MCXB_ABI_VERSION 4
 
 /* error codes returned by every entry point (0 = success).  The reference reports OpenCL errors
  * negated through ocl_assess (src/mcx_host.cpp:213-217); CUDA runtime errors are reported the same
@@ -59,12 +59,17 @@ enum mcxb_srctype {
 };
 
 /* output types: same numbering as TOutputType (src/mcx_utils.h:58-60).  Flux / fluence / energy / otL are forward
- * outputs; Jacobian (absorption sensitivity), WP (scattering-count sensitivity), DCS (momentum transfer) and their
- * time-of-flight weighted forms WLTOF / WPTOF exist only in replay mode (replay_seed != NULL).  The RF types
- * (6, 8) and the adjoint types (11+) are not part of this build. */
+ * outputs; Jacobian (absorption sensitivity), WP (scattering-count sensitivity), DCS (momentum transfer), their
+ * time-of-flight weighted forms WLTOF / WPTOF and the RF Jacobians (RF: absorption, RFMUS: scattering, both complex,
+ * omega > 0) exist only in replay mode (replay_seed != NULL).  The adjoint types are forward fluence runs over the
+ * sources AND the detectors (the front-end appends the detectors as extra sources and sets srcid = -1,
+ * src/mcx_utils.c:1902-1925) whose volumes mcxb_adjoint_products then multiplies pairwise. */
 enum mcxb_outputtype { MCXB_OT_FLUX = 0, MCXB_OT_FLUENCE = 1, MCXB_OT_ENERGY = 2, MCXB_OT_JACOBIAN = 3, MCXB_OT_WP = 4, MCXB_OT_DCS = 5,
-                       MCXB_OT_L = 7, MCXB_OT_WLTOF = 9, MCXB_OT_WPTOF = 10
+                       MCXB_OT_RF = 6, MCXB_OT_L = 7, MCXB_OT_RFMUS = 8, MCXB_OT_WLTOF = 9, MCXB_OT_WPTOF = 10,
+                       MCXB_OT_ADJOINT = 11, MCXB_OT_ADJOINT_DCOEFF = 12, MCXB_OT_ADJOINT_MUS = 13, MCXB_OT_ADJOINT_MUSP = 14,
+                       MCXB_OT_ADJOINT_MUA_D = 15, MCXB_OT_ADJOINT_MUA_MUSP = 16
                      };
+#define MCXB_NANGLES 181             /* NANGLES: rows of one Mueller matrix table (src/mcx_const.h:67) */
 
 /* boundary codes: TBoundary (src/mcx_utils.h:65) */
 enum mcxb_mediaformat { MCXB_MEDIA_LABEL_HALF = 99, MCXB_MEDIA_AS_F2H = 100, MCXB_MEDIA_MUA_FLOAT = 101, MCXB_MEDIA_AS_HALF = 102,
@@ -106,7 +111,8 @@ typedef struct mcxb_config {
      * segment like updateproperty (src/mcx_core.cl:1079-1193): 99 MEDIA_LABEL_HALF {half value, 2-bit slot, 14-bit
      * label}, 100 MEDIA_AS_F2H / 102 MEDIA_AS_HALF {half mua, half mus}, 101 MEDIA_MUA_FLOAT {float mua},
      * 103 MEDIA_ASGN_BYTE {mua, mus, g, n as bytes between prop[1] and prop[2]}, 104 MEDIA_AS_SHORT {mua, mus as
-     * shorts between prop[1] and prop[2]}.  (96 two-word, 97 SVMC and 98 mixed-label media are not part of this build.) */
+     * shorts between prop[1] and prop[2]}.  (97 SVMC is not part of this build; 96 two-word and 98 mixed-label media are
+     * formats no front-end of the reference can produce / its kernel has no decoder for.) */
     uint32_t mediaformat;
 
     /* ---- media table: Config.prop / medianum ({mua,mus,g,n}, row 0 = background) ---- */
@@ -132,7 +138,7 @@ typedef struct mcxb_config {
     uint32_t detnum;
     const mcxb_f4* detpos;         /* xyz centre (voxel units, 0-based), w = radius */
     int32_t  issavedet;
-    uint32_t savedetflag;          /* bits D S P M X V W (I unsupported), src/mcx_const.h:94-101 */
+    uint32_t savedetflag;          /* bits D S P M X V W I (I = Stokes vector, polarised runs only), src/mcx_const.h:94-101 */
     uint32_t maxdetphoton;
     int32_t  issaveseed;
     int32_t  issaveref;
@@ -195,6 +201,23 @@ typedef struct mcxb_config {
      *      launch, per scattering event and per termination of every packet (src/mcx_core.cl:1497-1503, 2243-2249,
      *      2625-2632), up to maxjumpdebug records, in arbitrary order (one atomic counter) ---- */
     uint32_t maxjumpdebug;
+
+    /* ---- polarised light: Config.polmedianum / smatrix / srciquv (src/mcx_utils.h:184-194).  smatrix holds, per
+     *      non-background medium, MCXB_NANGLES rows {S11, S12, S33, S43} of its Mie scattering matrix on a uniform grid of
+     *      the polar angle (mcx_prep_polarized, src/mcx_utils.c:1483-1519, run by the front-end; prop[] already carries the
+     *      Mie mus and g).  With polmedianum > 0 every packet carries a Stokes vector (initially srciquv), scattering
+     *      angles are drawn by rejection against the Mueller matrix (src/mcx_core.cl:2454-2468, 801-835) and savedetflag
+     *      bit 7 (I) appends {I, Q, U, V} to the detected-photon record.  Label media, 3-D domains. ---- */
+    uint32_t polmedianum;
+    const mcxb_f4* smatrix;
+    mcxb_f4  srciquv;
+    /* ---- RF: Config.omega, the modulation angular frequency in rad/s.  In a forward run omega > 0 turns the packet
+     *      weight into a complex number that rotates by omega*n/c0 per unit length (src/mcx_core.cl:2750-2763) and the
+     *      output into TWO volume sets, real parts then imaginary parts (mcxb_output.fieldlen doubles; src/mcx_host.cpp:
+     *      1263-1268); in a replay it drives the RF / RFMUS Jacobians, also two volume sets.  (The reference's kernel adds
+     *      the imaginary part of RFMUS two volume sets behind the real one, :2601, past the end of the buffer its host
+     *      allocates; here it goes into the second set, where the host looks for it.) ---- */
+    float    omega;
 } mcxb_config;
 
 typedef struct mcxb_output {
@@ -314,6 +337,16 @@ uint32_t mcxb_sim_acc_copies(mcxb_sim* sim);        /* replicated accumulator vo
 const char* mcxb_sim_kernel_name(mcxb_sim* sim);    /* which specialisation was selected */
 float mcxb_sim_last_kernel_ms(mcxb_sim* sim);       /* CUDA-event time of the most recent launch (syncs on it) */
 void mcxb_sim_destroy(mcxb_sim* sim);
+
+/* the post-kernels of the adjoint output types (mcx_adjoint_kernel / mcx_adjoint_dcoeff_kernel, src/mcx_core.cl:3393-3512,
+ * launched by src/mcx_host.cpp:1498-1537) on CUDA device `device`.  field_re (and field_im for an RF run, else NULL)
+ * hold the NORMALISED fluence of ns source volumes followed by nd detector volumes, maxgate gates each (host memory,
+ * dimxyz * maxgate * (ns + nd) floats).  out receives dimxyz * ns * nd floats, pair (s, d) at (s * nd + d) * dimxyz --
+ * gates summed, then phi_src * phi_det (gradient == 0) or grad phi_src . grad phi_det by second-order finite differences
+ * in voxel units (gradient != 0) -- followed, when field_im is given, by the same number of imaginary parts.  The scale
+ * factors (-Vvox, -unitinmm, 1 / (3 (1-g) mus^2) ...) stay with the caller (src/mcx_host.cpp:1560-1640). */
+int mcxb_adjoint_products(int device, const float* field_re, const float* field_im, uint32_t dimx, uint32_t dimy, uint32_t dimz,
+                          uint32_t maxgate, uint32_t ns, uint32_t nd, int gradient, float* out);
 
 /* host-side normalisation shared by fetch and by the multi-GPU reducer (src/mcx_host.cpp:1382-1465):
  * returns the scale factor for the given totals */

@@ -129,6 +129,12 @@ void fill_config(const Config* cfg, mcxb_config* c) {
     c->sched = MCXB_SCHED_DYNAMIC;
     c->accum = MCXB_ACCUM_F64;
 
+    /* polarised light and RF: tables and scalars the front-end prepared (mcx_prep_polarized, src/mcx_utils.c:1483-1519) */
+    c->polmedianum = cfg->smatrix ? cfg->polmedianum : 0;
+    c->smatrix = reinterpret_cast<const mcxb_f4*>(cfg->smatrix);
+    c->srciquv = f4(cfg->srciquv);
+    c->omega = cfg->omega;
+
     if (cfg->seed == SEED_FROM_FILE) {
         /* photon replay: the records mcx_replayinit / mcx_replayprep prepared (src/mcx_utils.c:1355-1470) take the place
          * of the gseed / greplayw / greplaytof / greplaydetid buffers of src/mcx_host.cpp:722-737 */
@@ -142,9 +148,10 @@ void fill_config(const Config* cfg, mcxb_config* c) {
 
 /* floats per detected-photon record (hostdetreclen, src/mcx_host.cpp:494-496) */
 unsigned int record_length(const Config* cfg) {
-    const unsigned int flag = cfg->issavedet ? (cfg->savedetflag & 0x7Fu) : 0u;
+    const unsigned int flag = cfg->issavedet ? (cfg->savedetflag & ((cfg->polmedianum && cfg->smatrix) ? 0xFFu : 0x7Fu)) : 0u;
     const unsigned int nmed = cfg->medianum - 1;
-    return nmed * ((flag >> 1 & 1u) + (flag >> 2 & 1u) + (flag >> 3 & 1u)) + (flag & 1u) + 3 * ((flag >> 4 & 1u) + (flag >> 5 & 1u)) + (flag >> 6 & 1u);
+    return nmed * ((flag >> 1 & 1u) + (flag >> 2 & 1u) + (flag >> 3 & 1u)) + (flag & 1u) + 3 * ((flag >> 4 & 1u) + (flag >> 5 & 1u)) + (flag >> 6 & 1u) +
+           4 * (flag >> 7 & 1u);
 }
 
 /* what this build's hot path does not cover is refused loudly, never approximated */
@@ -153,16 +160,16 @@ void check_supported(const Config* cfg) {
         mcx_error(-1, "SVMC, mixed-label and two-word media formats are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
     }
 
-    if (cfg->seed == SEED_FROM_FILE && (cfg->replay.seed == NULL || cfg->outputtype == otRF || cfg->outputtype == otRFmus)) {
-        mcx_error(-1, "RF replay is outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
+    if (cfg->seed == SEED_FROM_FILE && cfg->replay.seed == NULL) {
+        mcx_error(-1, "replay needs the saved RNG states of the detected photons", __FILE__, __LINE__);
     }
 
     if (cfg->respin < 1) {
         mcx_error(-1, "negative respin is not supported by the CUDA engine", __FILE__, __LINE__);
     }
 
-    if (cfg->polmedianum || cfg->omega > 0.f) {
-        mcx_error(-1, "polarised and RF modes are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
+    if (cfg->istrajstokes && (cfg->debuglevel & (MCX_DEBUG_MOVE | MCX_DEBUG_MOVE_ONLY))) {
+        mcx_error(-1, "trajectory records with Stokes vectors are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
     }
 }
 
@@ -277,7 +284,11 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
     const unsigned int nsrcvol = sharing ? cfg->srcnum : ((cfg->extrasrclen && cfg->srcid < 0) ? cfg->extrasrclen + 1 : 1);
     const bool replay = cfg->seed == SEED_FROM_FILE;
     const unsigned int nrepvol = (replay && cfg->replaydet == -1) ? std::max(1u, cfg->detnum) : 1u;     /* src/mcx_host.cpp:684-689 */
-    const size_t fieldlen = dimxyz * cfg->maxgate * nsrcvol * nrepvol;
+    /* RF outputs are complex, real volumes followed by imaginary volumes (src/mcx_host.cpp:1263-1276) */
+    const bool isrfforward = cfg->omega > 0.f && !replay;
+    const bool rfplanes = isrfforward || (replay && (cfg->outputtype == otRF || cfg->outputtype == otRFmus));
+    const size_t planelen = dimxyz * cfg->maxgate * nsrcvol * nrepvol;
+    const size_t fieldlen = planelen * (rfplanes ? 2 : 1);
 
     if (replay) {
         workdev = 1;        /* "replay should only work with a single device" (src/mcx_host.cpp:723) */
@@ -652,7 +663,7 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         MCX_FPRINTF(cfg->flog, "normalizing raw data ...\t");
         cfg->energyabs += cfg->energytot - cfg->energyesc;
         const bool sens = cfg->outputtype == otJacobian || cfg->outputtype == otWP || cfg->outputtype == otDCS ||
-                          cfg->outputtype == otWLTOF || cfg->outputtype == otWPTOF;
+                          cfg->outputtype == otWLTOF || cfg->outputtype == otWPTOF || cfg->outputtype == otRF || cfg->outputtype == otRFmus;
 
         if (replay && sens && cfg->replaydet == -1) {
             /* every detector at once: one scale per detector volume (src/mcx_host.cpp:1398-1421) */
@@ -675,6 +686,10 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
                 cfg->his.normalizer = scale;
                 MCX_FPRINTF(cfg->flog, "normalization factor for detector %d alpha=%f\n", detid, scale);
                 mcx_normalize(cfg->exportfield + (detid - 1) * block, scale, (int)block, cfg->isnormalized, 0, 1);
+
+                if (rfplanes) {       /* src/mcx_host.cpp:1415-1417 */
+                    mcx_normalize(cfg->exportfield + planelen + (detid - 1) * block, scale, (int)block, cfg->isnormalized, 0, 1);
+                }
             }
         } else if (sharing) {
             /* per-pattern totals and scales, the reference's post-processing (src/mcx_host.cpp:1351-1380, 1436-1462) */
@@ -729,11 +744,115 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
         cfg->energyabs += cfg->energytot - cfg->energyesc;
     }
 
+    /* ---- adjoint Jacobians: products of the normalised source and detector fluences (src/mcx_host.cpp:1468-1641); the
+     *      per-voxel products run on the device (mcxb_adjoint_products), the scale factors are applied here ---- */
+    if (cfg->issave2pt && MCX_IS_ADJOINT_TYPE(cfg->outputtype) && !replay && cfg->detdir != NULL && cfg->exportfield) {
+        const unsigned int tic = GetTimeMillis();
+        const int isdual = MCX_IS_DUAL_ADJOINT_TYPE(cfg->outputtype);
+        const unsigned int Nd = cfg->detnum, Ns = cfg->extrasrclen + 1 - cfg->detnum;
+        const size_t adjointlen = dimxyz * Ns * Nd, single = adjointlen * (isrfforward ? 2 : 1);
+        const float Vvox = cfg->steps.x * cfg->steps.y * cfg->steps.z;
+        const int dev0 = (int)(intptr_t)devices[0] - 1;
+        std::vector<float> hmua, hsecond(single);
+        const float* im = isrfforward ? cfg->exportfield + planelen : NULL;
+        const bool wantprod = isdual || cfg->outputtype == otAdjoint;
+
+        if (wantprod) {
+            hmua.resize(single);
+            rc = mcxb_adjoint_products(dev0, cfg->exportfield, im, cfg->dim.x, cfg->dim.y, cfg->dim.z, cfg->maxgate, Ns, Nd, 0, hmua.data());
+        }
+
+        if (rc == MCXB_OK && (isdual || cfg->outputtype != otAdjoint)) {
+            rc = mcxb_adjoint_products(dev0, cfg->exportfield, im, cfg->dim.x, cfg->dim.y, cfg->dim.z, cfg->maxgate, Ns, Nd, 1, hsecond.data());
+        }
+
+        if (rc != MCXB_OK) {
+            free(gpu);
+            raise(rc, __FILE__, __LINE__);
+            return;
+        }
+
+        /* 1 / (3 (1-g) mus^2) or 1 / (3 (1-g)^2 mus^2) per voxel (:1569-1583, 1612-1636) */
+        auto opscale = [&](size_t vox, bool musp) -> float {
+            const unsigned int medid = cfg->vol[vox] & 0xFF;
+
+            if (medid < cfg->medianum) {
+                const float mus = cfg->prop[medid].mus, onemg = 1.f - cfg->prop[medid].g;
+
+                if (mus > 0.f && onemg > 0.f) {
+                    return musp ? 1.f / (3.f * onemg * onemg * mus * mus) : 1.f / (3.f * onemg * mus * mus);
+                }
+            }
+
+            return 0.f;
+        };
+
+        if (cfg->exportjacob) {
+            free(cfg->exportjacob);
+        }
+
+        cfg->exportjacob = (float*)malloc(sizeof(float) * single * (isdual ? 2 : 1));
+
+        if (isdual) {
+            for (size_t k = 0; k < single; k++) {
+                hmua[k] *= -Vvox;
+                hsecond[k] *= -cfg->unitinmm;
+            }
+
+            if (cfg->outputtype == otAdjointMuaMusp) {
+                for (size_t vox = 0; vox < dimxyz; vox++) {
+                    const float f = opscale(vox, true);
+
+                    for (unsigned int sd = 0; sd < Ns * Nd; sd++) {
+                        hsecond[vox + (size_t)sd * dimxyz] *= f;
+
+                        if (isrfforward) {
+                            hsecond[vox + (size_t)sd * dimxyz + adjointlen] *= f;
+                        }
+                    }
+                }
+            }
+
+            /* {mua Re, second Re, mua Im, second Im} (:1592-1600) */
+            memcpy(cfg->exportjacob, hmua.data(), adjointlen * sizeof(float));
+            memcpy(cfg->exportjacob + adjointlen, hsecond.data(), adjointlen * sizeof(float));
+
+            if (isrfforward) {
+                memcpy(cfg->exportjacob + 2 * adjointlen, hmua.data() + adjointlen, adjointlen * sizeof(float));
+                memcpy(cfg->exportjacob + 3 * adjointlen, hsecond.data() + adjointlen, adjointlen * sizeof(float));
+            }
+        } else {
+            const float* src = (cfg->outputtype == otAdjoint) ? hmua.data() : hsecond.data();
+            const float adjscale = (cfg->outputtype == otAdjoint) ? -Vvox : -cfg->unitinmm;
+
+            for (size_t k = 0; k < single; k++) {
+                cfg->exportjacob[k] = src[k] * adjscale;
+            }
+
+            if (cfg->outputtype == otAdjointMus || cfg->outputtype == otAdjointMusp) {
+                for (size_t vox = 0; vox < dimxyz; vox++) {
+                    const float f = opscale(vox, cfg->outputtype == otAdjointMusp);
+
+                    for (unsigned int sd = 0; sd < Ns * Nd; sd++) {
+                        cfg->exportjacob[vox + (size_t)sd * dimxyz] *= f;
+
+                        if (isrfforward) {
+                            cfg->exportjacob[vox + (size_t)sd * dimxyz + adjointlen] *= f;
+                        }
+                    }
+                }
+            }
+        }
+
+        MCX_FPRINTF(cfg->flog, "adjoint Jacobian computation complete : %d ms\n", GetTimeMillis() - tic);
+    }
+
 #ifndef MCX_CONTAINER
 
     if (cfg->issave2pt && cfg->parentid == mpStandalone) {
-        MCX_FPRINTF(cfg->flog, "saving data to file ... %zu %d\t", fieldlen, cfg->maxgate);
-        mcx_savedata(cfg->exportfield, fieldlen, cfg);
+        /* like the reference, the volume file of an RF run holds the real parts only (src/mcx_host.cpp:1646-1648) */
+        MCX_FPRINTF(cfg->flog, "saving data to file ... %zu %d\t", planelen, cfg->maxgate);
+        mcx_savedata(cfg->exportfield, planelen, cfg);
         MCX_FPRINTF(cfg->flog, "saving data complete\n\n");
         mcx_flush(cfg);
     }

@@ -6,7 +6,8 @@ or ``python -m mcxcl_b200.build``) every entry point raises, it never reroutes t
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
+NANGLES = 181
 DEBUG_RNG = 1
 DEBUG_MOVE, DEBUG_MOVE_ONLY = 2, 8
 TRAJ_RECLEN = 6
@@ -85,6 +86,10 @@ class Config(C.Structure):
         ("replaydet", C.c_int32),
         ("respin", C.c_int32),
         ("maxjumpdebug", C.c_uint32),
+        ("polmedianum", C.c_uint32),
+        ("smatrix", C.POINTER(F4)),
+        ("srciquv", F4),
+        ("omega", C.c_float),
     ]
 
 
@@ -179,6 +184,7 @@ SYMBOLS = [
     ("mcxb_sim_last_kernel_ms", C.c_float, [_VP]),
     ("mcxb_sim_destroy", None, [_VP]),
     ("mcxb_normalizer", C.c_float, [C.POINTER(Config), C.c_double]),
+    ("mcxb_adjoint_products", C.c_int, [C.c_int, _VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _VP]),
     ("mcxb_test_rng", C.c_int, [C.c_int, _VP, C.c_uint32, C.c_uint32, _VP, _VP]),
     ("mcxb_test_trace", C.c_int, [C.c_int, _VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_float, _VP]),

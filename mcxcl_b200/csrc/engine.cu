@@ -382,6 +382,10 @@ struct mcxb_sim {
     std::vector<float> h_rweight;                /* host copies for the replay normalisation */
     std::vector<int32_t> h_rdetid;
     uint32_t nrepvol = 1;
+    uint32_t rfplanes = 1;           /* 2 = real + imaginary volume sets (RF outputs) */
+    uint64_t planelen = 0;           /* elements of one volume set: fieldlen = planelen * rfplanes */
+    bool ext = false;                /* extended-physics kernel (polarised / RF) */
+    float4* d_smatrix = nullptr;
     uint32_t acccopies = 1;                     /* replicated accumulator volumes (photon_kernel.cuh) */
     unsigned long long* h_progress = nullptr;   /* pinned word the progress poll copies the photon counter into */
     cudaStream_t pollstream = nullptr;
@@ -395,10 +399,11 @@ struct mcxb_sim {
 };
 
 /* det: 0 = no detector capture, 1 = the default record, 2 = any record flags (generic kernels take 1 and 2 alike) */
-static const KernelEntry* find_kernel(int src, bool refl, int det, int mediabits, bool acc64, bool stats, bool common, bool queue = false) {
+static const KernelEntry* find_kernel(int src, bool refl, int det, int mediabits, bool acc64, bool stats, bool common, bool queue = false, bool ext = false) {
     typedef const KernelEntry* (*GroupFn)(int*);
     static const GroupFn groups[kNumGroups] = { mcxb_kernel_group_0, mcxb_kernel_group_1, mcxb_kernel_group_2, mcxb_kernel_group_3,
-                                                mcxb_kernel_group_4, mcxb_kernel_group_5, mcxb_kernel_group_6, mcxb_kernel_group_7
+                                                mcxb_kernel_group_4, mcxb_kernel_group_5, mcxb_kernel_group_6, mcxb_kernel_group_7,
+                                                mcxb_kernel_group_8, mcxb_kernel_group_9
                                               };
     const bool m16 = mediabits == 16, m32 = mediabits == 32;
     /* most specialised first: {source, common} -> {any source, common} -> {any source, generic} */
@@ -414,7 +419,8 @@ static const KernelEntry* find_kernel(int src, bool refl, int det, int mediabits
                 const bool detok = wantgen[pass] ? ((e[i].savedet != 0) == (det != 0)) : (e[i].savedet == det);
 
                 if (e[i].src == wantsrc[pass] && e[i].generic == wantgen[pass] && e[i].reflect == refl && detok &&
-                        e[i].media16 == m16 && e[i].media32 == m32 && e[i].acc64 == acc64 && e[i].stats == stats && (e[i].queue != 0) == (queue && !wantgen[pass])) {
+                        e[i].media16 == m16 && e[i].media32 == m32 && e[i].acc64 == acc64 && e[i].stats == stats && (e[i].queue != 0) == (queue && !wantgen[pass]) &&
+                        e[i].ext == ext) {
                     return e + i;
                 }
             }
@@ -467,15 +473,16 @@ static uint32_t count_gates(const mcxb_config* cfg) {
     return (uint32_t)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);
 }
 
-extern "C" float mcxb_normalizer(const mcxb_config* cfg, double energytot) {
+static float normalizer_impl(const mcxb_config* cfg, double energytot, bool replay) {
     /* src/mcx_host.cpp:1389-1396, 1449-1451; Vvox = steps.x*steps.y*steps.z with steps == unitinmm */
     float scale = 1.f;
     const float Vvox = cfg->unitinmm * cfg->unitinmm * cfg->unitinmm;
+    const bool adjoint = cfg->outputtype >= MCXB_OT_ADJOINT && cfg->outputtype <= MCXB_OT_ADJOINT_MUA_MUSP;
 
-    if (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE) {
+    if (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE || adjoint || (cfg->omega > 0.f && !replay)) {
         scale = (float)(cfg->unitinmm / (energytot * Vvox * cfg->tstep));
 
-        if (cfg->outputtype == MCXB_OT_FLUENCE) {
+        if (cfg->outputtype == MCXB_OT_FLUENCE || adjoint) {
             scale *= cfg->tstep;
         }
     } else if (cfg->outputtype == MCXB_OT_ENERGY || cfg->outputtype == MCXB_OT_L) {
@@ -500,6 +507,10 @@ extern "C" float mcxb_normalizer(const mcxb_config* cfg, double energytot) {
     return scale;
 }
 
+extern "C" float mcxb_normalizer(const mcxb_config* cfg, double energytot) {
+    return normalizer_impl(cfg, energytot, cfg->replay_seed != nullptr);
+}
+
 /* ---- small device kernels -------------------------------------------------------------------- */
 template <typename AccT>
 __global__ void finalize_kernel(const AccT* __restrict__ acc, float* __restrict__ out, size_t n, uint32_t copies) {
@@ -511,6 +522,110 @@ __global__ void finalize_kernel(const AccT* __restrict__ acc, float* __restrict_
         }
 
         out[i] = (float)sum;
+    }
+}
+
+/* ---- adjoint post-kernels (mcx_adjoint_kernel / mcx_adjoint_dcoeff_kernel, src/mcx_core.cl:3313-3512).  The reference
+ *      re-sums the time gates of a volume for every voxel, every pair and every finite-difference neighbour; here the
+ *      continuous-wave volumes are formed once and the pair loop reads them ---- */
+__global__ void adjoint_cw_kernel(const float* __restrict__ field, float* __restrict__ cw, uint32_t dimxyz, uint32_t maxgate, uint32_t nslot) {
+    const size_t n = (size_t)dimxyz * nslot;
+
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t slot = i / dimxyz, vox = i - slot * dimxyz;
+        float sum = 0.f;
+
+        for (uint32_t t = 0; t < maxgate; t++) {       /* same order as mcx_cw_sum (:3322-3336) */
+            sum += field[vox + (size_t)(t + slot * maxgate) * dimxyz];
+        }
+
+        cw[i] = sum;
+    }
+}
+
+/* second-order finite difference along one axis in voxel units (mcx_fd_grad, :3345-3381) */
+__device__ __forceinline__ float adjoint_fd(const float* __restrict__ f, size_t at, uint32_t i, uint32_t n, size_t stride) {
+    if (n <= 1u) {
+        return 0.f;
+    }
+
+    const float f0 = f[at];
+
+    if (i == 0u) {
+        const float fp1 = f[at + stride];
+        return (n == 2u) ? (fp1 - f0) : (-3.f * f0 + 4.f * fp1 - f[at + 2 * stride]) * 0.5f;
+    }
+
+    if (i == n - 1u) {
+        const float fm1 = f[at - stride];
+        return (n == 2u) ? (f0 - fm1) : (f[at - 2 * stride] - 4.f * fm1 + 3.f * f0) * 0.5f;
+    }
+
+    return (f[at + stride] - f[at - stride]) * 0.5f;
+}
+
+__global__ void adjoint_pair_kernel(const float* __restrict__ re, const float* __restrict__ im, float* __restrict__ out, uint32_t nx, uint32_t ny,
+                                    uint32_t nz, uint32_t ns, uint32_t nd, int gradient) {
+    const uint32_t dimxyz = nx * ny * nz;
+    const size_t adjointlen = (size_t)dimxyz * ns * nd;
+
+    for (uint32_t vox = blockIdx.x * blockDim.x + threadIdx.x; vox < dimxyz; vox += gridDim.x * blockDim.x) {
+        const uint32_t ix = vox % nx, iy = (vox / nx) % ny, iz = vox / (nx * ny);
+
+        for (uint32_t sidx = 0; sidx < ns; sidx++) {
+            const size_t sa = (size_t)sidx * dimxyz + vox;
+            float sr[3], si[3] = { 0.f, 0.f, 0.f };
+
+            if (gradient) {
+                sr[0] = adjoint_fd(re, sa, ix, nx, 1);
+                sr[1] = adjoint_fd(re, sa, iy, ny, nx);
+                sr[2] = adjoint_fd(re, sa, iz, nz, (size_t)nx * ny);
+
+                if (im) {
+                    si[0] = adjoint_fd(im, sa, ix, nx, 1);
+                    si[1] = adjoint_fd(im, sa, iy, ny, nx);
+                    si[2] = adjoint_fd(im, sa, iz, nz, (size_t)nx * ny);
+                }
+            } else {
+                sr[0] = re[sa];
+                sr[1] = sr[2] = 0.f;
+                si[0] = im ? im[sa] : 0.f;
+            }
+
+            for (uint32_t d = 0; d < nd; d++) {
+                const size_t da = (size_t)(ns + d) * dimxyz + vox;
+                const size_t o = (size_t)(sidx * nd + d) * dimxyz + vox;
+                float dr[3], di[3] = { 0.f, 0.f, 0.f };
+
+                if (gradient) {
+                    dr[0] = adjoint_fd(re, da, ix, nx, 1);
+                    dr[1] = adjoint_fd(re, da, iy, ny, nx);
+                    dr[2] = adjoint_fd(re, da, iz, nz, (size_t)nx * ny);
+
+                    if (im) {
+                        di[0] = adjoint_fd(im, da, ix, nx, 1);
+                        di[1] = adjoint_fd(im, da, iy, ny, nx);
+                        di[2] = adjoint_fd(im, da, iz, nz, (size_t)nx * ny);
+                    }
+                } else {
+                    dr[0] = re[da];
+                    dr[1] = dr[2] = 0.f;
+                    di[0] = im ? im[da] : 0.f;
+                }
+
+                /* complex product / dot product (:3436-3449, 3497-3503), terms in the reference's order */
+                float val = gradient ? (__fmul_rn(sr[0], dr[0]) + __fmul_rn(sr[1], dr[1]) + __fmul_rn(sr[2], dr[2])) : __fmul_rn(sr[0], dr[0]);
+
+                if (im) {
+                    val -= gradient ? (__fmul_rn(si[0], di[0]) + __fmul_rn(si[1], di[1]) + __fmul_rn(si[2], di[2])) : __fmul_rn(si[0], di[0]);
+                    out[o + adjointlen] = gradient ? (__fmul_rn(sr[0], di[0]) + __fmul_rn(sr[1], di[1]) + __fmul_rn(sr[2], di[2])
+                                                      + __fmul_rn(si[0], dr[0]) + __fmul_rn(si[1], dr[1]) + __fmul_rn(si[2], dr[2]))
+                                          : (__fmul_rn(sr[0], di[0]) + __fmul_rn(si[0], dr[0]));
+                }
+
+                out[o] = val;
+            }
+        }
     }
 }
 
@@ -540,7 +655,7 @@ static void sim_free(mcxb_sim* s) {
     cudaDeviceSynchronize();        /* pooled buffers may be handed out again at once: nothing may still be using them */
     void* bufs[] = { s->d_traj, s->d_trajcount, s->d_media, s->d_field, s->d_field32, s->d_tables, s->d_seeds, s->d_det, s->d_detcount, s->d_seedout,
                      s->d_counter, s->d_energy, s->d_pattern, s->d_invcdf, s->d_stats, s->h_field, s->h_small,
-                     s->d_rseed, s->d_rweight, s->d_rtof, s->d_rdetid, s->h_progress
+                     s->d_rseed, s->d_rweight, s->d_rtof, s->d_rdetid, s->h_progress, s->d_smatrix
                    };
 
     for (void* b : bufs) {
@@ -623,10 +738,40 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         return fail(MCXB_ERR_ARG, "pattern sources need srcpattern");
     }
 
+    /* the adjoint types run the forward kernel as a fluence run (src/mcx_core.cl:2844; normalised like fluence,
+     * src/mcx_host.cpp:1389-1394); the products are formed afterwards by mcxb_adjoint_products */
+    const bool adjoint_ot = cfg->outputtype >= MCXB_OT_ADJOINT && cfg->outputtype <= MCXB_OT_ADJOINT_MUA_MUSP;
     const bool forward_ot = cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE || cfg->outputtype == MCXB_OT_ENERGY ||
-                            cfg->outputtype == MCXB_OT_L;
+                            cfg->outputtype == MCXB_OT_L || adjoint_ot;
+    const bool rf_ot = cfg->outputtype == MCXB_OT_RF || cfg->outputtype == MCXB_OT_RFMUS;
     const bool replay_ot = cfg->outputtype == MCXB_OT_JACOBIAN || cfg->outputtype == MCXB_OT_WP || cfg->outputtype == MCXB_OT_DCS ||
-                           cfg->outputtype == MCXB_OT_WLTOF || cfg->outputtype == MCXB_OT_WPTOF;
+                           cfg->outputtype == MCXB_OT_WLTOF || cfg->outputtype == MCXB_OT_WPTOF || rf_ot;
+    /* complex packet weights: a modulation frequency in a forward run (src/mcx_host.cpp:473) */
+    const bool rfforward = cfg->omega > 0.f && !cfg->replay_seed;
+    const bool polarized = cfg->polmedianum > 0;
+
+    if (adjoint_ot && cfg->replay_seed) {
+        return fail(MCXB_ERR_ARG, "the adjoint output types are forward runs");
+    }
+
+    if (rf_ot && !(cfg->omega > 0.f)) {
+        return fail(MCXB_ERR_ARG, "the RF replay outputs need a modulation frequency (omega > 0)");
+    }
+
+    if (polarized) {
+        /* src/mcx_utils.c:1535-1548: one Mueller matrix per non-background medium of a LABEL volume */
+        if (!cfg->smatrix || cfg->medianum != cfg->polmedianum + 1 || cfg->mediaformat > 4) {
+            return fail(MCXB_ERR_ARG, "polarised runs need label media and one Mueller matrix (smatrix) per medium: medianum = polmedianum + 1");
+        }
+
+        if (cfg->dimx == 1 || cfg->dimy == 1 || cfg->dimz == 1) {
+            return fail(MCXB_ERR_ARG, "polarised light is simulated in 3-D domains only");
+        }
+    }
+
+    if ((rfforward || rf_ot || polarized) && cfg->srcnum > 1) {
+        return fail(MCXB_ERR_ARG, "photon sharing cannot be combined with RF or polarised runs in this build");
+    }
 
     if (!forward_ot && !replay_ot) {
         return fail(MCXB_ERR_ARG, "output type %d is outside this build's hot path", cfg->outputtype);
@@ -695,6 +840,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->cfg.replay_weight = nullptr;
     s->cfg.replay_tof = nullptr;
     s->cfg.replay_detid = nullptr;
+    s->cfg.smatrix = nullptr;
 
     const uint64_t dimxyz = (uint64_t)cfg->dimx * cfg->dimy * cfg->dimz;
     const uint32_t maxgate = count_gates(cfg);
@@ -709,13 +855,19 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->nsrcvol = nsrcvol;
     /* src/mcx_host.cpp:684-689: one volume per detector when every detector is replayed at once */
     s->nrepvol = (cfg->replay_seed && cfg->replaydet == -1) ? std::max(1u, cfg->detnum) : 1u;
-    s->fieldlen = dimxyz * maxgate * nsrcvol * s->nrepvol;
     s->rngdebug = (cfg->debuglevel & 1u) != 0;
+    /* RF outputs are complex: a second volume set (imaginary parts) follows the first (src/mcx_host.cpp:1263-1276; what
+     * pmcxcl allocates, src/pmcxcl.cpp:1209-1211) */
+    s->rfplanes = ((rfforward || (rf_ot && cfg->replay_seed)) && !s->rngdebug) ? 2u : 1u;
+    s->planelen = dimxyz * maxgate * nsrcvol * s->nrepvol;
+    s->fieldlen = s->planelen * s->rfplanes;
+    s->ext = (rfforward || rf_ot || polarized) && !s->rngdebug;
     const bool savedet = cfg->issavedet != 0 && !s->rngdebug;
-    const uint32_t flag = savedet ? (cfg->savedetflag & 0x7Fu) : 0u;
+    /* the I flag (Stokes vector of a detected photon) exists in polarised runs only (src/mcx_utils.c:1777-1781) */
+    const uint32_t flag = savedet ? (cfg->savedetflag & (polarized ? 0xFFu : 0x7Fu)) : 0u;
     const uint32_t nmed = cfg->medianum - 1;
     const uint32_t partialdata = nmed * ((flag >> 1 & 1u) + (flag >> 2 & 1u) + (flag >> 3 & 1u));
-    s->reclen = partialdata + (flag & 1u) + 3 * ((flag >> 4 & 1u) + (flag >> 5 & 1u)) + (flag >> 6 & 1u);
+    s->reclen = partialdata + (flag & 1u) + 3 * ((flag >> 4 & 1u) + (flag >> 5 & 1u)) + (flag >> 6 & 1u) + 4 * (flag >> 7 & 1u);
 
     /* ---- continuous media: the words go to the device as they are (src/mcx_host.cpp:739-745) ---- */
     const bool continuous = cfg->mediaformat > 4;
@@ -875,6 +1027,13 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         CU_TRY(cudaMemcpy(s->d_invcdf, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
     }
 
+    /* ---- Mueller matrices of a polarised run (src/mcx_host.cpp:823-827) ---- */
+    if (polarized) {
+        const size_t n = (size_t)cfg->polmedianum * MCXB_NANGLES;
+        CU_TRY(dev_alloc(&s->d_smatrix, device, sizeof(float4) * n));
+        CU_TRY(cudaMemcpy(s->d_smatrix, cfg->smatrix, sizeof(float4) * n, cudaMemcpyHostToDevice));
+    }
+
     /* ---- replay records (src/mcx_host.cpp:722-737) ---- */
     if (cfg->replay_seed) {
         const size_t n = std::max<uint64_t>(cfg->nphoton, 1);
@@ -903,7 +1062,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->acc64 = cfg->accum != MCXB_ACCUM_F32;
     const bool refl = needs_reflection(cfg);
     const bool stats = (cfg->debuglevel & MCXB_DEBUG_STATS) != 0;
-    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32;
+    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32 && !s->ext;
     const int detmode = savedet ? (flag == 0x5u ? 1 : 2) : 0;
     /* Scattering queue (photon_kernel.cuh): pays where a packet crosses several voxels per scattering event.  Measured on
      * B200: +8..10 % at mus = 1 per voxel (cube60 / cube60b), +20 % at mus <= 0.2 (skinvessel), -9..-12 % at mus = 8..40
@@ -918,6 +1077,10 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     const KernelEntry* ke = nullptr;
     const int mediabits = s->media32 ? 32 : (s->media16 ? 16 : 8);
 
+    if (stats && s->ext) {
+        return fail(MCXB_ERR_ARG, "the instrumented (stats) kernel does not carry the polarised / RF code");
+    }
+
     if (stats && s->media32) {
         return fail(MCXB_ERR_ARG, "the instrumented (stats) kernel exists for label media only");
     }
@@ -930,7 +1093,12 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         }
 
         if (!ke) {
-            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, false);
+            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, false, s->ext);
+        }
+
+        if (!ke && s->ext && !s->acc64) {
+            s->acc64 = true;        /* the extended-physics kernels exist with fp64 accumulators only */
+            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, true, false, common, false, true);
         }
     }
 
@@ -1066,7 +1234,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     P.gscatter = cfg->gscatter;
     P.doreflect = cfg->isreflect != 0;
     P.save2pt = cfg->issave2pt != 0;
-    P.outputtype = (uint32_t)cfg->outputtype;
+    P.outputtype = adjoint_ot ? (uint32_t)MCXB_OT_FLUENCE : (uint32_t)cfg->outputtype;
     {
         uint32_t is2d = (cfg->dimx == 1 ? 1 : (cfg->dimy == 1 ? 2 : (cfg->dimz == 1 ? 3 : 0)));
 
@@ -1144,6 +1312,15 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     P.trajcount = s->d_trajcount;
     P.maxjumpdebug = cfg->maxjumpdebug;
     P.idbase = 0;
+    P.smatrix = s->d_smatrix;
+    P.maxpolmedia = polarized ? cfg->polmedianum : 0u;
+    P.s0i = cfg->srciquv.x;
+    P.s0q = cfg->srciquv.y;
+    P.s0u = cfg->srciquv.z;
+    P.s0v = cfg->srciquv.w;
+    P.omega = cfg->omega;
+    P.rfforward = rfforward ? 1u : 0u;
+    P.rfplane = (s->rfplanes == 2) ? s->planelen : 0ull;
 
     if (getenv("MCXB_DEBUG_PTRS")) {
         fprintf(stderr, "mcxb buffers: media %p field %p field32 %p tables %p seeds %p det %p detcount %p counter %p energy %p\n",
@@ -1407,7 +1584,7 @@ extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) 
              * detected THERE) (src/mcx_host.cpp:1398-1421) */
             const uint64_t block = (uint64_t)s->P.dimxyz * s->maxgate;
 
-            for (uint64_t v = 0; v < (uint64_t)s->nsrcvol * s->nrepvol; v++) {
+            for (uint64_t v = 0; v < (uint64_t)s->nsrcvol * s->nrepvol * s->rfplanes; v++) {
                 const int det = (int)(v % s->nrepvol) + 1;
                 float scale = 0.f;
 
@@ -1430,7 +1607,7 @@ extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) 
         } else if (s->cfg.isnormalized && s->cfg.srcnum > 1 && out->energytot > 0.0) {
             /* photon sharing: pattern i is scaled by psize / sum(pattern i) (src/mcx_host.cpp:1436-1447); the volumes
              * are interleaved pattern-fastest, as mcx_normalize(field, scale, n, op, i, srcnum) walks them */
-            const float ref = mcxb_normalizer(&s->cfg, out->energytot);
+            const float ref = normalizer_impl(&s->cfg, out->energytot, s->d_rseed != nullptr);
             const float psize = (float)((int)s->cfg.src.param1.w * (int)s->cfg.src.param2.w);
             const uint32_t ns = s->cfg.srcnum;
             std::vector<float> scale(ns);
@@ -1448,7 +1625,7 @@ extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) 
             mcxb_config nc = s->cfg;
             nc.replay_weight = (sens && !s->h_rweight.empty()) ? s->h_rweight.data() : nullptr;
             nc.nphoton = s->P.nphoton;
-            const float scale = mcxb_normalizer(&nc, out->energytot);
+            const float scale = normalizer_impl(&nc, out->energytot, s->d_rseed != nullptr);
             out->normalizer = scale;
 
             for (uint64_t i = 0; i < n; i++) {
@@ -1461,6 +1638,65 @@ extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) 
         }
     }
 
+    return MCXB_OK;
+}
+
+extern "C" int mcxb_adjoint_products(int device, const float* field_re, const float* field_im, uint32_t dimx, uint32_t dimy, uint32_t dimz,
+                                     uint32_t maxgate, uint32_t ns, uint32_t nd, int gradient, float* out) {
+    if (!field_re || !out || dimx == 0 || dimy == 0 || dimz == 0 || maxgate == 0 || ns == 0 || nd == 0) {
+        return fail(MCXB_ERR_ARG, "mcxb_adjoint_products: fluence volumes of at least one source and one detector are required");
+    }
+
+    const uint64_t dimxyz = (uint64_t)dimx * dimy * dimz;
+
+    if (dimxyz * (ns + nd) * maxgate >= 0xFFFFFFFFull || dimxyz * ns * nd >= 0xFFFFFFFFull) {
+        return fail(MCXB_ERR_ARG, "mcxb_adjoint_products: volumes too large");
+    }
+
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+
+    if (device < 0 || device >= ndev) {
+        return fail(MCXB_ERR_NODEVICE, "Specified GPU does not exist");
+    }
+
+    CU_TRY(cudaSetDevice(device));
+    const size_t inlen = dimxyz * maxgate * (ns + nd), cwlen = dimxyz * (ns + nd), pairs = dimxyz * ns * nd;
+    const int planes = field_im ? 2 : 1;
+    float* d_in = nullptr;
+    float* d_cw = nullptr;
+    float* d_out = nullptr;
+    int rc = MCXB_OK;
+    auto release = [&]() {
+        pool().put(d_in);
+        pool().put(d_cw);
+        pool().put(d_out);
+    };
+#define ADJ_TRY(call)                                                                                             \
+    do {                                                                                                          \
+        cudaError_t e__ = (call);                                                                                 \
+        if (e__ != cudaSuccess) {                                                                                 \
+            rc = fail(MCXB_ERR_CUDA_BASE - (int)e__, "%s failed: %s", #call, cudaGetErrorString(e__));              \
+            release();                                                                                            \
+            return rc;                                                                                            \
+        }                                                                                                         \
+    } while (0)
+    ADJ_TRY(dev_alloc(&d_in, device, sizeof(float) * inlen));
+    ADJ_TRY(dev_alloc(&d_cw, device, sizeof(float) * cwlen * planes));
+    ADJ_TRY(dev_alloc(&d_out, device, sizeof(float) * pairs * planes));
+    const int grid = (int)std::min<uint64_t>((cwlen + 255) / 256, 148 * 8);
+
+    for (int p = 0; p < planes; p++) {
+        ADJ_TRY(cudaMemcpy(d_in, p ? field_im : field_re, sizeof(float) * inlen, cudaMemcpyHostToDevice));
+        adjoint_cw_kernel <<< grid, 256>>>(d_in, d_cw + (size_t)p * cwlen, (uint32_t)dimxyz, maxgate, ns + nd);
+        ADJ_TRY(cudaGetLastError());
+    }
+
+    adjoint_pair_kernel <<< (int)std::min<uint64_t>((dimxyz + 255) / 256, 148 * 8), 256>>>(d_cw, field_im ? d_cw + cwlen : nullptr, d_out, dimx, dimy, dimz, ns, nd, gradient);
+    ADJ_TRY(cudaGetLastError());
+    ADJ_TRY(cudaMemcpy(out, d_out, sizeof(float) * pairs * planes, cudaMemcpyDeviceToHost));
+#undef ADJ_TRY
+    release();
     return MCXB_OK;
 }
 

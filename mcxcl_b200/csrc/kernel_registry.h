@@ -19,11 +19,12 @@ struct KernelEntry {
     int  savedet;      /* 0 none, 1 default record folded at compile time, 2 record flags at run time */
     bool media16, media32, acc64, stats, generic;     /* media word: 8 bits, 16 bits, or 32 bits (continuous media) */
     int  queue;        /* depth of the scattering queue (shared memory, 16 bytes x depth per thread), 0 = none */
+    bool ext;          /* extended physics compiled in (polarised light, RF): generic kernels at 128 registers */
     PhotonKernelFn fn;
     const char* name;
 };
 
-constexpr int kNumGroups = 8;
+constexpr int kNumGroups = 10;
 
 } // namespace mcxb
 
@@ -35,3 +36,5 @@ extern "C" const mcxb::KernelEntry* mcxb_kernel_group_4(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_5(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_6(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_7(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_8(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_9(int* n);

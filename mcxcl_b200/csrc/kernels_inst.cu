@@ -12,18 +12,23 @@
  *   group 5: any source (run time), 8-bit media, generic  (+ the instrumented variant that counts segments/deposits/scatters)
  *   group 6: any source (run time), 16-bit media, generic (volumes with more than 127 labels)
  *   group 7: any source (run time), 32-bit media words, generic (continuous media formats 99-104: the word encodes the properties)
+ *   group 8: any source (run time), 8-bit media, generic + extended physics (polarised light, RF forward / replay)
+ *   group 9: any source (run time), 16- and 32-bit media, generic + extended physics
  */
 #include "kernel_registry.h"
 
 #ifndef MCXB_INST_GROUP
-    #error "compile with -DMCXB_INST_GROUP=<0..7>"
+    #error "compile with -DMCXB_INST_GROUP=<0..9>"
 #endif
 
 namespace mcxb {
 
 #define MCXB_STR2(x) #x
 #define MCXB_STR(x) MCXB_STR2(x)
-#define MCXB_KQ(SRC, R, D, M, A, S, G, Q) { SRC, R, D, sizeof(M) == 2, sizeof(M) == 4, sizeof(A) == 8, S, G, Q, photon_kernel<SRC, R, D, M, A, S, G, Q>, #SRC "/" #R "/det" #D "/" #M "/" #A "/" #G "/q" MCXB_STR(Q) }
+#define MCXB_KQ(SRC, R, D, M, A, S, G, Q) { SRC, R, D, sizeof(M) == 2, sizeof(M) == 4, sizeof(A) == 8, S, G, Q, false, photon_kernel<SRC, R, D, M, A, S, G, Q>, #SRC "/" #R "/det" #D "/" #M "/" #A "/" #G "/q" MCXB_STR(Q) }
+/* generic kernel with the extended physics, reflection x detector capture */
+#define MCXB_KX(R, D, M) { srcAny, R, D, sizeof(M) == 2, sizeof(M) == 4, true, false, true, 0, true, photon_kernel<srcAny, R, D, M, double, false, true, 0, true>, "srcAny/" #R "/det" #D "/" #M "/double/true/ext" }
+#define MCXB_RDX(M) MCXB_KX(false, 0, M), MCXB_KX(true, 0, M), MCXB_KX(false, 1, M), MCXB_KX(true, 1, M)
 #define MCXB_K(SRC, R, D, M, A, S, G) MCXB_KQ(SRC, R, D, M, A, S, G, 0)
 /* reflection x detector capture (0 = none, 1 = default record) */
 #define MCXB_RD(SRC, M, A, G) MCXB_K(SRC, false, 0, M, A, false, G), MCXB_K(SRC, true, 0, M, A, false, G), \
@@ -52,6 +57,10 @@ static const KernelEntry entries[] = {
     MCXB_RD(srcAny, uint16_t, double, true), MCXB_RD(srcAny, uint16_t, float, true), MCXB_K(srcAny, true, 1, uint16_t, double, true, true)
 #elif MCXB_INST_GROUP == 7
     MCXB_RD(srcAny, uint32_t, double, true), MCXB_RD(srcAny, uint32_t, float, true)
+#elif MCXB_INST_GROUP == 8
+    MCXB_RDX(uint8_t)
+#elif MCXB_INST_GROUP == 9
+    MCXB_RDX(uint16_t), MCXB_RDX(uint32_t)
 #endif
 };
 

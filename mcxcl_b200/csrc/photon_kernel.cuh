@@ -99,7 +99,16 @@ struct SimParam {
     uint32_t     widedep;         /* common kernels: bit 0 = more than one gate, bit 1 = one volume per source */
     uint32_t     acccopies;
     unsigned long long accstride; /* elements between two copies (= fieldlen) */
+    /* extended physics (EXT kernels only) */
+    const float4* smatrix;        /* polarised light: maxpolmedia x kNAngles rows {S11, S12, S33, S43} (src/mcx_core.cl:801-812), or NULL */
+    uint32_t     maxpolmedia;     /* media with a Mueller matrix (Config.polmedianum), 0 = unpolarised */
+    float        s0i, s0q, s0u, s0v;   /* Stokes vector of a fresh packet (Config.srciquv, :1633-1638) */
+    float        omega;           /* RF modulation angular frequency (Config.omega) */
+    uint32_t     rfforward;       /* omega > 0 in a forward run: complex packet weights (:2750-2763, 2833-2841) */
+    unsigned long long rfplane;   /* RF outputs: elements between the real and the imaginary volume (0 = no second plane) */
 };
+
+constexpr int kNAngles = 181;      /* NANGLES, src/mcx_const.h:67 */
 
 
 /* per-photon state that survives across segments */
@@ -582,7 +591,7 @@ static __device__ __noinline__ void save_traj(const SimParam& P, uint32_t id, fl
  * ------------------------------------------------------------------------------------------------- */
 __device__ __forceinline__ void save_detected(const SimParam& P, const float4* __restrict__ dets, const float* ppath,
         uint32_t pstride, const Photon& ph, uint32_t detarg, float w0init, int cursrc,
-        const unsigned long long* photonseed) {
+        const unsigned long long* photonseed, const float* stokes = nullptr) {
     int detid = 0;
 
     if (detarg == kOutsideMin) {
@@ -654,6 +663,36 @@ __device__ __forceinline__ void save_detected(const SimParam& P, const float4* _
     if (flag & 0x40u) {
         *rec++ = w0init;
     }
+
+    if ((flag & 0x80u) && stokes) {       /* SAVE_IQUV (:912-917) */
+        *rec++ = stokes[0];
+        *rec++ = stokes[1];
+        *rec++ = stokes[2];
+        *rec++ = stokes[3];
+    }
+}
+
+/* Stokes vector after a scattering event by polar angle theta and azimuth phi (updatestokes, src/mcx_core.cl:801-835):
+ * rotate into the scattering plane, apply the Mueller matrix row of this medium and angle, rotate into the new
+ * meridian plane, normalise to I = 1.  (ux,uy,uz) / (nx,ny,nz) = direction before / after the event. */
+__device__ __forceinline__ void update_stokes(float& sI, float& sQ, float& sU, float& sV, float theta, float phi, float uz, float nz,
+        const float4* __restrict__ sm, uint32_t label) {
+    float s2p, c2p;
+    __sincosf(2.f * phi, &s2p, &c2p);
+    const float costheta = __cosf(theta);
+    const float qi = sQ * c2p + sU * s2p, ui = -sQ * s2p + sU * c2p;
+    const float4 m = __ldg(sm + (size_t)kNAngles * (label - 1u) + (uint32_t)(theta * (float)kNAngles * (0.318309886183791f - kEps)));
+    const float i1 = m.x * sI + m.y * qi, q1 = m.y * sI + m.x * qi, u1 = m.z * ui + m.w * sV, v1 = -m.w * ui + m.z * sV;
+    const float temp = (nz > -1.f && nz < 1.f) ? fast_rsqrt((1.f - costheta * costheta) * (1.f - nz * nz)) : 0.f;
+    float cosi = (temp == 0.f) ? 0.f : (((phi > kOnePi && phi < kTwoPi) ? 1.f : -1.f) * (nz * costheta - uz) * temp);
+    cosi = fmaxf(-1.f, fminf(cosi, 1.f));
+    const float sini = fast_sqrt(1.f - cosi * cosi);
+    const float cos22 = 2.f * cosi * cosi - 1.f, sin22 = 2.f * sini * cosi;
+    const float inv = mufu_rcp(i1);
+    sI = 1.f;
+    sQ = (q1 * cos22 - u1 * sin22) * inv;
+    sU = (q1 * sin22 + u1 * cos22) * inv;
+    sV = v1 * inv;
 }
 
 /* ---------------------------------------------------------------------------------------------------
@@ -707,10 +746,11 @@ constexpr int kBlock = MCXB_BLOCK;
 constexpr int kQueueDepth = MCXB_QUEUE_DEPTH;
 static_assert(kQueueDepth > 0 && (kQueueDepth & (kQueueDepth - 1)) == 0, "queue depth must be a power of two");
 
-template <int SRC, bool REFLECT, int SAVEDET, typename MediaT, typename AccT, bool STATS, bool GEN, int QDEPTH = 0>
-__global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __grid_constant__ SimParam P) {
+template <int SRC, bool REFLECT, int SAVEDET, typename MediaT, typename AccT, bool STATS, bool GEN, int QDEPTH = 0, bool EXT = false>
+__global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kernel(const __grid_constant__ SimParam P) {
     extern __shared__ float4 smem[];
     static_assert(QDEPTH == 0 || (!GEN && SAVEDET < 2), "the scattering queue exists for the common-configuration kernels with the default record");
+    static_assert(!EXT || GEN, "the extended-physics kernels (polarised light, RF) are generic kernels");
     constexpr uint32_t QK = (uint32_t)QDEPTH;
     float4* const queue = smem + threadIdx.x;             /* entry j of this thread: queue[j * kBlock] */
     float4* tab = smem + QK * kBlock;                     /* optical properties, row 0 = background */
@@ -817,6 +857,9 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
     uint32_t patidx = 0;                              /* photon sharing: pattern cell the live packet was launched from */
     bool relaunch = true;
     uint32_t qs = 0;                                  /* scattering queue: events queued (low byte) + 256 x events ever pushed */
+    float sI = 1.f, sQ = 0.f, sU = 0.f, sV = 0.f;     /* EXT: Stokes vector of the live packet */
+    float wre = 0.f, wim = 0.f, w0re = 0.f, w0im = 0.f;   /* EXT, RF forward: complex weight now and at the last deposit; ph.w is its magnitude */
+    float rfcos = 1.f, rfsin = 0.f;                   /* EXT, RF replay: cos / sin of omega x detected time of flight of the replayed record */
     unsigned long long c_seg = 0, c_dep = 0, c_scat = 0;
 
     /* Retire the packet that just ended (if any) and launch the next one; returns true when this thread has nothing
@@ -843,7 +886,12 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
                 if (SAVEDET) {
                     if ((detarg & kDetMask) && ph.label == 0 && (!GEN || P.issaveref < 2)) {
-                        save_detected(P, dettab, ppath, kBlock, ph, detarg, w0init, GEN ? cursrc : (P.extrasrclen ? *srcslot : 0), photonseed);
+                        if (EXT) {
+                            const float st[4] = { sI, sQ, sU, sV };
+                            save_detected(P, dettab, ppath, kBlock, ph, detarg, w0init, cursrc, photonseed, st);
+                        } else {
+                            save_detected(P, dettab, ppath, kBlock, ph, detarg, w0init, GEN ? cursrc : (P.extrasrclen ? *srcslot : 0), photonseed);
+                        }
                     }
                 }
             }
@@ -1058,6 +1106,19 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             pacc = 0.f;
             qs &= ~0xFFu;        /* queued directions belonged to the previous packet */
 
+            if (EXT) {
+                sI = P.s0i;          /* :1633-1638 */
+                sQ = P.s0q;
+                sU = P.s0u;
+                sV = P.s0v;
+                wre = w0re = ph.w;   /* :2427-2430 */
+                wim = w0im = 0.f;
+
+                if (P.replayseed && (P.outputtype == otRF || P.outputtype == otRFmus)) {      /* :2257-2263 */
+                    __sincosf(P.omega * __ldg(P.replaytof + curid), &rfsin, &rfcos);
+                }
+            }
+
             if (GEN && P.trajdata) {          /* where the packet starts (:2243-2249) */
                 save_traj(P, curid + 1u, ph.px, ph.py, ph.pz, ph.w, cursrc);
             }
@@ -1150,12 +1211,36 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             {
                 float sphi = 0.f, cphi = 1.f, stheta, ctheta;
                 const bool flat = GEN && P.is2d;
+                const bool polar = EXT && P.maxpolmedia != 0u && !flat;
+                float theta = 0.f, phi = 0.f;
 
-                if (!flat) {
+                if (polar) {
+                    /* polarised light (:2454-2468): polar angle and azimuth drawn together by rejection against the
+                     * intensity the Mueller matrix of this medium scatters into that direction for the current Stokes vector */
+                    const float4* sm = P.smatrix + (size_t)kNAngles * (ph.label - 1u);
+                    const float4 m0 = __ldg(sm);
+                    float i0, i1;
+
+                    do {
+                        theta = acosf(2.f * rng_uniform(rng) - 1.f);
+                        phi = kTwoPi * rng_uniform(rng);
+                        float s2p, c2p;
+                        __sincosf(2.f * phi, &s2p, &c2p);
+                        const float4 m = __ldg(sm + (uint32_t)(theta * (float)kNAngles * (0.318309886183791f - kEps)));
+                        const float qq = sQ * c2p + sU * s2p;
+                        i0 = m0.x * sI + m0.y * qq;
+                        i1 = m.x * sI + m.y * qq;
+                    } while (rng_uniform(rng) * i0 >= i1);
+
+                    __sincosf(phi, &sphi, &cphi);
+                    __sincosf(theta, &stheta, &ctheta);
+                } else if (!flat) {
                     mufu_sincos(kTwoPi * rng_uniform(rng), sphi, cphi);
                 }
 
-                if (GEN && P.nphase > 2) {
+                if (polar) {
+                    /* angles are set */
+                } else if (GEN && P.nphase > 2) {
                     /* tabulated phase function: linear interpolation of the inverse CDF of cos(theta) */
                     float u = rng_uniform(rng) * (float)(P.nphase - 1);
                     const float fr = u - (float)(int)u;
@@ -1175,7 +1260,9 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     ctheta = (fabsf(gg) > kEps) ? chg : (2.f * u - 1.f);
                 }
 
-                stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
+                if (!polar) {
+                    stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
+                }
 
                 if (SAVEDET) {
                     const uint32_t flag = detflag;
@@ -1191,6 +1278,8 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     }
                 }
 
+                const float olduz = ph.vz;
+
                 if (flat) {
                     rotate_direction_2d(ph.vx, ph.vy, ph.vz, (rng_uniform(rng) > 0.5f ? stheta : -stheta), ctheta, (int)P.is2d);
                 } else {
@@ -1199,6 +1288,10 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
                 ph.nscat++;
 
+                if (polar) {
+                    update_stokes(sI, sQ, sU, sV, theta, phi, olduz, ph.vz, P.smatrix, ph.label);
+                }
+
                 if (GEN && P.trajdata) {      /* every scattering site (:2625-2632) */
                     save_traj(P, curid + 1u, ph.px, ph.py, ph.pz, ph.w, cursrc);
                 }
@@ -1206,14 +1299,18 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 /* scattering-site sensitivities of a replayed packet (:2567-2592): WP counts the events, DCS sums the
                  * momentum transfer 1-cos(theta), WPTOF weights the count by the time of flight; each scaled by the
                  * detected weight and binned by the DETECTED time of flight */
-                if (GEN && P.replayseed && (P.outputtype == otWP || P.outputtype == otDCS || P.outputtype == otWPTOF)) {
+                if (GEN && P.replayseed && (P.outputtype == otWP || P.outputtype == otDCS || P.outputtype == otWPTOF || (EXT && P.outputtype == otRFmus))) {
                     float sw = __ldg(P.replayweight + curid);
                     const float rtof = __ldg(P.replaytof + curid);
+                    float swim = 0.f;
 
                     if (P.outputtype == otDCS) {
                         sw *= 1.f - ctheta;
                     } else if (P.outputtype == otWPTOF) {
                         sw *= rtof;
+                    } else if (EXT && P.outputtype == otRFmus) {      /* :2572-2577: detected weight x cos / sin(omega tof) */
+                        swim = sw * rfsin;
+                        sw *= rfcos;
                     }
 
                     uint32_t tshift = (uint32_t)max(0, min((int)floorf((rtof - P.twin0) * P.Rtstep), (int)P.maxgate - 1));
@@ -1227,6 +1324,12 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     }
 
                     red_add(field + ((size_t)tshift * P.dimxyz + ph.idx1d), sw);
+
+                    if (EXT && P.outputtype == otRFmus) {
+                        /* imaginary part into the second plane, where the host reads it (src/mcx_host.cpp:1270-1276); the
+                         * reference's kernel adds it two planes further (:2601, 2617), outside the buffer its host allocates */
+                        red_add(field + (P.rfplane + (size_t)tshift * P.dimxyz + ph.idx1d), swim);
+                    }
                 }
 
                 if (STATS) {
@@ -1260,7 +1363,19 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
             ph.iy += (ph.face == 1) ? d : 0;
             ph.iz += (ph.face == 2) ? d : 0;
         }
-        ph.w *= mufu_ex2(mua * len * -1.4426950408889634f);
+        if (EXT && P.rfforward) {
+            /* RF forward (:2750-2763): w <- w exp[-(mua + i omega n / c0) ds]; the magnitude drives roulette and the energy ledger */
+            const float att = mufu_ex2(mua * len * -1.4426950408889634f);
+            float rs, rc;
+            __sincosf(P.omega * nmed * P.oneoverc0 * len, &rs, &rc);
+            const float tre = att * (wre * rc + wim * rs), tim = att * (-wre * rs + wim * rc);
+            wre = tre;
+            wim = tim;
+            ph.w = sqrtf(wre * wre + wim * wim);
+        } else {
+            ph.w *= mufu_ex2(mua * len * -1.4426950408889634f);
+        }
+
         ph.slen -= slen;
         ph.tof += len * nmed * P.oneoverc0;
 
@@ -1387,7 +1502,16 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                     tshift = (uint32_t)min((int)floorf((ph.tof - P.twin0) * P.Rtstep), (int)P.maxgate - 1);
                 }
 
-                if (GEN && P.outputtype == otEnergy) {
+                float weight_im = 0.f;       /* EXT: what goes into the second (imaginary) plane of an RF output */
+
+                if (EXT && P.rfforward) {
+                    /* RF forward (:2833-2841): (w0 - w) / (mua + i omega n / c0), a complex quotient */
+                    const float dre = w0re - wre, dim = w0im - wim;
+                    const float aim = P.omega * nmed * P.oneoverc0;
+                    const float amag2 = mua * mua + aim * aim;
+                    weight = (amag2 < kEps) ? (w0re * ph.pathlen) : (dre * mua + dim * aim) / amag2;
+                    weight_im = (amag2 < kEps) ? (w0im * ph.pathlen) : (dim * mua - dre * aim) / amag2;
+                } else if (GEN && P.outputtype == otEnergy) {
                     weight = ph.w0 - ph.w;
                 } else if (GEN && P.outputtype == otL) {
                     weight = ph.w0 * ph.pathlen;
@@ -1397,9 +1521,15 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                      * flight and, with replaydet == -1, by detector; WP / DCS / WPTOF deposit at scattering sites */
                     weight = 0.f;
 
-                    if (P.replayseed && (P.outputtype == otJacobian || P.outputtype == otWLTOF)) {
+                    if (P.replayseed && (P.outputtype == otJacobian || P.outputtype == otWLTOF || (EXT && P.outputtype == otRF))) {
                         const float rtof = __ldg(P.replaytof + curid);
                         weight = __ldg(P.replayweight + curid) * ph.pathlen * (P.outputtype == otWLTOF ? rtof : 1.f);
+
+                        if (EXT && P.outputtype == otRF) {       /* RF Jacobian (:2853-2855, 2895-2897): -w L {cos, sin}(omega tof) */
+                            weight_im = -weight * rfsin;
+                            weight = -weight * rfcos;
+                        }
+
                         tshift = (uint32_t)max(0, min((int)floorf((rtof - P.twin0) * P.Rtstep), (int)P.maxgate - 1));
 
                         if (P.replaydet == -1) {
@@ -1426,7 +1556,11 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                             red_add(dst + i, weight * wi);
                         }
                     }
-                } else if (fabsf(weight) > 0.f) {
+                } else if (fabsf(weight) > 0.f || (EXT && P.rfplane && fabsf(weight_im) > 0.f)) {
+                    if (EXT && P.rfplane) {
+                        red_add(static_cast<AccT*>(P.field) + (P.rfplane + (size_t)tshift * P.dimxyz + (oldidx + copyoff)), weight_im);
+                    }
+
 #if defined(MCXB_EXP_NODEPOSIT)
                     /* timing experiment only (tools/): what the kernel costs without its reductions */
                     if (weight == 123456.789f) {
@@ -1463,6 +1597,11 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
 
             ph.w0 = moved ? ph.w : ph.w0;
             ph.pathlen = moved ? 0.f : ph.pathlen;
+
+            if (EXT && moved) {
+                w0re = wre;
+                w0im = wim;
+            }
         }
 
         /* Everything below only has work to do for the few packets that changed medium (which includes leaving the
@@ -1520,6 +1659,13 @@ __global__ void __launch_bounds__(kBlock, MCXB_MINBLOCKS) photon_kernel(const __
                 if (fabsf(ph.w) < P.minenergy) {
                     if (rng_uniform(rng) * kRouletteSize <= 1.f) {
                         ph.w *= kRouletteSize;
+
+                        if (EXT) {       /* :3035-3040 */
+                            wre *= kRouletteSize;
+                            wim *= kRouletteSize;
+                            w0re *= kRouletteSize;
+                            w0im *= kRouletteSize;
+                        }
                     } else {
                         detarg = olddet;
                         relaunch = true;

@@ -216,6 +216,9 @@ def shape_field(p, field):
     if p.c.srcnum > 1:          # photon sharing: patterns interleaved fastest, pmcxcl returns (srcnum*Nx, Ny, Nz, Ng) (src/pmcxcl.cpp:1330)
         return field[:p.fieldlen].reshape((p.c.srcnum * nx, ny, nz, p.maxgate), order="F")
     shp = (nx, ny, nz, p.maxgate) + ((p.nrepvol,) if p.nrepvol > 1 else ()) + ((p.nsrcvol,) if p.nsrcvol > 1 else ())
+    if p.rfplanes == 2:         # RF outputs: real volumes, then imaginary volumes -> one complex array
+        half = p.fieldlen // 2
+        return (field[:half] + 1j * field[half:p.fieldlen]).astype(np.complex64).reshape(shp, order="F")
     return field[:p.fieldlen].reshape(shp, order="F")
 
 

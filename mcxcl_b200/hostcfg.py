@@ -18,9 +18,11 @@ from . import abi
 SRCTYPES = ["pencil", "isotropic", "cone", "gaussian", "planar", "pattern", "fourier", "arcsine", "disk",
             "fourierx", "fourierx2d", "zgaussian", "line", "slit", "pencilarray", "pattern3d", "hyperboloid", "ring"]
 # names of src/pmcxcl.cpp:854-872 (wl -> jacobian, wp -> nscat, wm = momentum transfer) and the -O letters of src/mcx_utils.c:143
-OUTPUTTYPES = {"flux": 0, "fluence": 1, "energy": 2, "jacobian": 3, "wl": 3, "nscat": 4, "wp": 4, "wm": 5, "length": 7, "wltof": 9, "wptof": 10,
-               "x": 0, "f": 1, "e": 2, "j": 3, "p": 4, "m": 5, "l": 7, "t": 9, "b": 10}
-REPLAY_OUTPUTS = (3, 4, 5, 9, 10)
+OUTPUTTYPES = {"flux": 0, "fluence": 1, "energy": 2, "jacobian": 3, "wl": 3, "nscat": 4, "wp": 4, "wm": 5, "rf": 6, "length": 7, "rfmus": 8,
+               "wltof": 9, "wptof": 10, "adjoint": 11, "adjointdcoeff": 12, "adjointmus": 13, "adjointmusp": 14, "adjointmuad": 15,
+               "adjointmuamusp": 16,
+               "x": 0, "f": 1, "e": 2, "j": 3, "p": 4, "m": 5, "r": 6, "l": 7, "s": 8, "t": 9, "b": 10}
+REPLAY_OUTPUTS = (3, 4, 5, 6, 8, 9, 10)
 SEED_FROM_FILE = -999        # src/mcx_const.h
 R_C0 = np.float32(3.335640951981520e-12)   # 1/c0 in s/mm
 BC_CODES = "_ramc"           # boundarycond[] (src/mcx_utils.c:170)
@@ -174,8 +176,14 @@ class Prepared:
         return max(1, self.c.detnum) if (bool(self.c.replay_seed) and self.c.replaydet == -1) else 1
 
     @property
+    def rfplanes(self):
+        # RF outputs are complex: real volumes, then imaginary volumes (src/pmcxcl.cpp:1209-1211)
+        replay = bool(self.c.replay_seed)
+        return 2 if ((self.c.omega > 0 and not replay) or (replay and self.c.outputtype in (6, 8))) else 1
+
+    @property
     def fieldlen(self):
-        return self.dimxyz * self.maxgate * self.nsrcvol * self.nrepvol
+        return self.dimxyz * self.maxgate * self.nsrcvol * self.nrepvol * self.rfplanes
 
     @property
     def partialdata(self):
@@ -459,7 +467,20 @@ def prepare(cfg):
         p.det_voxels = maskdet(flat, (nx, ny, nz), detpos)
     if c.issavedet and c.savedetflag == 0:
         c.savedetflag = 0x5
-    c.savedetflag &= ~0x80                  # no Stokes vector without polarised media
+    # polarised light: the Mueller-matrix tables mcx_prep_polarized (src/mcx_utils.c:1483-1519) would compute from `polprop`
+    # are taken as given here (cfg['smatrix']: polmedianum x 181 x 4), with prop[] already holding the matching mus / g
+    c.omega = float(cfg.get("omega", 0.0))
+    if cfg.get("smatrix") is not None:
+        sm = np.ascontiguousarray(np.asarray(cfg["smatrix"], dtype=np.float32).reshape(-1, abi.NANGLES, 4)).copy()
+        if sm.shape[0] + 1 != c.medianum:
+            raise ConfigError(-6, "number of polprop and prop is not consistent")            # src/mcx_utils.c:1540-1542
+        p.keep["smatrix"] = sm
+        c.polmedianum = sm.shape[0]
+        c.smatrix = sm.ctypes.data_as(C.POINTER(abi.F4))
+        iquv = _f4(cfg.get("srciquv", [1.0, 0.0, 0.0, 0.0]))      # default of mcx_initcfg (src/mcx_utils.c:338-339)
+        c.srciquv = abi.F4(*[float(t) for t in iquv])
+    else:
+        c.savedetflag &= ~0x80              # no Stokes vector without polarised media (src/mcx_utils.c:1777-1781)
     if c.issaveref > 1:
         raise ConfigError(-4, "issaveref > 1 is outside the hot path of this build")
 

@@ -31,6 +31,7 @@ typedef void (*ref_kernel_fn)(const unsigned int*, float*, float*, unsigned int*
 
 thread_local unsigned int* mcxref_jumpdebug = NULL;
 thread_local float* mcxref_debugdata = NULL;
+thread_local const void* mcxref_smatrix = NULL;      /* Mueller-matrix tables of a polarised run (gsmatrix, kernel argument 19) */
 
 #define REF_DECL(name) \
     extern "C" void mcxref_kernel_##name##_r0_d0(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*); \
@@ -121,6 +122,13 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     }
 
     const size_t fieldlen = (size_t)dimxyz * maxgate * nsrcvol * nrepvol;
+    /* RF outputs (src/mcx_host.cpp:473, 770, 1243-1276): a forward run with omega > 0 keeps real parts in [0,F) + shadow
+     * [F,2F) and imaginary parts in [2F,3F) + shadow [3F,4F); the RF replay Jacobian keeps real parts in [0,F) and imaginary
+     * parts in [F,2F).  The scattering-site form (otRFmus) writes its imaginary part at +2F like the forward run (:2601),
+     * which the reference's host neither allocates nor reads; this driver allocates 4F always and folds it from there. */
+    const bool rfforward = cfg->omega > 0.f && !replay;
+    const bool rfreplay = replay && (cfg->outputtype == 6 || cfg->outputtype == 8) && cfg->omega > 0.f;
+    const size_t planes = (rfforward || rfreplay) ? 2 : 1;
 
     const unsigned int flag = cfg->issavedet ? cfg->savedetflag : 0;
     const unsigned int partialdata = (cfg->medianum - 1) * (SAVE_NSCAT(flag) + SAVE_PPATH(flag) + SAVE_MOM(flag));
@@ -182,6 +190,10 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     param.gscatter = cfg->gscatter;
     param.is2d = is2d;
     param.srcnum = cfg->srcnum ? cfg->srcnum : 1;
+    param.maxpolmedia = cfg->smatrix ? cfg->polmedianum : 0;     /* src/mcx_host.cpp:522-523 */
+    param.istrajstokes = 0;
+    param.s0 = to_f4(cfg->srciquv);
+    param.omega = cfg->omega;
     /* inverse-CDF tables live at the head of the __local scratch (src/mcx_core.cl:2354-2383, src/mcx_host.cpp:1013) */
     param.nphase = cfg->invcdf ? cfg->nphase : 0;
     param.nphaselen = param.nphase + (param.nphase & 1);
@@ -251,7 +263,8 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     #pragma omp parallel num_threads(hostthreads)
     {
         const int tid = omp_get_thread_num();
-        tfield[tid].assign(fieldlen * 2, 0.f);
+        tfield[tid].assign(fieldlen * 4, 0.f);
+        mcxref_smatrix = cfg->smatrix;
 
         if (wanttraj) {
             /* every host thread records into its own buffer with its own counter (the kernel's atomic_inc, :930) */
@@ -301,28 +314,38 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
 
     /* fold shadow half and sum host threads (src/mcx_host.cpp:1252-1258, 1292-1296) */
     if (res->field) {
-        if (res->fieldlen < fieldlen) {
+        if (res->fieldlen < fieldlen * planes) {
             return -2;
         }
 
         for (size_t i = 0; i < fieldlen; i++) {
-            float acc = 0.f;
+            float acc = 0.f, acc_im = 0.f;
 
             for (int t = 0; t < hostthreads; t++) {
                 float v = tfield[t][i];
 
-                if (!(param.debuglevel & 1u)) {
+                if (!(param.debuglevel & 1u) && !(rfreplay && cfg->outputtype == 6)) {
                     v += tfield[t][i + fieldlen];
                 }
 
                 acc += v;
+
+                if (rfforward || (rfreplay && cfg->outputtype == 8)) {
+                    acc_im += tfield[t][i + 2 * fieldlen] + tfield[t][i + 3 * fieldlen];
+                } else if (rfreplay) {
+                    acc_im += tfield[t][i + fieldlen];
+                }
             }
 
             res->field[i] = acc;
+
+            if (planes == 2) {
+                res->field[i + fieldlen] = acc_im;
+            }
         }
     }
 
-    res->fieldlen = fieldlen;
+    res->fieldlen = fieldlen * planes;
 
     double etot = 0.0, eesc = 0.0;
 

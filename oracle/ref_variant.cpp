@@ -24,6 +24,7 @@ namespace REF_CAT(refk_, REF_SUFFIX) {
  * way so that the kernel wrappers keep one signature */
 extern thread_local unsigned int* mcxref_jumpdebug;
 extern thread_local float* mcxref_debugdata;
+extern thread_local const void* mcxref_smatrix;
 
 extern "C" void REF_CAT(mcxref_kernel_, REF_SUFFIX)(
     const unsigned int* media, float* field, float* genergy, unsigned int* n_seed,
@@ -36,6 +37,6 @@ extern "C" void REF_CAT(mcxref_kernel_, REF_SUFFIX)(
                   (const float4*)gdetpos, gprogress, detectedphoton,
                   replayweight, photontof, photondetid,
                   (RandType*)gseeddata, mcxref_jumpdebug, mcxref_debugdata,
-                  ginvcdf, gangleinvcdf, (RandType*)sharedmem, /*gsmatrix*/ NULL,
+                  ginvcdf, gangleinvcdf, (RandType*)sharedmem, (float4*)mcxref_smatrix,
                   (const MCXParam*)gcfg);
 }
