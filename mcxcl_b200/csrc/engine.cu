@@ -441,7 +441,8 @@ static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t npha
     const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
     return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->issaveref == 0 && !(cfg->debuglevel & (MCXB_DEBUG_MOVE | MCXB_DEBUG_MOVE_ONLY)) &&
            cfg->issave2pt != 0 && cfg->replay_seed == nullptr && cfg->srcnum <= 1 &&
-           (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE);
+           (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE ||
+            (cfg->outputtype >= MCXB_OT_ADJOINT && cfg->outputtype <= MCXB_OT_ADJOINT_MUA_MUSP));      /* adjoint types run as fluence */
 }
 
 /* the reference's rule for compiling the reflection code in (src/mcx_host.cpp:945-956) */

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from mcxcl_b200 import abi, benchmarks, engine, hostcfg
-from test_replay import replay_cfg, shift_records_for_the_reference
+from test_replay import replay_cfg
 
 OMEGA = 2 * np.pi * 100e6       # 100 MHz modulation
 
@@ -98,7 +98,7 @@ def test_gpu_polarised_run_matches_the_reference_source(ref):
         se = np.sqrt(so[:, k].var() / len(so) + sg[:, k].var() / len(sg)) + 1e-9
         assert abs(sg[:, k].mean() - so[:, k].mean()) < 5 * se, k
         assert sg[:, k].std() == pytest.approx(so[:, k].std(), rel=0.15, abs=0.01), k
-    assert abs(sg[:, 1].mean()) > 0.02              # the detected light IS partially polarised (otherwise the test says nothing)
+    assert np.abs(sg[:, 1:3]).mean() > 0.2          # the detected light IS partially polarised (otherwise the test says nothing)
     # fluence
     fg, fo = g["field"].astype(np.float64), o["field"].astype(np.float64) / (o["energytot"] * 5e-9)      # flux normalisation, src/mcx_host.cpp:1389-1391
     assert fg.sum() == pytest.approx(fo.sum(), rel=0.01)
@@ -139,11 +139,28 @@ def test_gpu_rf_forward_matches_the_reference_source(ref):
     assert abs(slow["field"][n:].astype(np.float64).sum()) < 1e-5 * plain["field"].astype(np.float64).sum()
 
 
+def test_reference_rf_replay_loses_its_phase_factors(ref):
+    """Why the RF replay outputs are NOT compared with the reference source: launchnewphoton advances its ppath pointer
+    by partialdata (src/mcx_core.cl:1620) and then stores cos / sin(omega tof) at ppath[w0offset + srcnum] (:2261-2262),
+    i.e. partialdata floats further than where the main loop reads them (:2573-2574, 2854, 2896) -- past this work-item's
+    shared-memory row.  A replay always carries partial paths (mcx_replayinit insists on the P flag), so the factors are
+    read as zero and the reference's RF Jacobian is empty; the absorption Jacobian of the same records is not."""
+    cfg = dict(benchmarks.get("cube60", 50000), issaveseed=1, savedetflag="DSPM")
+    base = ref.run(hostcfg.prepare(cfg), 1024, hostthreads=0)
+    assert base["detected"] > 50
+    jac = ref.run(hostcfg.prepare(replay_cfg(cfg, base["detp"], base["seeds"], outputtype="jacobian", isnormalized=0)), 1, hostthreads=0)
+    rf = ref.run(hostcfg.prepare(replay_cfg(cfg, base["detp"], base["seeds"], outputtype="rf", isnormalized=0, omega=OMEGA)), 1, hostthreads=0)
+    assert jac["field"].sum() > 0 and not rf["field"].any()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("ot", ["rf", "rfmus"])
-def test_gpu_rf_replay_matches_the_reference_source(ref, ot):
-    """RF Jacobians of a replay: the SAME records replayed by the reference source and by the CUDA kernel, plus the
-    identities  sum(Re) = -sum_i w_i L_i cos(omega t_i)  (rf)  /  sum_i w_i nscat_i cos(omega t_i)  (rfmus)"""
+def test_gpu_rf_replay_satisfies_the_identities(ot):
+    """RF Jacobians of a replay (src/mcx_core.cl:2257-2263, 2572-2577, 2853-2855, 2895-2897), photon by photon:
+        rf:     sum(Re) = -sum_i w_i L_i cos(omega t_i),   sum(Im) = -sum_i w_i L_i sin(omega t_i)
+        rfmus:  sum(Re) =  sum_i w_i nscat_i cos(omega t_i), sum(Im) = sum_i w_i nscat_i sin(omega t_i)
+    and voxel by voxel the rf output is the absorption Jacobian of the same records with every photon's deposits scaled by
+    -cos / -sin(omega t_i) (checked with a replay of ONE photon at a time for a few photons)"""
     cfg = dict(benchmarks.get("cube60", 300000), issaveseed=1, savedetflag="DSPM")
     base = engine.run_prepared(hostcfg.prepare(cfg))
     n = min(1500, base["detected"])
@@ -153,8 +170,9 @@ def test_gpu_rf_replay_matches_the_reference_source(ref, ot):
     g = engine.run_prepared(p)["field"].astype(np.float64)
     w, tof = p.keep["replay_weight"].astype(np.float64), p.keep["replay_tof"].astype(np.float64)
     d = base["detp"][:n][p.keep["replay_index"]]
-    nscat = np.ascontiguousarray(d[:, 1:2]).view(np.uint32).astype(np.float64)[:, 0]
-    plen = d[:, 2].astype(np.float64)
+    M = p.c.medianum - 1                   # record: detector id, M scattering counts (uint32 bits), M partial paths, M momentum transfers
+    nscat = np.ascontiguousarray(d[:, 1:1 + M]).view(np.uint32).astype(np.float64).sum(axis=1)
+    plen = d[:, 1 + M:1 + 2 * M].astype(np.float64).sum(axis=1)
     F = 216000
     if ot == "rf":
         assert g[:F].sum() == pytest.approx(-(w * plen * np.cos(OMEGA * tof)).sum(), rel=1e-3)
@@ -162,13 +180,18 @@ def test_gpu_rf_replay_matches_the_reference_source(ref, ot):
     else:
         assert g[:F].sum() == pytest.approx((w * nscat * np.cos(OMEGA * tof)).sum(), rel=1e-3)
         assert g[F:].sum() == pytest.approx((w * nscat * np.sin(OMEGA * tof)).sum(), rel=1e-3)
-    po = hostcfg.prepare(rc)
-    if ot == "rfmus":
-        shift_records_for_the_reference(po)       # the scattering-site outputs of the reference read record i+1 (tests/test_replay.py)
-    o = ref.run(po, 1, hostthreads=0)["field"].astype(np.float64)
-    for part in (slice(0, F), slice(F, 2 * F)):
-        assert g[part].sum() == pytest.approx(o[part].sum(), rel=5e-3)
-        assert np.corrcoef(g[part], o[part])[0, 1] > 0.98
+    base_ot = "jacobian" if ot == "rf" else "wp"
+    sign = -1.0 if ot == "rf" else 1.0
+    for i in (0, 7, 19):
+        one = dict(rc, seed=rc["seed"][:, i:i + 1], detphotons=rc["detphotons"][:, i:i + 1])
+        pj = hostcfg.prepare(dict(one, outputtype=base_ot))
+        if pj.c.nphoton == 0:
+            continue
+        j = engine.run_prepared(pj)["field"].astype(np.float64)
+        r = engine.run_prepared(hostcfg.prepare(one))["field"].astype(np.float64)
+        t = float(pj.keep["replay_tof"][0])
+        np.testing.assert_allclose(r[:F], sign * j * np.cos(OMEGA * t), rtol=2e-3, atol=1e-7 * np.abs(j).max())
+        np.testing.assert_allclose(r[F:], sign * j * np.sin(OMEGA * t), rtol=2e-3, atol=1e-7 * np.abs(j).max())
 
 
 def numpy_adjoint(re, im, dims, maxgate, ns, nd, gradient):
@@ -223,10 +246,11 @@ def test_gpu_adjoint_run_is_a_fluence_run_over_sources_and_detectors():
     """an adjoint output type runs the forward kernel as a fluence run with one volume per source (src/mcx_core.cl:2844,
     src/mcx_host.cpp:1389-1394); the products of the source and detector volumes are the Jacobian"""
     cfg = dict(benchmarks.get("cube60", 200000), issavedet=0, srcpos=[[30, 30, 1, 1], [30, 40, 1, 1]], srcdir=[[0, 0, 1, 0], [0, 0, 1, 0]],
-               srcid=-1, tstep=2.5e-9)
+               srcid=-1, tstep=2.5e-9, sched=1)         # static photon split: the same packets walk in both runs
     a = engine.run_prepared(hostcfg.prepare(dict(cfg, outputtype="adjoint")))
     f = engine.run_prepared(hostcfg.prepare(dict(cfg, outputtype="fluence")))
-    assert a["field"].size == 216000 * 2 * 2 and np.array_equal(a["field"], f["field"])
+    assert a["field"].size == 216000 * 2 * 2 and a["field"].sum() > 0
+    np.testing.assert_allclose(a["field"], f["field"], rtol=1e-5, atol=1e-6 * float(f["field"].max()))
     out = np.zeros(216000, np.float32)
     abi.check(abi.load().mcxb_adjoint_products(0, a["field"].ctypes.data, None, 60, 60, 60, 2, 1, 1, 0, out.ctypes.data))
     v = a["field"].astype(np.float64).reshape(2, 2, 216000).sum(axis=1)
