@@ -19,8 +19,8 @@ SRCTYPES = ["pencil", "isotropic", "cone", "gaussian", "planar", "pattern", "fou
             "fourierx", "fourierx2d", "zgaussian", "line", "slit", "pencilarray", "pattern3d", "hyperboloid", "ring"]
 # names of src/pmcxcl.cpp:854-872 (wl -> jacobian, wp -> nscat, wm = momentum transfer) and the -O letters of src/mcx_utils.c:143
 OUTPUTTYPES = {"flux": 0, "fluence": 1, "energy": 2, "jacobian": 3, "wl": 3, "nscat": 4, "wp": 4, "wm": 5, "rf": 6, "length": 7, "rfmus": 8,
-               "wltof": 9, "wptof": 10, "adjoint": 11, "adjointdcoeff": 12, "adjointmus": 13, "adjointmusp": 14, "adjointmuad": 15,
-               "adjointmuamusp": 16,
+               "wltof": 9, "wptof": 10, "adjoint": 11, "adjoint_dcoeff": 12, "adjoint_mus": 13, "adjoint_musp": 14, "adjoint_mua_d": 15,
+               "adjoint_mua_musp": 16,
                "x": 0, "f": 1, "e": 2, "j": 3, "p": 4, "m": 5, "r": 6, "l": 7, "s": 8, "t": 9, "b": 10}
 REPLAY_OUTPUTS = (3, 4, 5, 6, 8, 9, 10)
 SEED_FROM_FILE = -999        # src/mcx_const.h
@@ -479,6 +479,8 @@ def prepare(cfg):
         c.smatrix = sm.ctypes.data_as(C.POINTER(abi.F4))
         iquv = _f4(cfg.get("srciquv", [1.0, 0.0, 0.0, 0.0]))      # default of mcx_initcfg (src/mcx_utils.c:338-339)
         c.srciquv = abi.F4(*[float(t) for t in iquv])
+        if c.issavedet:
+            c.savedetflag |= 0x04 | 0x20 | 0x40 | 0x80       # P, V, W, I are forced in polarised runs (src/mcx_utils.c:1777-1781)
     else:
         c.savedetflag &= ~0x80              # no Stokes vector without polarised media (src/mcx_utils.c:1777-1781)
     if c.issaveref > 1:

@@ -126,3 +126,60 @@ def test_replay_through_the_unchanged_front_end():
     np.testing.assert_allclose(jac.astype(np.float64).sum(), mine.astype(np.float64).sum(), rtol=1e-5)
     w = np.exp(-0.005 * detp[1] - 0.002 * detp[2])
     np.testing.assert_allclose(jac.astype(np.float64).sum(), float((w * (detp[1] + detp[2])).sum() / w.sum()), rtol=2e-3)
+
+
+@pytest.mark.gpu
+def test_rf_forward_through_the_unchanged_front_end():
+    """cfg['omega'] > 0 (src/pmcxcl.cpp:469): pmcxcl allocates two volume sets and returns a complex flux (:1209-1211,
+    1339-1400); the phase lag grows with depth and a vanishing frequency gives back the real run"""
+    m = load_module()
+    om = 2 * np.pi * 100e6
+    res = m.run(cube60(isreflect=1, issavedet=0, nphoton=500000, omega=om))
+    flux = res["flux"]
+    assert np.iscomplexobj(flux) and flux.shape[:3] == (60, 60, 60)
+    mine = engine.run(cube60(isreflect=1, issavedet=0, nphoton=500000, omega=om))["flux"]
+    axis_a, axis_b = flux.reshape(60, 60, 60, -1)[29, 29, 1:25, 0], mine[29, 29, 1:25, 0]
+    np.testing.assert_allclose(np.abs(axis_a), np.abs(axis_b), rtol=0.12)
+    assert np.max(np.abs(np.angle(axis_a / axis_b))) < 0.05
+    ph = np.unwrap(np.angle(axis_a))
+    assert ph[0] < 0 and ph[-1] < ph[0] - 0.2                           # lagging, and more so deeper in
+    assert abs(res["stat"]["energyabs"] / res["stat"]["energytot"] - 0.2701) < 0.005
+
+
+@pytest.mark.gpu
+def test_adjoint_jacobian_through_the_unchanged_front_end():
+    """outputtype 'adjoint' (src/pmcxcl.cpp:854-872, 1179-1198, 1414-1490): detectors are appended as sources, one fluence
+    volume per source / detector, and 'jmua' = -Vvox x phi_src x phi_det per voxel (src/mcx_host.cpp:1468-1641)"""
+    m = load_module()
+    cfg = cube60(isreflect=0, nphoton=300000, detpos=[[29, 39, 0, 1]], detdir=[[0, 0, 1, 0]], outputtype="adjoint", issavedet=0)
+    res = m.run(cfg)
+    assert "jmua" in res and res["jmua"].shape == (60, 60, 60, 1)
+    flux = np.asarray(res["flux"], dtype=np.float64).reshape((60, 60, 60, -1), order="F")
+    assert flux.shape[-1] == 2                                          # {source, detector-as-source}
+    want = -flux[..., 0] * flux[..., 1]                                 # Vvox = 1 mm^3, one gate
+    got = res["jmua"][..., 0].astype(np.float64)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-12)
+    assert (got < 0).sum() > 10000                                      # a banana between the two optodes, not an empty volume
+    both = m.run(dict(cfg, outputtype="adjoint_mua_d"))
+    assert "jmua" in both and "jd" in both and both["jd"].shape == (60, 60, 60, 1)
+    vols = np.asarray(both["flux"], dtype=np.float64).reshape((60, 60, 60, -1), order="F")
+    g0, g1 = np.gradient(vols[..., 0], edge_order=2), np.gradient(vols[..., 1], edge_order=2)
+    dot = sum(a * b for a, b in zip(g0, g1))                            # second-order differences, like mcx_fd_grad
+    np.testing.assert_allclose(both["jd"][..., 0].astype(np.float64), -dot, rtol=2e-3, atol=1e-6 * np.abs(dot).max())
+
+
+@pytest.mark.gpu
+def test_polarised_run_through_the_unchanged_front_end():
+    """cfg['polprop'] + cfg['lambda'] (src/pmcxcl.cpp:754-800, 470): the front-end's own Mie code fills prop and the Mueller
+    matrices (mcx_prep_polarized, src/mcx_utils.c:1483-1519); savedetflag 'i' appends the Stokes vector (src/mcx_core.cl:912-917)"""
+    m = load_module()
+    cfg = cube60(isreflect=1, nphoton=500000, prop=[[0, 0, 1, 1], [0.005, 1, 0.01, 1.37]], polprop=[[0.005, 0.05, 19.11, 1.59, 1.33]],
+                 savedetflag="dpi", srciquv=[1, 1, 0, 0])
+    cfg["lambda"] = 632.8
+    res = m.run(cfg)
+    detp = res["detp"]
+    assert detp.shape[0] == 1 + 1 + 3 + 1 + 4 and detp.shape[1] > 300   # D, P, and -- forced for polarised runs (src/mcx_utils.c:1777-1781) -- V, W, I
+    s = detp[-4:]
+    assert np.all(s[0] == 1.0) and np.all(np.abs(s[1:]) <= 1.0 + 1e-4) and np.abs(s[1:3]).mean() > 0.05
+    st = res["stat"]
+    assert 0.05 < st["energyabs"] / st["energytot"] < 0.9 and abs(st["energytot"] - 5e5) <= 10
