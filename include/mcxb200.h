@@ -72,7 +72,7 @@ enum mcxb_outputtype { MCXB_OT_FLUX = 0, MCXB_OT_FLUENCE = 1, MCXB_OT_ENERGY = 2
 #define MCXB_NANGLES 181             /* NANGLES: rows of one Mueller matrix table (src/mcx_const.h:67) */
 
 /* boundary codes: TBoundary (src/mcx_utils.h:65) */
-enum mcxb_mediaformat { MCXB_MEDIA_LABEL_HALF = 99, MCXB_MEDIA_AS_F2H = 100, MCXB_MEDIA_MUA_FLOAT = 101, MCXB_MEDIA_AS_HALF = 102,
+enum mcxb_mediaformat { MCXB_MEDIA_2LABEL_SPLIT = 97, MCXB_MEDIA_LABEL_HALF = 99, MCXB_MEDIA_AS_F2H = 100, MCXB_MEDIA_MUA_FLOAT = 101, MCXB_MEDIA_AS_HALF = 102,
                         MCXB_MEDIA_ASGN_BYTE = 103, MCXB_MEDIA_AS_SHORT = 104
                       };
 
@@ -111,8 +111,12 @@ typedef struct mcxb_config {
      * segment like updateproperty (src/mcx_core.cl:1079-1193): 99 MEDIA_LABEL_HALF {half value, 2-bit slot, 14-bit
      * label}, 100 MEDIA_AS_F2H / 102 MEDIA_AS_HALF {half mua, half mus}, 101 MEDIA_MUA_FLOAT {float mua},
      * 103 MEDIA_ASGN_BYTE {mua, mus, g, n as bytes between prop[1] and prop[2]}, 104 MEDIA_AS_SHORT {mua, mus as
-     * shorts between prop[1] and prop[2]}.  (97 SVMC is not part of this build; 96 two-word and 98 mixed-label media are
-     * formats no front-end of the reference can produce / its kernel has no decoder for.) */
+     * shorts between prop[1] and prop[2]}.
+     * 97 MEDIA_2LABEL_SPLIT (split-voxel Monte Carlo, src/mcx_core.cl:1231-1344): vol holds TWO words per voxel, first
+     * dimxyz words {lower label << 24 | upper label << 16 | px << 8 | py}, then dimxyz words {pz << 24 | nx << 16 | ny << 8 |
+     * nz}, as mcx_preprocess leaves them (src/mcx_utils.c:1688-1712): a plane through (px, py, pz) / 255 inside the voxel
+     * with normal (nx, ny, nz) * 2 / 255 - 1 separates the lower from the upper tissue; upper label 0 = ordinary voxel.
+     * (96 two-word and 98 mixed-label media are formats no front-end of the reference produces / its kernel does not decode.) */
     uint32_t mediaformat;
 
     /* ---- media table: Config.prop / medianum ({mua,mus,g,n}, row 0 = background) ---- */

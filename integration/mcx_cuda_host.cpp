@@ -73,7 +73,7 @@ void fill_config(const Config* cfg, mcxb_config* c) {
     c->dimz = cfg->dim.z;
     c->vol = cfg->vol;
     c->unitinmm = cfg->unitinmm;
-    c->mediaformat = cfg->mediabyte;       /* <= 4: label media; 99..104: the continuous formats packed by the front-end */
+    c->mediaformat = cfg->mediabyte;       /* <= 4: label media; 99..104: the continuous formats packed by the front-end; 97: split-voxel media, two words per voxel */
     c->medianum = cfg->medianum;
     c->prop = reinterpret_cast<const mcxb_f4*>(cfg->prop);          /* Medium {mua,mus,g,n}, 16 bytes */
     c->srctype = cfg->srctype;
@@ -156,8 +156,8 @@ unsigned int record_length(const Config* cfg) {
 
 /* what this build's hot path does not cover is refused loudly, never approximated */
 void check_supported(const Config* cfg) {
-    if (cfg->mediabyte > 4 && (cfg->mediabyte < MEDIA_LABEL_HALF || cfg->mediabyte > MEDIA_AS_SHORT)) {
-        mcx_error(-1, "SVMC, mixed-label and two-word media formats are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
+    if (cfg->mediabyte > 4 && (cfg->mediabyte < MEDIA_LABEL_HALF || cfg->mediabyte > MEDIA_AS_SHORT) && cfg->mediabyte != MEDIA_2LABEL_SPLIT) {
+        mcx_error(-1, "mixed-label and two-word media formats are outside the photon-transport path of the CUDA engine", __FILE__, __LINE__);
     }
 
     if (cfg->seed == SEED_FROM_FILE && cfg->replay.seed == NULL) {

@@ -750,6 +750,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     /* complex packet weights: a modulation frequency in a forward run (src/mcx_host.cpp:473) */
     const bool rfforward = cfg->omega > 0.f && !cfg->replay_seed;
     const bool polarized = cfg->polmedianum > 0;
+    const bool svmc = cfg->mediaformat == MCXB_MEDIA_2LABEL_SPLIT;
 
     if (adjoint_ot && cfg->replay_seed) {
         return fail(MCXB_ERR_ARG, "the adjoint output types are forward runs");
@@ -862,7 +863,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->rfplanes = ((rfforward || (rf_ot && cfg->replay_seed)) && !s->rngdebug) ? 2u : 1u;
     s->planelen = dimxyz * maxgate * nsrcvol * s->nrepvol;
     s->fieldlen = s->planelen * s->rfplanes;
-    s->ext = (rfforward || rf_ot || polarized) && !s->rngdebug;
+    s->ext = (rfforward || rf_ot || polarized || svmc) && !s->rngdebug;
     const bool savedet = cfg->issavedet != 0 && !s->rngdebug;
     /* the I flag (Stokes vector of a detected photon) exists in polarised runs only (src/mcx_utils.c:1777-1781) */
     const uint32_t flag = savedet ? (cfg->savedetflag & (polarized ? 0xFFu : 0x7Fu)) : 0u;
@@ -876,8 +877,24 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     if (continuous) {
         const uint32_t f = cfg->mediaformat;
 
-        if (f < MCXB_MEDIA_LABEL_HALF || f > MCXB_MEDIA_AS_SHORT) {
-            return fail(MCXB_ERR_ARG, "media format %u (two-word, SVMC or mixed-label media) is outside this build's hot path", f);
+        if ((f < MCXB_MEDIA_LABEL_HALF || f > MCXB_MEDIA_AS_SHORT) && f != MCXB_MEDIA_2LABEL_SPLIT) {
+            return fail(MCXB_ERR_ARG, "media format %u (two-word or mixed-label media) is outside this build's hot path", f);
+        }
+
+        if (svmc) {
+            /* split-voxel media: two words per voxel, labels in the two top bytes of the first (src/mcx_utils.c:1688-1712) */
+            for (uint64_t i = 0; i < dimxyz; i++) {
+                const uint32_t w = cfg->vol[i] & 0x7FFFFFFFu;
+
+                if ((w >> 24) >= cfg->medianum || ((w >> 16) & 0xFFu) >= cfg->medianum) {
+                    return fail(MCXB_ERR_ARG, "input media optical properties are less than the labels in the volume");
+                }
+            }
+
+            if (cfg->isspecular > 0) {
+                /* the reference indexes its media table with the whole media word there (src/mcx_core.cl:1428-1433) */
+                return fail(MCXB_ERR_ARG, "isspecular is not available with split-voxel media");
+            }
         }
 
         /* src/mcx_utils.c:1760-1766 */
@@ -889,7 +906,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
             return fail(MCXB_ERR_ARG, "the 'prop' field must contain at least 3 rows for the requested media format");
         }
 
-        if (cfg->issavedet && (cfg->savedetflag & 0x0Eu) && !(cfg->debuglevel & 1u)) {
+        if (!svmc && cfg->issavedet && (cfg->savedetflag & 0x0Eu) && !(cfg->debuglevel & 1u)) {
             /* the reference indexes its per-medium rows with the media word itself there (src/mcx_core.cl:2515, 2787) */
             return fail(MCXB_ERR_ARG, "per-medium detector records (savedetflag S, P, M) need label media; use savedetflag 'dxvw' or issavedet=0 with continuous media");
         }
@@ -899,8 +916,9 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         }
 
         s->media32 = true;
-        CU_TRY(dev_alloc(&s->d_media, device, 4 * dimxyz));
-        CU_TRY(cudaMemcpy(s->d_media, cfg->vol, 4 * dimxyz, cudaMemcpyHostToDevice));
+        const uint64_t words = svmc ? 2 * dimxyz : dimxyz;
+        CU_TRY(dev_alloc(&s->d_media, device, 4 * words));
+        CU_TRY(cudaMemcpy(s->d_media, cfg->vol, 4 * words, cudaMemcpyHostToDevice));
     }
 
     /* ---- media volume: labels packed to 8 (or 16) bits with the detector flag in the top bit ---- */
@@ -1063,7 +1081,10 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->acc64 = cfg->accum != MCXB_ACCUM_F32;
     const bool refl = needs_reflection(cfg);
     const bool stats = (cfg->debuglevel & MCXB_DEBUG_STATS) != 0;
-    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32 && !s->ext;
+    /* adjoint runs (and srcid == -2) launch the detectors appended to the source list as disks (src/mcx_core.cl:2154-2183):
+     * that code lives in the generic kernels */
+    const bool detsources = (adjoint_ot || cfg->srcid == -2) && cfg->detnum > 0 && cfg->extrasrclen >= cfg->detnum;
+    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32 && !s->ext && !detsources;
     const int detmode = savedet ? (flag == 0x5u ? 1 : 2) : 0;
     /* Scattering queue (photon_kernel.cuh): pays where a packet crosses several voxels per scattering event.  Measured on
      * B200: +8..10 % at mus = 1 per voxel (cube60 / cube60b), +20 % at mus <= 0.2 (skinvessel), -9..-12 % at mus = 8..40
@@ -1322,6 +1343,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     P.omega = cfg->omega;
     P.rfforward = rfforward ? 1u : 0u;
     P.rfplane = (s->rfplanes == 2) ? s->planelen : 0ull;
+    P.adjfirstdet = detsources ? (cfg->extrasrclen + 1 - cfg->detnum) : 0xFFFFFFFFu;
 
     if (getenv("MCXB_DEBUG_PTRS")) {
         fprintf(stderr, "mcxb buffers: media %p field %p field32 %p tables %p seeds %p det %p detcount %p counter %p energy %p\n",

@@ -106,6 +106,7 @@ struct SimParam {
     float        omega;           /* RF modulation angular frequency (Config.omega) */
     uint32_t     rfforward;       /* omega > 0 in a forward run: complex packet weights (:2750-2763, 2833-2841) */
     unsigned long long rfplane;   /* RF outputs: elements between the real and the imaginary volume (0 = no second plane) */
+    uint32_t     adjfirstdet;     /* adjoint runs / srcid == -2: sources with an id above this are detectors launched as disks (:2154-2183); else 0xFFFFFFFF */
 };
 
 constexpr int kNAngles = 181;      /* NANGLES, src/mcx_const.h:67 */
@@ -571,6 +572,79 @@ __device__ __forceinline__ void sample_source(const SimParam& P, const float4* _
     }
 }
 
+/* ---------------------------------------------------------------------------------------------------
+ * split-voxel media (SVMC, MED_TYPE 97 = MEDIA_2LABEL_SPLIT, src/mcx_core.cl:1231-1344).  Two words per voxel:
+ *   media[idx]          = lower label << 24 | upper label << 16 | px << 8 | py      (bit 31: detector flag)
+ *   media[idx + dimxyz] = pz << 24 | nx << 16 | ny << 8 | nz
+ * an oriented plane through the point (px, py, pz) / 255 inside the voxel with normal (nx, ny, nz) * 2/255 - 1 splits the
+ * voxel into a "lower" and an "upper" (the side the normal points to) tissue; upper label 0 = an ordinary voxel.
+ * The state keeps the plane oriented TOWARDS the other side of the packet, so only rays with v.n > 0 can hit it.
+ * ------------------------------------------------------------------------------------------------- */
+struct SplitVoxel {
+    float nx, ny, nz, pd;      /* plane n.x = pd (nuvox.nv, nuvox.pd) */
+    uint32_t sv;               /* bits 0-7 lower label, 8-15 upper label, 16 split, 17 packet is in the upper part (:577-587) */
+};
+__device__ __forceinline__ uint32_t sv_lower(uint32_t sv) {
+    return sv & 0xFFu;
+}
+__device__ __forceinline__ uint32_t sv_upper(uint32_t sv) {
+    return (sv >> 8) & 0xFFu;
+}
+__device__ __forceinline__ uint32_t sv_label(uint32_t sv) {
+    return (sv & 0x20000u) ? sv_upper(sv) : sv_lower(sv);
+}
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+
+/* updateproperty_svmc (:1231-1278): properties of the part of voxel idx1d the point p lies in, and the plane state */
+__device__ __forceinline__ float4 svmc_update(const SimParam& P, const float4* __restrict__ tab, uint32_t word, uint32_t idx1d, float px, float py,
+        float pz, int ix, int iy, int iz, SplitVoxel& nu) {
+    if (idx1d == kOutsideMin || idx1d == kOutsideMax) {
+        return tab[0];          /* the plane state is left as it was (:1235-1238) */
+    }
+
+    const uint32_t lo = __ldg(static_cast<const uint32_t*>(P.media) + idx1d + P.dimxyz);
+    const uint32_t hi = word & 0x7FFFFFFFu;
+    uint32_t sv = (hi >> 24) | (((hi >> 16) & 0xFFu) << 8);
+
+    if ((hi >> 16) & 0xFFu) {
+        const float rx = __fadd_rn(__fmul_rn((float)((hi >> 8) & 0xFFu), 1.f / 255.f), (float)ix);
+        const float ry = __fadd_rn(__fmul_rn((float)(hi & 0xFFu), 1.f / 255.f), (float)iy);
+        const float rz = __fadd_rn(__fmul_rn((float)(lo >> 24), 1.f / 255.f), (float)iz);
+        float nx = __fsub_rn(__fmul_rn((float)((lo >> 16) & 0xFFu), 2.f / 255.f), 1.f);
+        float ny = __fsub_rn(__fmul_rn((float)((lo >> 8) & 0xFFu), 2.f / 255.f), 1.f);
+        float nz = __fsub_rn(__fmul_rn((float)(lo & 0xFFu), 2.f / 255.f), 1.f);
+        const float r = rsqrtf(dot3_rn(nx, ny, nz, nx, ny, nz));
+        nx = __fmul_rn(nx, r);
+        ny = __fmul_rn(ny, r);
+        nz = __fmul_rn(nz, r);
+        float pd = dot3_rn(rx, ry, rz, nx, ny, nz);
+        float4 pr;
+
+        if (dot3_rn(px, py, pz, nx, ny, nz) > pd) {
+            pr = tab[sv_upper(sv)];
+            sv |= 0x20000u;
+            nx = -nx;
+            ny = -ny;
+            nz = -nz;
+            pd = -pd;
+        } else {
+            pr = tab[sv_lower(sv)];
+        }
+
+        nu.nx = nx;
+        nu.ny = ny;
+        nu.nz = nz;
+        nu.pd = pd;
+        nu.sv = sv | 0x10000u;
+        return pr;
+    }
+
+    nu.sv = sv & 0xFFFFu;       /* an ordinary voxel; the plane coefficients keep their last values */
+    return tab[hi >> 24];
+}
+
 /* one trajectory record (savedebugdata, src/mcx_core.cl:929-948): {photon id, x, y, z, weight, source id} */
 static __device__ __noinline__ void save_traj(const SimParam& P, uint32_t id, float x, float y, float z, float w, int srcid) {
     const uint32_t pos = atomicAdd(P.trajcount, 1u);
@@ -860,6 +934,11 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
     float sI = 1.f, sQ = 0.f, sU = 0.f, sV = 0.f;     /* EXT: Stokes vector of the live packet */
     float wre = 0.f, wim = 0.f, w0re = 0.f, w0im = 0.f;   /* EXT, RF forward: complex weight now and at the last deposit; ph.w is its magnitude */
     float rfcos = 1.f, rfsin = 0.f;                   /* EXT, RF replay: cos / sin of omega x detected time of flight of the replayed record */
+    /* EXT, split-voxel media (MED_TYPE 97): the plane of the current voxel as seen from the packet's side, whether the next
+     * segment has to be tested against it, and whether the last segment ended on it */
+    const bool svmc = EXT && sizeof(MediaT) == 4 && P.mediaformat == 97u;
+    SplitVoxel nu = { 0.f, 0.f, 0.f, 0.f, 0u };
+    bool testint = true, hitintf = false;
     unsigned long long c_seg = 0, c_dep = 0, c_scat = 0;
 
     /* Retire the packet that just ended (if any) and launch the next one; returns true when this thread has nothing
@@ -885,7 +964,7 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
                 }
 
                 if (SAVEDET) {
-                    if ((detarg & kDetMask) && ph.label == 0 && (!GEN || P.issaveref < 2)) {
+                    if ((detarg & kDetMask) && (ph.label == 0 || (svmc && sv_label(nu.sv) == 0u)) && (!GEN || P.issaveref < 2)) {      /* :1555-1561 */
                         if (EXT) {
                             const float st[4] = { sI, sQ, sU, sV };
                             save_detected(P, dettab, ppath, kBlock, ph, detarg, w0init, cursrc, photonseed, st);
@@ -1061,6 +1140,28 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
                     }
                 }
 
+                if (GEN && P.adjfirstdet != 0xFFFFFFFFu && (uint32_t)((P.extrasrclen & (P.srcid < 0 ? 1u : 0u)) ? cursrc : 0) > P.adjfirstdet) {
+                    /* adjoint runs: a detector is launched as a disk of its radius around its position, perpendicular to
+                     * its direction (:2154-2183).  The reference takes the source id from `extrasrclen & (srcid < 0)`, a
+                     * bitwise AND: with an even number of extra sources detectors launch as plain points -- kept */
+                    float sphi, cphi;
+                    __sincosf(kTwoPi * rng_uniform(rng), &sphi, &cphi);
+                    const float rad = fast_sqrt(rng_uniform(rng)) * S[2].x;
+
+                    if (ph.vz > -1.f + kEps && ph.vz < 1.f - kEps) {
+                        const float t0 = 1.f - ph.vz * ph.vz;
+                        const float t1 = rad * fast_rsqrt(t0);
+                        ph.px += t1 * (ph.vx * ph.vz * cphi - ph.vy * sphi);
+                        ph.py += t1 * (ph.vy * ph.vz * cphi + ph.vx * sphi);
+                        ph.pz -= t1 * t0 * cphi;
+                    } else {
+                        ph.px += rad * cphi;
+                        ph.py += rad * sphi;
+                    }
+
+                    locate<MediaT>(P, ph, rawlabel, rawdet);
+                }
+
                 if (rawlabel == 0) {
                     /* the marcher takes the packet by reference and is not inlined: hand it a copy so that the
                      * live packet state never has its address taken and stays in registers */
@@ -1093,7 +1194,16 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
             budget--;
             ph.label = rawlabel;
             ph.detflag = rawdet;
-            nmed = medium<MediaT>(P, tab, ph.label).w;
+
+            if (svmc) {          /* :1640-1642, 2217 */
+                nu.sv = 0u;
+                nmed = svmc_update(P, tab, ph.label, ph.idx1d, ph.px, ph.py, ph.pz, ph.ix, ph.iy, ph.iz, nu).w;
+                testint = true;
+                hitintf = false;
+            } else {
+                nmed = medium<MediaT>(P, tab, ph.label).w;
+            }
+
             e_launched += ph.w;
             ph.w0 = ph.w;
             w0init = ph.w;
@@ -1207,6 +1317,7 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
             }
         } else if (ph.slen <= 0.f) {
             ph.slen = rng_scatlen(rng);
+            testint = true;          /* SVMC: a new direction may hit the plane again (:2638-2648) */
 
             {
                 float sphi = 0.f, cphi = 1.f, stheta, ctheta;
@@ -1267,14 +1378,16 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
                 if (SAVEDET) {
                     const uint32_t flag = detflag;
                     const uint32_t M = P.medianum - 1;
+                    /* the row of the tissue the event happened in: the label, or the current part of a split voxel (:2503-2531) */
+                    const uint32_t row = svmc ? sv_label(nu.sv) : ph.label;
 
-                    if (flag & 0x02u) {
-                        uint32_t* cnt = reinterpret_cast<uint32_t*>(ppath + (ph.label - 1) * kBlock);
+                    if ((flag & 0x02u) && row) {
+                        uint32_t* cnt = reinterpret_cast<uint32_t*>(ppath + (row - 1) * kBlock);
                         *cnt += 1u;
                     }
 
-                    if (flag & 0x08u) {
-                        ppath[(M * ((flag >> 1 & 1u) + (flag >> 2 & 1u)) + ph.label - 1) * kBlock] += 1.f - ctheta;
+                    if ((flag & 0x08u) && row) {
+                        ppath[(M * ((flag >> 1 & 1u) + (flag >> 2 & 1u)) + row - 1) * kBlock] += 1.f - ctheta;
                     }
                 }
 
@@ -1341,7 +1454,8 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
         /* ------------------------------------------------------------------ one ray segment (:2652-2765) */
         ph.n1 = nmed;
         {
-            const float4 pr = medium<MediaT>(P, tab, ph.label);
+            /* SVMC re-derives the part of the voxel from the position in every iteration (:2666-2669) */
+            const float4 pr = svmc ? svmc_update(P, tab, ph.label, ph.idx1d, ph.px, ph.py, ph.pz, ph.ix, ph.iy, ph.iz, nu) : medium<MediaT>(P, tab, ph.label);
             mua = pr.x;
             mus = pr.y;
             g = pr.z;
@@ -1350,7 +1464,29 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
         const float dist = face_distance(ph.px, ph.py, ph.pz, ph.vx, ph.vy, ph.vz, ph.ix, ph.iy, ph.iz, ph.face);
         const float musp = (GEN && (uint32_t)(ph.nscat + 1) > P.gscatter) ? __fmul_rn(mus, __fsub_rn(1.f, g)) : mus;
         float slen;
-        const float len = step_length(dist, musp, ph.slen, slen);
+        float len = step_length(dist, musp, ph.slen, slen);
+
+        if (EXT) {
+            hitintf = false;
+
+            if (svmc && (nu.sv & 0x10000u) && testint) {
+                /* ray_plane_intersect (:1280-1300): the segment ends on the plane if it would cross it */
+                const float vdotn = dot3_rn(ph.vx, ph.vy, ph.vz, nu.nx, nu.ny, nu.nz);
+
+                if (vdotn > 0.f) {
+                    const float d0 = __fsub_rn(dot3_rn(ph.px, ph.py, ph.pz, nu.nx, nu.ny, nu.nz), nu.pd);
+                    const float d1 = __fadd_rn(d0, __fmul_rn(len, vdotn));
+
+                    if (!(__fmul_rn(d0, d1) > 0.f)) {
+                        const float len0 = __fdiv_rn(__fmul_rn(len, d0), __fsub_rn(d0, d1));
+                        len = (len0 > 0.f) ? len0 : len;
+                        slen = __fmul_rn(len, musp);
+                        hitintf = true;
+                    }
+                }
+            }
+        }
+
         ph.pathlen += len;
         ph.px = advance(ph.px, len, ph.vx);
         ph.py = advance(ph.py, len, ph.vy);
@@ -1358,7 +1494,7 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
         {
             /* reached the face before the scattering site: step into the neighbour across that face */
             const float vf = (ph.face == 0) ? ph.vx : ((ph.face == 1) ? ph.vy : ph.vz);
-            const int d = (slen != ph.slen) ? ((vf > 0.f) ? 1 : -1) : 0;
+            const int d = (slen != ph.slen && !(EXT && hitintf)) ? ((vf > 0.f) ? 1 : -1) : 0;
             ph.ix += (ph.face == 0) ? d : 0;
             ph.iy += (ph.face == 1) ? d : 0;
             ph.iz += (ph.face == 2) ? d : 0;
@@ -1384,7 +1520,15 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
         }
 
         if (SAVEDET) {
-            pacc += len;     /* moved to the partial-path row of this medium when the packet leaves it (below) */
+            if (svmc) {      /* split voxels: straight into the row of the current part (:2778-2782) */
+                const uint32_t row = sv_label(nu.sv);
+
+                if ((detflag & 0x04u) && row) {
+                    ppath_len[row * kBlock] += len;
+                }
+            } else {
+                pacc += len;     /* moved to the partial-path row of this medium when the packet leaves it (below) */
+            }
         }
 
         /* ------------------------------------------------------------------ new voxel (:2796-2811) */
@@ -1491,7 +1635,8 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
         } else
 #endif
         {
-            const bool moved = ph.idx1d != oldidx;
+            /* a segment that ended on the plane of a split voxel deposits like one that ended on a face (:2816-2825) */
+            const bool moved = ph.idx1d != oldidx || (EXT && hitintf);
 
             if (moved && oldlabel && (!GEN || P.save2pt) && ph.tof >= P.twin0 && ph.tof < P.twin1) {
                 float weight;
@@ -1604,16 +1749,33 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
             }
         }
 
+        float4 svprop = make_float4(0.f, 0.f, 0.f, 0.f);      /* SVMC: properties on the far side of the face just crossed */
+
+        if (svmc) {
+            /* :2931-2949: a new voxel is looked up at the packet's position; a crossed plane swaps the two parts */
+            if (ph.idx1d != oldidx) {
+                svprop = svmc_update(P, tab, ph.label, ph.idx1d, ph.px, ph.py, ph.pz, ph.ix, ph.iy, ph.iz, nu);
+                testint = true;
+            } else if (hitintf) {
+                nu.nx = -nu.nx;
+                nu.ny = -nu.ny;
+                nu.nz = -nu.nz;
+                nu.pd = -nu.pd;
+                nu.sv ^= 0x20000u;
+                testint = false;
+            }
+        }
+
         /* Everything below only has work to do for the few packets that changed medium (which includes leaving the
          * grid), ran out of time or fell below the roulette threshold: one test keeps the other lanes out of it.
          * (With the label unchanged n1 == n of the current medium, so the index-mismatch block is a no-op, and
          * boundary codes are only ever attached to a label-0 step out of the grid.) */
         /* (!(|w| >= minenergy) instead of |w| < minenergy: identical for numbers, and true for the NaN weight of the dummy
          * packet every thread starts with when the launch code lives in this block) */
-        if (ph.label != oldlabel || ph.tof > P.twin1 || !(fabsf(ph.w) >= P.minenergy)) {
+        if (ph.label != oldlabel || ph.tof > P.twin1 || !(fabsf(ph.w) >= P.minenergy) || (svmc && (ph.idx1d != oldidx || hitintf || ph.n1 != nmed))) {
             qs &= ~0xFFu;        /* the medium (g) or the direction may change below: queued events no longer apply */
 
-            if (SAVEDET) {
+            if (SAVEDET && !svmc) {
                 if (ph.label != oldlabel) {
                     if ((detflag & 0x04u) && oldlabel) {
                         ppath_len[oldlabel * kBlock] += pacc;
@@ -1626,8 +1788,11 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
             /* ------------------------------------------------------------------ leave / time out (:2957-3028) */
             const uint32_t bcode = ph.detflag & 0xFu;
 
+            /* SVMC (:2962-2966): the packet stepped into the empty lower part of a voxel (through a face or through the plane) */
+            const bool svexit = svmc && (ph.idx1d != oldidx || hitintf) && !(nu.sv & 0x20000u) && sv_lower(nu.sv) == 0u && (!P.doreflect || ph.n1 == n0);
+
             if ((ph.label == 0 && (bcode == bcAbsorb || (GEN && bcode == bcCyclic) || (bcode == bcReflect && ph.n1 == n0))) || ph.tof > P.twin1 ||
-                    (kLaunchInTail && ph.w != ph.w)) {
+                    (kLaunchInTail && ph.w != ph.w) || svexit) {
                 bool reentered = false;
 
                 if (GEN && ph.detflag == bcCyclic) {
@@ -1673,8 +1838,66 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
                 }
 
                 /* -------------------------------------------------------------- index mismatch (:3063-3297) */
-                if (REFLECT && !relaunch) {
-                    const float n2 = (ph.label == oldlabel) ? nmed : medium<MediaT>(P, tab, ph.label).w;
+                if (REFLECT && !relaunch && svmc && hitintf) {
+                    /* ---------------------------------------------------------- the plane inside a split voxel (:3074-3111) */
+                    const float nlo = tab[sv_lower(nu.sv)].w, nup = tab[sv_upper(nu.sv)].w;
+
+                    if (nlo != nup) {
+                        /* reflectray_svmc (:1302-1343), with the normal turned back towards the side the packet came from */
+                        nu.nx = -nu.nx;
+                        nu.ny = -nu.ny;
+                        nu.nz = -nu.nz;
+                        nu.pd = -nu.pd;
+                        const float icos = fabsf(dot3_rn(ph.vx, ph.vy, ph.vz, nu.nx, nu.ny, nu.nz));
+                        const float n2 = (nu.sv & 0x20000u) ? nup : nlo;
+                        const float t0 = ph.n1 * ph.n1, t1 = n2 * n2;
+                        float t2 = 1.f - t0 / t1 * (1.f - icos * icos);
+                        bool reflected = true;
+
+                        if (t2 > 0.f) {
+                            float re = t0 * icos * icos + t1 * t2;
+                            t2 = sqrtf(t2);
+                            const float im = 2.f * ph.n1 * n2 * icos * t2;
+                            float rtot = (re - im) / (re + im);
+                            re = t1 * icos * icos + t0 * t2 * t2;
+                            rtot = (rtot + (re - im) / (re + im)) * 0.5f;
+                            reflected = rng_uniform(rng) <= rtot;
+                        }
+
+                        if (reflected) {
+                            ph.vx += -2.f * icos * nu.nx;
+                            ph.vy += -2.f * icos * nu.ny;
+                            ph.vz += -2.f * icos * nu.nz;
+                            nu.sv ^= 0x20000u;          /* back in the part it came from */
+                        } else {
+                            const float r = ph.n1 / n2;
+                            ph.vx = t2 * nu.nx + r * (ph.vx - icos * nu.nx);
+                            ph.vy = t2 * nu.ny + r * (ph.vy - icos * nu.ny);
+                            ph.vz = t2 * nu.nz + r * (ph.vz - icos * nu.nz);
+                            nu.nx = -nu.nx;
+                            nu.ny = -nu.ny;
+                            nu.nz = -nu.nz;
+                            nu.pd = -nu.pd;
+
+                            if (sv_label(nu.sv) == 0u) {
+                                detarg = olddet;       /* refracted into the empty part of the voxel: the packet leaves (:3083-3103) */
+                                relaunch = true;
+                            } else {
+                                nmed = tab[sv_label(nu.sv)].w;
+                            }
+                        }
+
+                        const float rn = rsqrtf(ph.vx * ph.vx + ph.vy * ph.vy + ph.vz * ph.vz);
+                        ph.vx *= rn;
+                        ph.vy *= rn;
+                        ph.vz *= rn;
+                    } else {
+                        nmed = tab[sv_label(nu.sv)].w;
+                    }
+                } else if (REFLECT && !relaunch) {
+                    /* SVMC compares with the properties looked up on the far side of the face (:2936-2941, 3143-3147) */
+                    const float n2 = svmc ? ((ph.idx1d != oldidx) ? svprop.w : nmed)
+                                     : ((ph.label == oldlabel) ? nmed : medium<MediaT>(P, tab, ph.label).w);
                     const bool mirror = GEN && bcode == bcMirror;
                     bool handle = false;
 
@@ -1720,6 +1943,16 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
                             ph.label = oldlabel;
                             ph.detflag = olddet;
                             nmed = ph.n1;
+
+                            if (svmc) {
+                                /* back in the old voxel: which part of it? (:3218-3221); the empty part ends the packet */
+                                nmed = svmc_update(P, tab, ph.label, ph.idx1d, ph.px, ph.py, ph.pz, ph.ix, ph.iy, ph.iz, nu).w;
+
+                                if (sv_label(nu.sv) == 0u) {
+                                    detarg = olddet;
+                                    relaunch = true;
+                                }
+                            }
                         }
                     } else {
                         nmed = n2;

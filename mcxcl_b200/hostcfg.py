@@ -83,7 +83,7 @@ def parse_bc(bc):
     return codes
 
 
-def maskdet(vol, dims, detpos):
+def maskdet(vol, dims, detpos, svmc=False):
     """Flag the surface voxels covered by each detector sphere in bit 31 (mcx_maskdet).
 
     vol: uint32[dimxyz] x-fastest (modified in place); returns the per-detector voxel counts.
@@ -131,7 +131,13 @@ def maskdet(vol, dims, detpos):
                     if mind2 is None or mind2 >= lim:
                         continue
                     pz, py, px = int(iz + f32(1)), int(iy + f32(1)), int(ix + f32(1))
-                    if pad[pz, py, px]:
+                    if svmc:
+                        # split-voxel media (src/mcx_utils.c:4157-4168): a split voxel whose lower part is empty
+                        w = int(pad[pz, py, px])
+                        if not (w >> 24) & 0x7F and (w >> 16) & 0xFF:
+                            vol3[int(iz), int(iy), int(ix)] |= np.uint32(DET_MASK)
+                            count += 1
+                    elif pad[pz, py, px]:
                         if not all(pad[pz + a, py + b, px + c2] for a, b, c2 in nb):
                             vol3[int(iz), int(iy), int(ix)] |= np.uint32(DET_MASK)
                             count += 1
@@ -214,6 +220,7 @@ class Prepared:
 
 
 MEDIA_LABEL_HALF, MEDIA_AS_F2H, MEDIA_MUA_FLOAT, MEDIA_AS_HALF, MEDIA_ASGN_BYTE, MEDIA_AS_SHORT = 99, 100, 101, 102, 103, 104
+MEDIA_2LABEL_SPLIT = 97
 
 
 def _float_to_half_bits(f):
@@ -241,6 +248,13 @@ def pack_continuous_volume(vol, unitinmm=1.0):
         raise ConfigError(-4, "a continuous-media volume is 4-D: (component, x, y, z)")
     ch = v.shape[0]
     u = np.float32(unitinmm)
+    if v.dtype in (np.int8, np.uint8) and ch == 8:
+        # split-voxel media (src/pmcxcl.cpp:123-134 + mcx_preprocess, src/mcx_utils.c:1688-1712): the 8 bytes of a voxel are
+        # {lower label, upper label, px, py, pz, nx, ny, nz}; two planes of words come out, (2, x, y, z)
+        b = v.astype(np.uint8).astype(np.uint32)
+        hi = (b[0] << 24) | (b[1] << 16) | (b[2] << 8) | b[3]
+        lo = (b[4] << 24) | (b[5] << 16) | (b[6] << 8) | b[7]
+        return np.stack([hi, lo]), MEDIA_2LABEL_SPLIT
     if v.dtype in (np.int8, np.uint8) and ch == 4:
         b = v.astype(np.uint8).astype(np.uint32)
         return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24), MEDIA_ASGN_BYTE
@@ -288,12 +302,17 @@ def prepare(cfg):
     c.mediaformat = int(cfg.get("mediaformat", 0))          # explicit format code with already packed uint32 words
     if vol.ndim == 4:
         vol, c.mediaformat = pack_continuous_volume(vol, float(cfg.get("unitinmm", 1.0)))
+    second = None
+    if c.mediaformat == MEDIA_2LABEL_SPLIT and vol.ndim == 4:
+        vol, second = vol[0], vol[1]
     if vol.ndim != 3:
         raise ConfigError(-4, "the 'vol' field must be a 3D array of labels or a 4D array of optical properties")
     if vol.size == 0:
         raise ConfigError(-4, "the 'vol' field in the input structure can not be empty")
     nx, ny, nz = vol.shape
     flat = np.ascontiguousarray(vol.astype(np.uint32, copy=False).ravel(order="F")).copy()
+    if second is not None:      # the second word of every voxel follows the dimxyz first words (src/mcx_utils.c:1706-1707)
+        flat = np.concatenate([flat, np.ascontiguousarray(second.astype(np.uint32, copy=False).ravel(order="F"))])
     c.dimx, c.dimy, c.dimz = nx, ny, nz
 
     prop = np.array(cfg["prop"], dtype=np.float32).reshape(-1, 4).copy()
@@ -464,7 +483,7 @@ def prepare(cfg):
             srcp2[i, 2:4] = np.array([idx, lab], dtype=np.uint32).view(np.float32)
 
     if c.issavedet:
-        p.det_voxels = maskdet(flat, (nx, ny, nz), detpos)
+        p.det_voxels = maskdet(flat[:nx * ny * nz], (nx, ny, nz), detpos, svmc=(c.mediaformat == MEDIA_2LABEL_SPLIT))
     if c.issavedet and c.savedetflag == 0:
         c.savedetflag = 0x5
     # polarised light: the Mueller-matrix tables mcx_prep_polarized (src/mcx_utils.c:1483-1519) would compute from `polprop`

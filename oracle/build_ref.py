@@ -32,7 +32,7 @@ SOURCES = [
 # what the reference passes at its default optlevel for label media with atomics on
 # (src/mcx_host.cpp:857-891), minus USE_MACRO_CONST so gcfg-> fields are read from the struct
 BASEFLAGS = ["-DMED_TYPE=1", "-DUSE_ATOMIC", "-DMCX_USE_NATIVE"]
-MEDIA_FORMATS = [99, 100, 101, 102, 103, 104]        # MEDIA_LABEL_HALF .. MEDIA_AS_SHORT (src/mcx_const.h:59-64)
+MEDIA_FORMATS = [97, 99, 100, 101, 102, 103, 104]    # MEDIA_2LABEL_SPLIT (SVMC), MEDIA_LABEL_HALF .. MEDIA_AS_SHORT (src/mcx_const.h:57-64)
 CXX = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fpermissive", "-w", "-fPIC", "-fopenmp", "-x", "c++"]
 
 PATCHES = [

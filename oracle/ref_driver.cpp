@@ -51,15 +51,15 @@ static const ref_kernel_fn ref_kernels[18][4] = {
     REF_ROW(line), REF_ROW(slit), REF_ROW(pencilarray), REF_ROW(pattern3d), REF_ROW(hyperboloid), REF_ROW(ring)
 };
 
-/* continuous-media builds of the pencil-source kernel (-DMED_TYPE=99..104), [format - 99][reflect + 2*savedet] */
+/* continuous-media and split-voxel builds of the pencil-source kernel (-DMED_TYPE=99..104, 97), [format - 99 | 6][reflect + 2*savedet] */
 #define REF_MDECL(m) \
     extern "C" void mcxref_kernel_pencil_m##m##_r0_d0(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*); \
     extern "C" void mcxref_kernel_pencil_m##m##_r1_d0(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*); \
     extern "C" void mcxref_kernel_pencil_m##m##_r0_d1(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*); \
     extern "C" void mcxref_kernel_pencil_m##m##_r1_d1(const unsigned int*, float*, float*, unsigned int*, float*, const void*, float*, const void*, volatile unsigned int*, unsigned int*, unsigned long*, float*, float*, void*, const void*, float*, float*, int*);
 #define REF_MROW(m) { mcxref_kernel_pencil_m##m##_r0_d0, mcxref_kernel_pencil_m##m##_r1_d0, mcxref_kernel_pencil_m##m##_r0_d1, mcxref_kernel_pencil_m##m##_r1_d1 }
-REF_MDECL(99) REF_MDECL(100) REF_MDECL(101) REF_MDECL(102) REF_MDECL(103) REF_MDECL(104)
-static const ref_kernel_fn ref_media_kernels[6][4] = { REF_MROW(99), REF_MROW(100), REF_MROW(101), REF_MROW(102), REF_MROW(103), REF_MROW(104) };
+REF_MDECL(97) REF_MDECL(99) REF_MDECL(100) REF_MDECL(101) REF_MDECL(102) REF_MDECL(103) REF_MDECL(104)
+static const ref_kernel_fn ref_media_kernels[7][4] = { REF_MROW(99), REF_MROW(100), REF_MROW(101), REF_MROW(102), REF_MROW(103), REF_MROW(104), REF_MROW(97) };
 
 static inline float4 to_f4(const mcxb_f4& a) {
     return float4(a.x, a.y, a.z, a.w);
@@ -234,11 +234,11 @@ extern "C" int mcxref_run(const mcxb_config* cfg, uint32_t nthread, int hostthre
     ref_kernel_fn kern = ref_kernels[cfg->srctype][(ref_needs_reflection(cfg) ? 1 : 0) + (cfg->issavedet ? 2 : 0)];
 
     if (cfg->mediaformat > 4) {
-        if (cfg->mediaformat < 99 || cfg->mediaformat > 104 || cfg->srctype != 0) {
-            return -3;      /* only the pencil-source builds of MED_TYPE 99..104 exist */
+        if (((cfg->mediaformat < 99 || cfg->mediaformat > 104) && cfg->mediaformat != 97) || cfg->srctype != 0) {
+            return -3;      /* only the pencil-source builds of MED_TYPE 97 and 99..104 exist */
         }
 
-        kern = ref_media_kernels[cfg->mediaformat - 99][(ref_needs_reflection(cfg) ? 1 : 0) + (cfg->issavedet ? 2 : 0)];
+        kern = ref_media_kernels[cfg->mediaformat == 97 ? 6 : cfg->mediaformat - 99][(ref_needs_reflection(cfg) ? 1 : 0) + (cfg->issavedet ? 2 : 0)];
     }
 
 

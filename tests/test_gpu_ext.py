@@ -246,7 +246,7 @@ def test_gpu_adjoint_run_is_a_fluence_run_over_sources_and_detectors():
     """an adjoint output type runs the forward kernel as a fluence run with one volume per source (src/mcx_core.cl:2844,
     src/mcx_host.cpp:1389-1394); the products of the source and detector volumes are the Jacobian"""
     cfg = dict(benchmarks.get("cube60", 200000), issavedet=0, srcpos=[[30, 30, 1, 1], [30, 40, 1, 1]], srcdir=[[0, 0, 1, 0], [0, 0, 1, 0]],
-               srcid=-1, tstep=2.5e-9, sched=1)         # static photon split: the same packets walk in both runs
+               srcid=-1, tstep=2.5e-9, sched=1)         # static photon split: the same packets walk in both runs (no detectors: both in the common kernels)
     a = engine.run_prepared(hostcfg.prepare(dict(cfg, outputtype="adjoint")))
     f = engine.run_prepared(hostcfg.prepare(dict(cfg, outputtype="fluence")))
     assert a["field"].size == 216000 * 2 * 2 and a["field"].sum() > 0
@@ -255,3 +255,27 @@ def test_gpu_adjoint_run_is_a_fluence_run_over_sources_and_detectors():
     abi.check(abi.load().mcxb_adjoint_products(0, a["field"].ctypes.data, None, 60, 60, 60, 2, 1, 1, 0, out.ctypes.data))
     v = a["field"].astype(np.float64).reshape(2, 2, 216000).sum(axis=1)
     np.testing.assert_allclose(out, v[0] * v[1], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_adjoint_launches_detectors_as_disks_like_the_reference(ref):
+    """adjoint forward run (src/mcx_core.cl:2154-2183): the sources appended for the detectors start from a disk of the
+    detector's radius, perpendicular to its direction; compared with the reference source on the detector's volume"""
+    cfg = dict(benchmarks.get("cube60", 500000), issavedet=0, srcpos=[[30, 30, 1, 1], [30, 42, 1, 1]], srcdir=[[0, 0, 1, 0], [0, 0, 1, 0]],
+               srcparam1=[[0, 0, 0, 0], [4, 0, 0, 0]], detpos=[[30, 42, 1, 4]], srcid=-1, outputtype="adjoint", isnormalized=0)
+    p = hostcfg.prepare(cfg)
+    assert p.c.extrasrclen == 1 and p.c.detnum == 1 and p.nsrcvol == 2
+    g = engine.run_prepared(p)["field"].astype(np.float64).reshape(2, 60, 60, 60)
+    o = ref.run(hostcfg.prepare(dict(cfg, nphoton=200000)), 2048, hostthreads=0)["field"].astype(np.float64).reshape(2, 60, 60, 60)
+    g, o = g / 5e5, o / 2e5
+    for k in (0, 1):
+        assert g[k].sum() == pytest.approx(o[k].sum(), rel=0.02)
+    # the entry layer of the detector volume: a disk of radius 4 voxels, not a point
+    lg, lo = g[1, 0], o[1, 0]
+    yy, xx = np.mgrid[0:60, 0:60]
+    disk = (xx + 0.5 - 29) ** 2 + (yy + 0.5 - 41) ** 2 < 16
+    assert lg[disk].sum() / lg.sum() == pytest.approx(lo[disk].sum() / lo.sum(), abs=0.02)
+    assert lg[41, 29] / lg.sum() == pytest.approx(lo[41, 29] / lo.sum(), rel=0.2)
+    # while the true source stays a pencil beam: its entry voxel holds several times the share the disk's centre voxel holds
+    assert g[0, 0, 29, 29] / g[0, 0].sum() == pytest.approx(o[0, 0, 29, 29] / o[0, 0].sum(), rel=0.1)
+    assert g[0, 0, 29, 29] / g[0, 0].sum() > 2.5 * lg[41, 29] / lg.sum()
