@@ -863,7 +863,9 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->rfplanes = ((rfforward || (rf_ot && cfg->replay_seed)) && !s->rngdebug) ? 2u : 1u;
     s->planelen = dimxyz * maxgate * nsrcvol * s->nrepvol;
     s->fieldlen = s->planelen * s->rfplanes;
-    s->ext = (rfforward || rf_ot || polarized || svmc) && !s->rngdebug;
+    /* adjoint runs (and srcid == -2) launch the detectors appended to the source list as disks (src/mcx_core.cl:2154-2183) */
+    const bool detsources = (adjoint_ot || cfg->srcid == -2) && cfg->detnum > 0 && cfg->extrasrclen >= cfg->detnum;
+    s->ext = (rfforward || rf_ot || polarized || svmc || detsources) && !s->rngdebug;
     const bool savedet = cfg->issavedet != 0 && !s->rngdebug;
     /* the I flag (Stokes vector of a detected photon) exists in polarised runs only (src/mcx_utils.c:1777-1781) */
     const uint32_t flag = savedet ? (cfg->savedetflag & (polarized ? 0xFFu : 0x7Fu)) : 0u;
@@ -1081,10 +1083,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->acc64 = cfg->accum != MCXB_ACCUM_F32;
     const bool refl = needs_reflection(cfg);
     const bool stats = (cfg->debuglevel & MCXB_DEBUG_STATS) != 0;
-    /* adjoint runs (and srcid == -2) launch the detectors appended to the source list as disks (src/mcx_core.cl:2154-2183):
-     * that code lives in the generic kernels */
-    const bool detsources = (adjoint_ot || cfg->srcid == -2) && cfg->detnum > 0 && cfg->extrasrclen >= cfg->detnum;
-    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32 && !s->ext && !detsources;
+    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32 && !s->ext;
     const int detmode = savedet ? (flag == 0x5u ? 1 : 2) : 0;
     /* Scattering queue (photon_kernel.cuh): pays where a packet crosses several voxels per scattering event.  Measured on
      * B200: +8..10 % at mus = 1 per voxel (cube60 / cube60b), +20 % at mus <= 0.2 (skinvessel), -9..-12 % at mus = 8..40

@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
                     }
                 }
 
-                if (GEN && P.adjfirstdet != 0xFFFFFFFFu && (uint32_t)((P.extrasrclen & (P.srcid < 0 ? 1u : 0u)) ? cursrc : 0) > P.adjfirstdet) {
+                if (EXT && P.adjfirstdet != 0xFFFFFFFFu && (uint32_t)((P.extrasrclen & (P.srcid < 0 ? 1u : 0u)) ? cursrc : 0) > P.adjfirstdet) {
                     /* adjoint runs: a detector is launched as a disk of its radius around its position, perpendicular to
                      * its direction (:2154-2183).  The reference takes the source id from `extrasrclen & (srcid < 0)`, a
                      * bitwise AND: with an even number of extra sources detectors launch as plain points -- kept */
@@ -1381,12 +1381,12 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
                     /* the row of the tissue the event happened in: the label, or the current part of a split voxel (:2503-2531) */
                     const uint32_t row = svmc ? sv_label(nu.sv) : ph.label;
 
-                    if ((flag & 0x02u) && row) {
+                    if ((flag & 0x02u) && (!svmc || row)) {
                         uint32_t* cnt = reinterpret_cast<uint32_t*>(ppath + (row - 1) * kBlock);
                         *cnt += 1u;
                     }
 
-                    if ((flag & 0x08u) && row) {
+                    if ((flag & 0x08u) && (!svmc || row)) {
                         ppath[(M * ((flag >> 1 & 1u) + (flag >> 2 & 1u)) + row - 1) * kBlock] += 1.f - ctheta;
                     }
                 }
