@@ -127,6 +127,18 @@ def combine(sim, dist, rank, world, device):
     return combine_tensors(dist, rank, world, field, energy, mine, local, reclen, c.maxdetphoton, seeds)
 
 
+def _to_host(t):
+    """device tensor -> numpy through PINNED host memory: the gathered records of 8 GPUs are ~100 MB per call, which a
+    pageable `.cpu()` moves at a few GB/s; torch's caching host allocator hands the same pinned block out again on the next
+    call, and the returned array keeps it alive for as long as the caller holds it"""
+    import torch
+    if t.device.type != "cuda":
+        return t.numpy()
+    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t)
+    return buf.numpy()
+
+
 def run_distributed(cfg, workload=None):
     """`pmcxcl.run`-style call executed by every rank of an initialised torch.distributed NCCL group; rank 0
     returns the combined result dictionary, the other ranks return None."""
@@ -155,11 +167,11 @@ def run_distributed(cfg, workload=None):
             return None
         res = sim.fetch()
         if detp is not None:
-            res["detp"] = detp.cpu().numpy().reshape(-1, max(1, sim.reclen))
+            res["detp"] = _to_host(detp).reshape(-1, max(1, sim.reclen))
             res["detected"] = int(sum(counts))
             res["saved"] = res["detp"].shape[0]
             if seeds is not None:
-                res["seeds"] = seeds.cpu().numpy().view(np.uint64).reshape(-1, 2)
+                res["seeds"] = _to_host(seeds).view(np.uint64).reshape(-1, 2)
         res["nphoton"] = total
         res["shares"] = shares
         res["flux"] = engine.shape_field(p, res["field"])

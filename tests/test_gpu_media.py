@@ -85,6 +85,6 @@ def test_continuous_media_with_detectors_and_refusals():
     with pytest.raises(RuntimeError, match="label media"):
         run_gpu(cfg)                                        # default record "DP"
     with pytest.raises(RuntimeError, match="outside this build"):
-        run_gpu(dict(cfg, vol=(np.ones((60, 60, 60), np.uint32)), mediaformat=97))     # SVMC
+        run_gpu(dict(cfg, vol=(np.ones((60, 60, 60), np.uint32)), mediaformat=96))     # two-word media: no front-end produces them
     with pytest.raises(hostcfg.ConfigError):
         hostcfg.prepare(dict(cfg, prop=[[0, 0, 1, 1]]))
