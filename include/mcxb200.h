@@ -275,10 +275,13 @@ int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_output* out);
  * replaces the multi-device branch of mcx_run_simulation: the `-G 1101` device mask / `-W a,b,c` workload split
  * (src/mcx_host.cpp:650-662, 1011-1012, src/mcx_utils.c:4845-4865), one slice of the single rand() stream per device
  * (src/mcx_host.cpp:759-768), all devices inside one timing window (:1098-1168) -- and, where the reference reads every
- * device back and sums volumes, energies and detected-photon lists on the host (:1218-1232, 1292-1306), an NCCL
- * exchange over NVLink: reduce(float32 volume) + reduce(float64 energy pair) to devices[0], all-gather of the
- * detected counts, variable-length send/recv of the records (and RNG states) into devices[0]'s buffer; then one
- * device-to-host copy and one normalisation with the global launched energy.
+ * device back and sums volumes, energies and detected-photon lists on the host (:1218-1232, 1292-1306), an exchange
+ * over NVLink.  Default: peer memory -- ONE kernel on devices[0] reads the float32 volumes of all peers through
+ * NVLink-mapped pointers and adds them into its own, the records (and RNG states) are copied peer to peer into the
+ * tail of devices[0]'s buffer, the energy pairs and counts (a few bytes) go through the host; no communicator to build.
+ * With MCXB_MULTI_EXCHANGE=nccl, or when a peer cannot be mapped: ncclReduce(float32 volume) + ncclReduce(float64
+ * energy pair) to devices[0], ncclAllGather of the detected counts, grouped ncclSend / ncclRecv of the records.  Then
+ * one device-to-host copy and one normalisation with the global launched energy.
  *   devices   CUDA ordinals, devices[0] collects the result;  workload: ndev weights or NULL (= equal shares)
  *   out       as for mcxb_run_simulation (runtime_ms = the slowest device's kernel window)
  *   info      optional per-device report
@@ -286,7 +289,7 @@ int mcxb_run_simulation(const mcxb_config* cfg, int device, mcxb_output* out);
 #define MCXB_MAX_DEVICES 16
 typedef struct mcxb_multi_info {
     int32_t  ndev;
-    int32_t  nccl_version;                   /* e.g. 22703 */
+    int32_t  nccl_version;                   /* e.g. 22703; 0 = the exchange went over peer memory */
     uint64_t share[MCXB_MAX_DEVICES];        /* photons given to each device */
     uint32_t detected[MCXB_MAX_DEVICES];     /* photons each device detected */
     uint32_t nthread[MCXB_MAX_DEVICES];      /* RNG streams (= threads) of each device: its slice of the seed stream */

@@ -359,7 +359,7 @@ extern "C" void mcx_run_simulation(Config* cfg, float* fluence, float* totalener
 
         mcx_printheader(cfg);
         MCX_FPRINTF(cfg->flog, "- code name: [%s] compiled for sm_100a\n", kEngineName);
-        MCX_FPRINTF(cfg->flog, "- RNG: %s, photon scheduling: persistent threads with a per-GPU photon counter; %u devices combined over NCCL %d\n",
+        MCX_FPRINTF(cfg->flog, "- RNG: %s, photon scheduling: persistent threads with a per-GPU photon counter; %u devices combined over NVLink (peer memory; NCCL %d with MCXB_MULTI_EXCHANGE=nccl)\n",
                     MCX_RNG_NAME, workdev, mcxb_nccl_version());
         MCX_FPRINTF(cfg->flog, "initializing streams ...\t");
         mcx_flush(cfg);

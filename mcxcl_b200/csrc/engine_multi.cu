@@ -16,6 +16,15 @@
  *
  * NCCL is bound at run time (dlopen of libnccl.so.2: the copy already loaded in the process, e.g. PyTorch's, or the
  * system one), so single-GPU users of libmcxb200.so need no NCCL at all.
+ *
+ * Peer-memory exchange.  One host process can do better than a collective library for this pattern: when devices[0] can
+ * map the memory of every other device (NVLink / NVSwitch: always on a B200 box), ONE kernel on devices[0] reads the
+ * float32 volumes of all peers straight over NVLink and adds them into its own (peer_sum_kernel: the gather and the
+ * reduction are the same loads), the records are copied peer to peer into the tail of devices[0]'s buffer, and the
+ * 16-byte energy pairs and the counts go through the host.  No communicator has to be built -- ncclCommInitAll plus
+ * the first collective cost seconds, more than the photon kernels of a 1e9-photon colin27 run on 8 GPUs (measured:
+ * profiles/README.md) -- and the sum has a fixed order.  This is the default; MCXB_MULTI_EXCHANGE=nccl selects the NCCL
+ * path, which is also the fallback when a peer cannot be mapped.
  */
 #include "../../include/mcxb200.h"
 
@@ -24,6 +33,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -151,6 +161,71 @@ int get_comms(const std::vector<int>& devs, CommSet** out) {
     return MCXB_OK;
 }
 
+/* out[i] += sum over peers of src[p][i]: the peers' volumes are read over NVLink (peer-mapped pointers), 128 bits at a time */
+struct PeerList {
+    const float* src[MCXB_MAX_DEVICES];
+    int n;
+};
+
+__global__ void peer_sum_kernel(float* __restrict__ out, PeerList peers, size_t n) {
+    const size_t n4 = n / 4;
+    float4* out4 = reinterpret_cast<float4*>(out);
+
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 acc = out4[i];
+
+        for (int p = 0; p < peers.n; p++) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(peers.src[p]) + i);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+        }
+
+        out4[i] = acc;
+    }
+
+    for (size_t i = 4 * n4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = out[i];
+
+        for (int p = 0; p < peers.n; p++) {
+            acc += peers.src[p][i];
+        }
+
+        out[i] = acc;
+    }
+}
+
+/* can devices[0] map every other device's memory?  (enables the mappings on first use) */
+bool enable_peers(const std::vector<int>& devs) {
+    if (cudaSetDevice(devs[0]) != cudaSuccess) {
+        return false;
+    }
+
+    for (size_t i = 1; i < devs.size(); i++) {
+        int ok = 0;
+
+        if (cudaDeviceCanAccessPeer(&ok, devs[0], devs[i]) != cudaSuccess || !ok) {
+            return false;
+        }
+
+        const cudaError_t e = cudaDeviceEnablePeerAccess(devs[i], 0);
+
+        if (e == cudaErrorPeerAccessAlreadyEnabled) {
+            cudaGetLastError();
+        } else if (e != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+    }
+
+    return true;
+}
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 #define NCCL_TRY(call)                                                                                            \
     do {                                                                                                          \
         ncclResult_t r__ = (call);                                                                                \
@@ -248,11 +323,21 @@ extern "C" int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devi
     const std::vector<int> devs(devices, devices + ndev);
     CommSet* cs = nullptr;
     int rc = MCXB_OK;
-    /* the communicators of a device list are built once per process (ncclCommInitAll: about two seconds for a first call);
+    static const bool timing = getenv("MCXB_TIMING") != nullptr;
+    const double t_start = now_ms();
+    double t_created = 0, t_kernels = 0, t_exchanged = 0;
+    /* peer-memory exchange unless NCCL is asked for or a peer cannot be mapped (see the head of this file) */
+    const char* how = getenv("MCXB_MULTI_EXCHANGE");
+    const bool use_p2p = !(how && strcmp(how, "nccl") == 0) && enable_peers(devs);
+    /* NCCL path: the communicators of a device list are built once per process (ncclCommInitAll: seconds for a first call);
      * a first call builds them on a helper thread while this one uploads the volumes and the photon kernels run */
     int comm_rc = MCXB_OK;
     std::string comm_err;
     std::thread comm_thread([&] {
+        if (use_p2p) {
+            return;
+        }
+
         comm_rc = get_comms(devs, &cs);
 
         if (comm_rc != MCXB_OK) {
@@ -302,6 +387,8 @@ extern "C" int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devi
             goto done;
         }
     }
+
+    t_created = now_ms();
 
     /* ---- seed slices: device i continues the ONE rand() stream where device i-1 stopped (src/mcx_host.cpp:759-768) ---- */
     for (int i = 0; i < ndev; i++) {
@@ -371,7 +458,76 @@ extern "C" int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devi
         CUDA_TRY(cudaDeviceSynchronize());               /* finalize done: the exchange streams below are non-blocking ones */
     }
 
-    /* ---- the exchange step ---- */
+    t_kernels = now_ms();
+
+    /* ---- the exchange step, over peer memory ---- */
+    if (use_p2p) {
+        comm_thread.join();
+        fieldlen = mcxb_sim_fieldlen(sims[0]);
+        reclen = mcxb_sim_reclen(sims[0]);
+        CUDA_TRY(cudaSetDevice(devs[0]));
+
+        if (cfg->issave2pt) {
+            PeerList peers;
+            peers.n = ndev - 1;
+
+            for (int i = 1; i < ndev; i++) {
+                peers.src[i - 1] = static_cast<const float*>(mcxb_sim_field_devptr(sims[i]));
+            }
+
+            const int grid = (int)std::min<uint64_t>((fieldlen / 4 + 255) / 256 + 1, 148 * 8);
+            peer_sum_kernel <<< grid, 256>>>(static_cast<float*>(mcxb_sim_field_devptr(sims[0])), peers, (size_t)fieldlen);
+            CUDA_TRY(cudaGetLastError());
+        }
+
+        {
+            /* energy pairs and detected counts: a few bytes per device through the host */
+            double esum[2] = { 0.0, 0.0 };
+
+            for (int i = 0; i < ndev; i++) {
+                double e[2];
+                CUDA_TRY(cudaMemcpy(e, mcxb_sim_energy_devptr(sims[i]), sizeof(e), cudaMemcpyDeviceToHost));
+                esum[0] += e[0];
+                esum[1] += e[1];
+                CUDA_TRY(cudaMemcpy(&counts[i], mcxb_sim_detcount_devptr(sims[i]), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            }
+
+            CUDA_TRY(cudaMemcpy(mcxb_sim_energy_devptr(sims[0]), esum, sizeof(esum), cudaMemcpyHostToDevice));
+        }
+
+        if (mcxb_sim_detphoton_devptr(sims[0])) {
+            for (int i = 0; i < ndev; i++) {
+                const uint32_t have = std::min(counts[i], cfg->maxdetphoton);
+                offs[i] = kept;
+                stored[i] = std::min(have, cfg->maxdetphoton - kept);
+                kept += stored[i];
+                total += counts[i];
+            }
+
+            for (int i = 1; i < ndev; i++) {
+                if (!stored[i]) {
+                    continue;
+                }
+
+                if (reclen) {
+                    CUDA_TRY(cudaMemcpyPeerAsync((float*)mcxb_sim_detphoton_devptr(sims[0]) + (size_t)offs[i] * reclen, devs[0],
+                                                 mcxb_sim_detphoton_devptr(sims[i]), devs[i], sizeof(float) * (size_t)stored[i] * reclen, 0));
+                }
+
+                if (mcxb_sim_seeddata_devptr(sims[0])) {
+                    CUDA_TRY(cudaMemcpyPeerAsync((uint64_t*)mcxb_sim_seeddata_devptr(sims[0]) + (size_t)offs[i] * 2, devs[0],
+                                                 mcxb_sim_seeddata_devptr(sims[i]), devs[i], 16 * (size_t)stored[i], 0));
+                }
+            }
+
+            CUDA_TRY(cudaMemcpy(mcxb_sim_detcount_devptr(sims[0]), &total, sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+
+        CUDA_TRY(cudaDeviceSynchronize());
+        goto exchanged;
+    }
+
+    /* ---- the exchange step, over NCCL ---- */
     comm_thread.join();
 
     if (comm_rc != MCXB_OK) {
@@ -435,8 +591,15 @@ extern "C" int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devi
         CUDA_TRY(cudaStreamSynchronize(cs->stream[i]));
     }
 
+exchanged:
+    t_exchanged = now_ms();
     /* ---- one read-back, one normalisation with the global launched energy (src/mcx_host.cpp:1382-1465) ---- */
     rc = mcxb_sim_fetch(sims[0], nullptr, out);
+
+    if (timing) {
+        fprintf(stderr, "mcxb multi (%s, %d devices): create %.1f ms, kernels %.1f ms, exchange %.1f ms, fetch %.1f ms\n", use_p2p ? "peer memory" : "nccl", ndev,
+                t_created - t_start, t_kernels - t_created, t_exchanged - t_kernels, now_ms() - t_exchanged);
+    }
 
     if (rc == MCXB_OK) {
         out->runtime_ms = *std::max_element(ms.begin(), ms.end());
@@ -446,7 +609,7 @@ extern "C" int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devi
         if (info) {
             memset(info, 0, sizeof(*info));
             info->ndev = ndev;
-            info->nccl_version = mcxb_nccl_version();
+            info->nccl_version = use_p2p ? 0 : mcxb_nccl_version();      /* 0 = the exchange went over peer memory */
 
             for (int i = 0; i < ndev; i++) {
                 info->share[i] = share[i];
@@ -463,8 +626,16 @@ done:
         comm_thread.join();
     }
 
-    for (int i = 0; i < ndev; i++) {
-        mcxb_sim_destroy(sims[i]);
+    {
+        const double t0 = now_ms();
+
+        for (int i = 0; i < ndev; i++) {
+            mcxb_sim_destroy(sims[i]);
+        }
+
+        if (timing) {
+            fprintf(stderr, "mcxb multi: destroy %.1f ms, whole call %.1f ms\n", now_ms() - t0, now_ms() - t_start);
+        }
     }
 
     return rc;

@@ -1322,7 +1322,9 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
             {
                 float sphi = 0.f, cphi = 1.f, stheta, ctheta;
                 const bool flat = GEN && P.is2d;
-                const bool polar = EXT && P.maxpolmedia != 0u && !flat;
+                /* (a packet that carries label 0 through an in-grid empty voxel has no Mueller matrix: the reference indexes its
+                 * table with label - 1 there, :2455; here such a packet scatters by the scalar phase function) */
+                const bool polar = EXT && P.maxpolmedia != 0u && !flat && ph.label - 1u < P.maxpolmedia;
                 float theta = 0.f, phi = 0.f;
 
                 if (polar) {

@@ -348,3 +348,43 @@ def test_detected_photon_jdat_fields_read_back(tmp_path):
     assert abs(ppath[:, 0].mean() - d[3].mean()) < 0.05 * d[3].mean()
     counts = np.ascontiguousarray(d[1]).view(np.uint32).astype(np.float64)
     assert counts.min() >= 1 and abs(counts.mean() / ppath[:, 0].mean() - 1.0) < 0.1                 # mus = 1 per voxel: one event per unit path
+
+
+# ---- the extended modes through the unchanged CLI (JSON keys of src/mcx_utils.c:2510-2563, 2944-2949, 3049-3073) ----------------
+POLARIZED_DECK = """{
+ "Session": {"ID": "onelayer", "DoMismatch": 0, "DoAutoThread": 1, "MaxDetPhoton": 1000000, "BCFlags": "______001000",
+             "SaveDataMask": "IXVSPW", "Photons": 200000, "MinEnergy": 0.01},
+ "Forward": {"T0": 0, "T1": 5e-09, "Dt": 5e-09},
+ "Optode": {"Source": {"Pos": [10, 10, 0], "Dir": [0, 0, 1], "IQUV": [1, 1, 0, 0], "WaveLength": 632.8}},
+ "Domain": {"OriginType": 1, "LengthUnit": 1, "Media": [{"mua": 0, "mus": 0, "g": 1, "n": 1}, {"mua": 0, "mus": 0, "g": 1, "n": 1}],
+            "MieScatter": [{"mua": 0.0, "radius": 1.015, "rho": 0.0001152, "nsph": 1.59, "nmed": 1.33}],
+            "MediaFormat": "byte", "Dim": [20, 20, 10]},
+ "Shapes": [{"Grid": {"Tag": 1, "Size": [20, 20, 10]}}]
+}"""
+
+
+def test_polarised_deck_of_the_reference_examples(tmp_path):
+    """example/polarized/onelayer.json (the volume written as a Grid shape instead of the zipped array): the CLI's own Mie
+    code fills the media table and the Mueller matrices (mcx_prep_polarized), the engine tracks Stokes vectors, the detected
+    records carry them (`I` of SaveDataMask) and reach the unchanged .jdat writer"""
+    (tmp_path / "onelayer.json").write_text(POLARIZED_DECK)
+    rc, out = mcx(["-f", "onelayer.json", "-F", "jnii", "-S", "0"], tmp_path)
+    assert rc == 0, out[-2000:]
+    m = re.search(r"detected (\d+) photons", out)
+    assert m and int(m.group(1)) > 20000, out[-1500:]                   # the +z face is a detector (BCFlags); mua = 0: most packets leave there
+    assert absorbed(out) < 0.01
+    jd = json.loads((tmp_path / "onelayer_detp.jdat").read_text())
+    info = jd["MCXData"]["Info"]
+    assert info["DetectedPhoton"] == int(m.group(1)) and info["SavedPhoton"] == int(m.group(1))
+    # the reference's .jdat writer knows seven record fields and no Stokes columns (src/mcx_utils.c:1074): what it can name is there
+    assert {"nscat", "ppath", "p", "v", "w0"} <= set(jd["MCXData"]["PhotonData"])
+
+
+def test_rf_frequency_through_the_cli(tmp_path):
+    """Optode.Source.Frequency (src/mcx_utils.c:2944-2945) turns the run into an RF forward run: same packets, same absorbed
+    fraction.  (The adjoint types cannot be reached from the CLI: its JSON reader takes a detector's position from the
+    Detector ARRAY whenever the detector object has a third member such as "Dir" (src/mcx_utils.c:3047-3059), which
+    dereferences a NULL `next` for one detector -- `mcxcl --dumpjson` with such a deck dies before any device is touched.
+    The adjoint path is tested through pmcxcl, tests/test_gpu_pmcxcl.py.)"""
+    rc, out = mcx(["--bench", "cube60b", "-n", "2e5", "-S", "0", "--json", '{"Optode":{"Source":{"Frequency":1e8}}}'], tmp_path)
+    assert rc == 0 and re.search(r"absorbed:.*27\.[0-9]+%", out), out[-1500:]
