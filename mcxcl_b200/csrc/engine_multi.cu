@@ -328,6 +328,23 @@ extern "C" int mcxb_run_simulation_multi(const mcxb_config* cfg, const int* devi
     double t_created = 0, t_kernels = 0, t_exchanged = 0;
     /* peer-memory exchange unless NCCL is asked for or a peer cannot be mapped (see the head of this file) */
     const char* how = getenv("MCXB_MULTI_EXCHANGE");
+    {
+        /* a first call creates one CUDA context per device (hundreds of ms each): all of them at once */
+        std::vector<std::thread> th;
+
+        for (int i = 0; i < ndev; i++) {
+            th.emplace_back([&, i] {
+                if (cudaSetDevice(devs[i]) == cudaSuccess) {
+                    cudaFree(nullptr);
+                }
+            });
+        }
+
+        for (auto& t : th) {
+            t.join();
+        }
+    }
+    const double t_ctx = now_ms();
     const bool use_p2p = !(how && strcmp(how, "nccl") == 0) && enable_peers(devs);
     /* NCCL path: the communicators of a device list are built once per process (ncclCommInitAll: seconds for a first call);
      * a first call builds them on a helper thread while this one uploads the volumes and the photon kernels run */
@@ -597,8 +614,8 @@ exchanged:
     rc = mcxb_sim_fetch(sims[0], nullptr, out);
 
     if (timing) {
-        fprintf(stderr, "mcxb multi (%s, %d devices): create %.1f ms, kernels %.1f ms, exchange %.1f ms, fetch %.1f ms\n", use_p2p ? "peer memory" : "nccl", ndev,
-                t_created - t_start, t_kernels - t_created, t_exchanged - t_kernels, now_ms() - t_exchanged);
+        fprintf(stderr, "mcxb multi (%s, %d devices): contexts %.1f ms, create %.1f ms, kernels %.1f ms, exchange %.1f ms, fetch %.1f ms\n",
+                use_p2p ? "peer memory" : "nccl", ndev, t_ctx - t_start, t_created - t_ctx, t_kernels - t_created, t_exchanged - t_kernels, now_ms() - t_exchanged);
     }
 
     if (rc == MCXB_OK) {

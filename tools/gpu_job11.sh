@@ -1,8 +1,9 @@
 #!/bin/bash
-# 2 x B200: the C-ABI multi-GPU call with both exchanges, timings of the relinked CLI, and the new CLI tests
+# N x B200: timings of the relinked CLI with the peer-memory exchange (and NCCL for comparison)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_cli.py -m gpu -q 2>&1 | tail -15 > gpurun_out/r2_pytest_multi2.log; cat gpurun_out/r2_pytest_multi2.log | tail -12
+N=$(nvidia-smi -L | wc -l); MASK=$(printf '1%.0s' $(seq 1 $N))
+: > gpurun_out/r2_cli_exchange.log
 for ex in peer nccl; do
-  ( cd /tmp && MCXB_TIMING=1 MCXB_MULTI_EXCHANGE=$ex timeout 600 /root/repo/integration/_build/mcxcl --bench colin27 -n 1e8 -G 11 -H 10000000 -S 0 2>&1 | sed 's/\x1b\[[0-9;]*m//g' | grep -E "mcxb multi|kernel complete|transfer complete|speed|absorbed" | sed "s/^/[$ex] /" ) >> gpurun_out/r2_cli_exchange.log 2>&1
+  ( cd /tmp && MCXB_TIMING=1 MCXB_MULTI_EXCHANGE=$ex timeout 600 /root/repo/integration/_build/mcxcl --bench colin27 -n ${1:-1e8} -G $MASK -H 10000000 -S 0 2>&1 | sed 's/\x1b\[[0-9;]*m//g' | grep -E "mcxb multi|kernel complete|transfer complete|speed|absorbed" | sed "s/^/[$ex x$N] /" ) >> gpurun_out/r2_cli_exchange.log 2>&1
 done
 cat gpurun_out/r2_cli_exchange.log
