@@ -814,6 +814,10 @@ constexpr int kBlock = MCXB_BLOCK;
 #ifndef MCXB_LAUNCH_IN_TAIL
     #define MCXB_LAUNCH_IN_TAIL 1
 #endif
+#ifndef MCXB_GENERIC_SMEM
+    #define MCXB_GENERIC_SMEM 0
+#endif
+constexpr bool kSharedWindow = MCXB_GENERIC_SMEM == 0;
 #ifndef MCXB_QUEUE_DEPTH
     #define MCXB_QUEUE_DEPTH 8
 #endif
@@ -828,6 +832,17 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
     constexpr uint32_t QK = (uint32_t)QDEPTH;
     float4* const queue = smem + threadIdx.x;             /* entry j of this thread: queue[j * kBlock] */
     float4* tab = smem + QK * kBlock;                     /* optical properties, row 0 = background */
+    /* the table through a shared-window address, for the access inside the photon loop (photon_device.cuh) */
+    /* Measured (B200, profiles/r2_sweep_shared_window.log): the kernels WITHOUT the scattering queue gain from it (colin27
+     * 536.7 -> 522.8 ms, digimouse 355.0 -> 353.3), the queue kernels lose (cube60b 262.5 -> 264.6; with only the table
+     * through the window 271.1): used where QDEPTH == 0. */
+    constexpr bool useWindow = kSharedWindow && QK == 0;
+    uint32_t tab_s = smem_addr(tab);
+
+    if (useWindow) {
+        asm volatile("mov.u32 %0, %0;" : "+r"(tab_s));      /* opaque: keeps the window address in ONE register instead of rebuilding it per access */
+    }
+
     const float4* srctab = tab + P.medianum;              /* 4 rows per source, main source first  */
     const float4* dettab = srctab + 4 * (1 + P.extrasrclen);
     float* ftab = reinterpret_cast<float*>(tab + P.tablen);        /* inverse-CDF tables */
@@ -1294,6 +1309,7 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
                     const float stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));
                     rotate_direction(bx, by, bz, stheta, ctheta, sphi, cphi);
                     queue[((qs >> 8) & (QK - 1u)) * kBlock] = make_float4(bx, by, bz, ns);
+
                     qs += 257u;
                 }
             }
@@ -1457,7 +1473,8 @@ __global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kerne
         ph.n1 = nmed;
         {
             /* SVMC re-derives the part of the voxel from the position in every iteration (:2666-2669) */
-            const float4 pr = svmc ? svmc_update(P, tab, ph.label, ph.idx1d, ph.px, ph.py, ph.pz, ph.ix, ph.iy, ph.iz, nu) : medium<MediaT>(P, tab, ph.label);
+            const float4 pr = svmc ? svmc_update(P, tab, ph.label, ph.idx1d, ph.px, ph.py, ph.pz, ph.ix, ph.iy, ph.iz, nu)
+                              : ((useWindow && sizeof(MediaT) < 4) ? lds_f4(tab_s + ph.label * 16u) : medium<MediaT>(P, tab, ph.label));
             mua = pr.x;
             mus = pr.y;
             g = pr.z;
