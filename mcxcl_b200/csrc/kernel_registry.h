@@ -19,7 +19,7 @@ struct KernelEntry {
     int  savedet;      /* 0 none, 1 default record folded at compile time, 2 record flags at run time */
     bool media16, media32, acc64, stats, generic;     /* media word: 8 bits, 16 bits, or 32 bits (continuous media) */
     int  queue;        /* depth of the scattering queue (shared memory, 16 bytes x depth per thread), 0 = none */
-    bool ext;          /* extended physics compiled in (polarised light, RF): generic kernels at 128 registers */
+    bool ext;          /* extended physics compiled in (polarised light, RF, split voxels, adjoint detector sources): generic kernels with the extra per-packet state */
     PhotonKernelFn fn;
     const char* name;
 };

@@ -808,6 +808,11 @@ constexpr int kBlock = MCXB_BLOCK;
  * scattering event and the block runs every iteration anyway -- engine.cu picks the variant from the mean
  * scattering coefficient per voxel.  Per-thread RNG draw ORDER differs from the reference's, so runs that record
  * seeds for a replay use the kernels without the queue. */
+#ifndef MCXB_EXT_MINBLOCKS
+    #define MCXB_EXT_MINBLOCKS 4      /* resident blocks per SM of the extended-physics kernels: 64 registers with 68-104 bytes of spills beat 2 blocks
+                                         at 87-103 registers by 16-23 % (polarised 99.6 -> 83.5 ms, RF 65.8 -> 53.2, SVMC 89.7 -> 69.3, adjoint 52.9 -> 40.9
+                                         for 1e7 photons; profiles/r2_ext_minblocks.log) */
+#endif
 #ifndef MCXB_UNROLL
     #define MCXB_UNROLL 2
 #endif
@@ -825,7 +830,7 @@ constexpr int kQueueDepth = MCXB_QUEUE_DEPTH;
 static_assert(kQueueDepth > 0 && (kQueueDepth & (kQueueDepth - 1)) == 0, "queue depth must be a power of two");
 
 template <int SRC, bool REFLECT, int SAVEDET, typename MediaT, typename AccT, bool STATS, bool GEN, int QDEPTH = 0, bool EXT = false>
-__global__ void __launch_bounds__(kBlock, EXT ? 2 : MCXB_MINBLOCKS) photon_kernel(const __grid_constant__ SimParam P) {
+__global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLOCKS) photon_kernel(const __grid_constant__ SimParam P) {
     extern __shared__ float4 smem[];
     static_assert(QDEPTH == 0 || (!GEN && SAVEDET < 2), "the scattering queue exists for the common-configuration kernels with the default record");
     static_assert(!EXT || GEN, "the extended-physics kernels (polarised light, RF) are generic kernels");
