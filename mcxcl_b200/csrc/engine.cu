@@ -22,6 +22,7 @@
 #include <string>
 #include <chrono>
 #include <vector>
+#include <thread>
 #include <map>
 #include <mutex>
 #include <algorithm>
@@ -1522,6 +1523,33 @@ extern "C" int mcxb_sim_finalize(mcxb_sim* s, void* cuda_stream) {
     return MCXB_OK;
 }
 
+/* host loops over the whole output (accumulate + normalise, src/mcx_host.cpp:1292-1296 and mcx_normalize): split over a few
+ * threads once the volume is large (time-gated atlases reach hundreds of millions of elements, where one core needs ~0.5 s) */
+template <typename F> static void for_range(uint64_t n, F body) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (n < (4u << 20)) ? 1u : std::min(8u, hw);
+
+    if (nt == 1) {
+        body((uint64_t)0, n);
+        return;
+    }
+
+    std::vector<std::thread> th;
+    const uint64_t chunk = (n + nt - 1) / nt;
+
+    for (unsigned t = 0; t < nt; t++) {
+        const uint64_t a = t * chunk, b = std::min(n, a + chunk);
+
+        if (a < b) {
+            th.emplace_back([ =, &body] { body(a, b); });
+        }
+    }
+
+    for (auto& t : th) {
+        t.join();
+    }
+}
+
 extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) {
     if (!s || !out) {
         return fail(MCXB_ERR_ARG, "sim/out is NULL");
@@ -1650,13 +1678,17 @@ extern "C" int mcxb_sim_fetch(mcxb_sim* s, void* cuda_stream, mcxb_output* out) 
             const float scale = normalizer_impl(&nc, out->energytot, s->d_rseed != nullptr);
             out->normalizer = scale;
 
-            for (uint64_t i = 0; i < n; i++) {
-                dst[i] = (dst[i] + src[i]) * scale;
-            }
+            for_range(n, [&](uint64_t a, uint64_t b) {
+                for (uint64_t i = a; i < b; i++) {
+                    dst[i] = (dst[i] + src[i]) * scale;
+                }
+            });
         } else {
-            for (uint64_t i = 0; i < n; i++) {
-                dst[i] += src[i];
-            }
+            for_range(n, [&](uint64_t a, uint64_t b) {
+                for (uint64_t i = a; i < b; i++) {
+                    dst[i] += src[i];
+                }
+            });
         }
     }
 
