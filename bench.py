@@ -20,9 +20,11 @@ the configuration BASELINE.json quotes the metric on).  Printed by rank 0 as ONE
   cpu_baseline   the reference kernel source built for the host (oracle/_ref), all host cores, bounded sample
   parity_check   every step checks itself: energytot == N x nphoton exactly, whole-job detected count, records gathered
                  == sum of the per-rank counts, absorbed fraction within 0.5 % of the committed reference series
-  extra          the same measurement (value, e2e, parity_check) for colin27 and for digimouse (the deck the reference ships:
-                 a fourier wide-field source) at 1.25e8 photons per GPU: at 8 GPUs these are the 1e9-photon runs of
-                 BASELINE.json's configs, colin27 being its scaling target
+  extra          the same measurement (value, e2e, parity_check) for colin27, for digimouse (the deck the reference ships: a
+                 fourier wide-field source, one gate) and for digimouse_tg (this repository's reading of BASELINE.json's
+                 "multi-source time-gated": 4 pencil sources, one volume each, 10 gates = 392 M accumulators, DESIGN.md
+                 section 7) at 1.25e8 photons per GPU: at 8 GPUs these are the 1e9-photon runs of BASELINE.json's configs,
+                 colin27 being its scaling target
 
 --impl reference times that CPU implementation alone (rank 0 only under torchrun).
 """
@@ -301,7 +303,7 @@ def main():
     ap.add_argument("--ref-photons", type=float, default=1e6, help="photons per step of the CPU reference arm")
     ap.add_argument("--cpu-photons", type=float, default=2e6, help="bounded sample of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extra", default="colin27,digimouse", help="comma-separated extra workloads reported under `extra` (\"\" = none)")
+    ap.add_argument("--extra", default="colin27,digimouse,digimouse_tg", help="comma-separated extra workloads reported under `extra` (\"\" = none)")
     ap.add_argument("--extra-photons", type=float, default=1.25e8, help="photons per GPU per step of the extra workloads (1.25e8 x 8 GPUs = the 1e9-photon colin27 run)")
     ap.add_argument("--extra-steps", type=int, default=2)
     args = ap.parse_args()
