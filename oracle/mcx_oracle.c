@@ -1281,6 +1281,10 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
         return -3;      /* photon replay is not restated here: oracle/_ref (the reference source itself) checks it */
     }
 
+    if (cfg->mediaformat > 4 || cfg->polmedianum || cfg->omega > 0.f || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
+        return -3;      /* continuous / split-voxel media, polarised light, RF and adjoint runs: checked by oracle/_ref only */
+    }
+
     param_t g;
     memset(&g, 0, sizeof(g));
     g.cfg = cfg;
