@@ -63,7 +63,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     h = hashlib.sha256()
     for f in [os.path.join(HERE, "mcx_cuda_host.cpp"), os.path.join(HERE, "clstub", "CL", "cl.h"), os.path.abspath(__file__),
-              os.path.join(ROOT, "include", "mcxb200.h")] + [os.path.join(SRC, f) for f in C_FILES + CXX_FILES + ["pmcxcl.cpp"]]:
+              os.path.join(ROOT, "include", "mcxb200.h"), os.path.join(HERE, "mexstub", "mex.h")] + \
+            [os.path.join(SRC, f) for f in C_FILES + CXX_FILES + ["pmcxcl.cpp", "mcxlabcl.cpp"]]:
         h.update(open(f, "rb").read())
     stamp = os.path.join(OUT, "build.stamp")
     if not args.force and os.path.exists(exe) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
@@ -94,6 +95,7 @@ def main():
     print("build_cli: built", exe)
     mod = build_pmcxcl()
     print("build_cli: built", mod)
+    print("build_cli: built", build_mexcheck())
     with open(stamp, "w") as f:
         f.write(h.hexdigest())
     return 0
@@ -130,6 +132,39 @@ def build_pmcxcl():
     for o in objs:
         os.remove(o)
     return mod
+
+
+def build_mexcheck():
+    """The reference's UNCHANGED MATLAB / Octave front-end (src/mcxlabcl.cpp) compiled and linked against the B200 binding:
+    the `mcxlabcl` target of src/CMakeLists.txt:146-188 (MCX_CONTAINER MATLAB_MEX_FILE) with mcx_host.cpp ->
+    integration/mcx_cuda_host.cpp.  This image has neither MATLAB nor Octave, so <mex.h> is integration/mexstub/mex.h
+    (declarations of the public MEX API only) and the result, integration/_build/mcxlabcl_check.so, keeps its mx* / mex*
+    symbols undefined -- what a MEX file looks like before MATLAB loads it.  It cannot be run here; it shows that the file
+    compiles and that the only symbols it needs from the host layer are the three the binding exports."""
+    defs = DEFS + ["-DMCX_CONTAINER", "-DMATLAB_MEX_FILE"]
+    inc = ["-I" + os.path.join(HERE, "mexstub")] + INC
+    out = os.path.join(OUT, "mcxlabcl_check.so")
+    jobs, objs = [], []
+
+    def add(cmd, src, tag="mex_"):
+        obj = os.path.join(OUT, tag + os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        jobs.append(cmd + ["-c", os.path.join(SRC, src) if not os.path.isabs(src) else src, "-o", obj])
+        objs.append(obj)
+
+    for f in ["mcx_utils.c", "mcx_shapes.c", "mcx_lang.c", "mcx_tictoc.c", "cjson/cJSON.c", "ubj/ubjw.c"]:
+        add(["gcc", "-std=c99", "-O2", "-w", "-m64", "-fPIC"] + defs + inc, f)
+    for f in ["mcx_mie.cpp", "mcx_neurojson.cpp", "mcxlabcl.cpp"]:
+        add(["g++", "-O2", "-w", "-m64", "-fPIC"] + defs + inc, f)
+    for f in ZMAT_FILES:
+        add(["gcc", "-O2", "-w", "-fPIC"] + ZMAT_DEFS + ZMAT_INC, f, tag="mexz_")
+    add(["g++", "-std=c++17", "-O2", "-Wall", "-m64", "-fPIC"] + defs + inc, os.path.join(HERE, "mcx_cuda_host.cpp"))
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        list(ex.map(run, jobs))
+    run(["g++", "-shared", "-o", out] + objs + ["-L" + os.path.join(ROOT, "mcxcl_b200"), "-lmcxb200", "-Wl,-rpath,$ORIGIN/../../mcxcl_b200",
+                                               "-lm", "-pthread"])
+    for o in objs:
+        os.remove(o)
+    return out
 
 
 if __name__ == "__main__":
