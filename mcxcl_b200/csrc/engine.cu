@@ -400,11 +400,12 @@ struct mcxb_sim {
 };
 
 /* det: 0 = no detector capture, 1 = the default record, 2 = any record flags (generic kernels take 1 and 2 alike) */
-static const KernelEntry* find_kernel(int src, bool refl, int det, int mediabits, bool acc64, bool stats, bool common, bool queue = false, bool ext = false) {
+static const KernelEntry* find_kernel(int src, bool refl, int det, int mediabits, bool acc64, bool stats, bool common, bool queue = false, bool ext = false,
+                                      bool bcodes = false) {
     typedef const KernelEntry* (*GroupFn)(int*);
     static const GroupFn groups[kNumGroups] = { mcxb_kernel_group_0, mcxb_kernel_group_1, mcxb_kernel_group_2, mcxb_kernel_group_3,
                                                 mcxb_kernel_group_4, mcxb_kernel_group_5, mcxb_kernel_group_6, mcxb_kernel_group_7,
-                                                mcxb_kernel_group_8, mcxb_kernel_group_9
+                                                mcxb_kernel_group_8, mcxb_kernel_group_9, mcxb_kernel_group_10, mcxb_kernel_group_11
                                               };
     const bool m16 = mediabits == 16, m32 = mediabits == 32;
     /* most specialised first: {source, common} -> {any source, common} -> {any source, generic} */
@@ -421,7 +422,7 @@ static const KernelEntry* find_kernel(int src, bool refl, int det, int mediabits
 
                 if (e[i].src == wantsrc[pass] && e[i].generic == wantgen[pass] && e[i].reflect == refl && detok &&
                         e[i].media16 == m16 && e[i].media32 == m32 && e[i].acc64 == acc64 && e[i].stats == stats && (e[i].queue != 0) == (queue && !wantgen[pass]) &&
-                        e[i].ext == ext) {
+                        e[i].ext == ext && e[i].bcodes == (bcodes && !wantgen[pass])) {
                     return e + i;
                 }
             }
@@ -433,12 +434,6 @@ static const KernelEntry* find_kernel(int src, bool refl, int det, int mediabits
 
 /* true when the configuration fits the compile-time assumptions of the GEN=false kernels (photon_kernel.cuh) */
 static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t nphase) {
-    for (int i = 0; i < 12; i++) {
-        if (cfg->bc[i] != 0) {
-            return false;
-        }
-    }
-
     const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
     return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->issaveref == 0 && !(cfg->debuglevel & (MCXB_DEBUG_MOVE | MCXB_DEBUG_MOVE_ONLY)) &&
            cfg->issave2pt != 0 && cfg->replay_seed == nullptr && cfg->srcnum <= 1 &&
@@ -1084,7 +1079,17 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
     s->acc64 = cfg->accum != MCXB_ACCUM_F32;
     const bool refl = needs_reflection(cfg);
     const bool stats = (cfg->debuglevel & MCXB_DEBUG_STATS) != 0;
-    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32 && !s->ext;
+    /* explicit per-face boundary codes / detect-on-face flags: common kernels of their own (BCODES; pencil or any source,
+     * 8-bit media, fp64 accumulators, default record), else the generic ones.  MCXB_BC_GENERIC=1: always generic (A/B) */
+    bool anybc = false;
+
+    for (int i = 0; i < 12; i++) {
+        anybc = anybc || cfg->bc[i] != 0;
+    }
+
+    const bool hasbc = anybc && getenv("MCXB_BC_GENERIC") == nullptr;
+    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32 && !s->ext && (!anybc || hasbc);
+
     const int detmode = savedet ? (flag == 0x5u ? 1 : 2) : 0;
     /* Scattering queue (photon_kernel.cuh): pays where a packet crosses several voxels per scattering event.  Measured on
      * B200: +8..10 % at mus = 1 per voxel (cube60 / cube60b), +20 % at mus <= 0.2 (skinvessel), -9..-12 % at mus = 8..40
@@ -1111,11 +1116,11 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         ke = find_kernel(srcAny, true, 1, mediabits, true, true, false);
     } else {
         if (queue) {
-            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, true);
+            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, true, false, hasbc);
         }
 
         if (!ke) {
-            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, false, s->ext);
+            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, false, s->ext, hasbc);
         }
 
         if (!ke && s->ext && !s->acc64) {
@@ -1154,7 +1159,7 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
 
         if (ke->queue && (!fits || perSM < MCXB_MINBLOCKS)) {
             /* the queue's shared memory would cost resident blocks (many partial-path rows): scatter in place instead */
-            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, false);
+            ke = find_kernel(cfg->srctype, refl, detmode, mediabits, s->acc64, false, common, false, false, hasbc);
 
             if (!ke) {
                 return fail(MCXB_ERR_ARG, "no kernel specialisation for this configuration");

@@ -19,12 +19,13 @@ struct KernelEntry {
     int  savedet;      /* 0 none, 1 default record folded at compile time, 2 record flags at run time */
     bool media16, media32, acc64, stats, generic;     /* media word: 8 bits, 16 bits, or 32 bits (continuous media) */
     int  queue;        /* depth of the scattering queue (shared memory, 16 bytes x depth per thread), 0 = none */
+    bool bcodes;       /* common kernel that honours per-face boundary codes / detect-on-face flags (`-B`, `--bc`) */
     bool ext;          /* extended physics compiled in (polarised light, RF, split voxels, adjoint detector sources): generic kernels with the extra per-packet state */
     PhotonKernelFn fn;
     const char* name;
 };
 
-constexpr int kNumGroups = 10;
+constexpr int kNumGroups = 12;
 
 } // namespace mcxb
 
@@ -38,3 +39,5 @@ extern "C" const mcxb::KernelEntry* mcxb_kernel_group_6(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_7(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_8(int* n);
 extern "C" const mcxb::KernelEntry* mcxb_kernel_group_9(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_10(int* n);
+extern "C" const mcxb::KernelEntry* mcxb_kernel_group_11(int* n);

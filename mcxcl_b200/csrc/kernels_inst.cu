@@ -14,20 +14,24 @@
  *   group 7: any source (run time), 32-bit media words, generic (continuous media formats 99-104: the word encodes the properties)
  *   group 8: any source (run time), 8-bit media, generic + extended physics (polarised light, RF forward / replay)
  *   group 9: any source (run time), 16- and 32-bit media, generic + extended physics
+ *   group 10 / 11: pencil beam / any source, 8-bit media, common kernels that honour per-face boundary codes (`-B`, `--bc`)
  */
 #include "kernel_registry.h"
 
 #ifndef MCXB_INST_GROUP
-    #error "compile with -DMCXB_INST_GROUP=<0..9>"
+    #error "compile with -DMCXB_INST_GROUP=<0..11>"
 #endif
 
 namespace mcxb {
 
 #define MCXB_STR2(x) #x
 #define MCXB_STR(x) MCXB_STR2(x)
-#define MCXB_KQ(SRC, R, D, M, A, S, G, Q) { SRC, R, D, sizeof(M) == 2, sizeof(M) == 4, sizeof(A) == 8, S, G, Q, false, photon_kernel<SRC, R, D, M, A, S, G, Q>, #SRC "/" #R "/det" #D "/" #M "/" #A "/" #G "/q" MCXB_STR(Q) }
+#define MCXB_KQ(SRC, R, D, M, A, S, G, Q) { SRC, R, D, sizeof(M) == 2, sizeof(M) == 4, sizeof(A) == 8, S, G, Q, false, false, photon_kernel<SRC, R, D, M, A, S, G, Q>, #SRC "/" #R "/det" #D "/" #M "/" #A "/" #G "/q" MCXB_STR(Q) }
 /* generic kernel with the extended physics, reflection x detector capture */
-#define MCXB_KX(R, D, M) { srcAny, R, D, sizeof(M) == 2, sizeof(M) == 4, true, false, true, 0, true, photon_kernel<srcAny, R, D, M, double, false, true, 0, true>, "srcAny/" #R "/det" #D "/" #M "/double/true/ext" }
+#define MCXB_KX(R, D, M) { srcAny, R, D, sizeof(M) == 2, sizeof(M) == 4, true, false, true, 0, false, true, photon_kernel<srcAny, R, D, M, double, false, true, 0, true>, "srcAny/" #R "/det" #D "/" #M "/double/true/ext" }
+/* common kernels with per-face boundary codes (8-bit media, fp64), with and without the scattering queue */
+#define MCXB_KB(SRC, R, D, Q) { SRC, R, D, false, false, true, false, false, Q, true, false, photon_kernel<SRC, R, D, uint8_t, double, false, false, Q, false, true>, #SRC "/" #R "/det" #D "/uint8_t/double/false/q" MCXB_STR(Q) "/bc" }
+#define MCXB_RDB(SRC, Q) MCXB_KB(SRC, false, 0, Q), MCXB_KB(SRC, true, 0, Q), MCXB_KB(SRC, false, 1, Q), MCXB_KB(SRC, true, 1, Q)
 #define MCXB_RDX(M) MCXB_KX(false, 0, M), MCXB_KX(true, 0, M), MCXB_KX(false, 1, M), MCXB_KX(true, 1, M)
 #define MCXB_K(SRC, R, D, M, A, S, G) MCXB_KQ(SRC, R, D, M, A, S, G, 0)
 /* reflection x detector capture (0 = none, 1 = default record) */
@@ -61,6 +65,10 @@ static const KernelEntry entries[] = {
     MCXB_RDX(uint8_t)
 #elif MCXB_INST_GROUP == 9
     MCXB_RDX(uint16_t), MCXB_RDX(uint32_t)
+#elif MCXB_INST_GROUP == 10
+    MCXB_RDB(srcPencil, 0), MCXB_RDB(srcPencil, MCXB_QUEUE_DEPTH)
+#elif MCXB_INST_GROUP == 11
+    MCXB_RDB(srcAny, 0), MCXB_RDB(srcAny, MCXB_QUEUE_DEPTH)
 #endif
 };
 

@@ -783,8 +783,9 @@ __device__ __forceinline__ void update_stokes(float& sI, float& sQ, float& sU, f
  *   QDEPTH   depth of the per-thread scattering queue (see above), 0 = scatter in place
  *   GEN      false = the common configuration, with everything below decided at compile time:
  *              3-D domain, Henyey-Greenstein phase function, no gscatter switch, flux or fluence
- *              output with save2pt on, no diffuse-reflectance output, all six boundary codes "unknown"
- *              (i.e. governed by isreflect alone) and no detect-on-face flags;
+ *              output with save2pt on, no diffuse-reflectance output, and -- unless BCODES is set -- all six boundary
+ *              codes "unknown" (i.e. governed by isreflect alone) and no detect-on-face flags;
+ *   BCODES   common kernels that honour per-face boundary codes and detect-on-face flags (resolved in the tail block);
  *            true  = every option read from SimParam at run time.
  * ------------------------------------------------------------------------------------------------- */
 #ifndef MCXB_BLOCK
@@ -829,7 +830,7 @@ constexpr bool kSharedWindow = MCXB_GENERIC_SMEM == 0;
 constexpr int kQueueDepth = MCXB_QUEUE_DEPTH;
 static_assert(kQueueDepth > 0 && (kQueueDepth & (kQueueDepth - 1)) == 0, "queue depth must be a power of two");
 
-template <int SRC, bool REFLECT, int SAVEDET, typename MediaT, typename AccT, bool STATS, bool GEN, int QDEPTH = 0, bool EXT = false>
+template <int SRC, bool REFLECT, int SAVEDET, typename MediaT, typename AccT, bool STATS, bool GEN, int QDEPTH = 0, bool EXT = false, bool BCODES = false>
 __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLOCKS) photon_kernel(const __grid_constant__ SimParam P) {
     extern __shared__ float4 smem[];
     static_assert(QDEPTH == 0 || (!GEN && SAVEDET < 2), "the scattering queue exists for the common-configuration kernels with the default record");
@@ -1810,16 +1811,28 @@ __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLO
             }
 
             /* ------------------------------------------------------------------ leave / time out (:2957-3028) */
+            /* Per-face boundary codes (`-B`, bc[0..5]) and detect-on-face flags (bc[6..11]) in the common kernels (BCODES
+             * instantiations): the loop above attaches the code that isreflect alone implies and the explicit code replaces
+             * it here, where a packet that left the grid always arrives -- no instruction in the loop (:2806-2808).  A
+             * compile-time axis, not a run-time flag: with the extra tail code present ptxas lays the whole loop out
+             * differently, and the decks WITHOUT codes lost up to 23 % (cube60b 261.5 -> 320.9 ms, measured) */
+            constexpr bool BC = GEN || BCODES;
+
+            if (!GEN && BCODES && ph.label == 0u && (ph.idx1d == kOutsideMin || ph.idx1d == kOutsideMax)) {
+                const uint32_t code = P.bc[(ph.idx1d == kOutsideMax) * 3 + ph.face];
+                ph.detflag = ((code & 0xFu) == bcUnknown) ? (P.doreflect ? (uint32_t)bcReflect : (uint32_t)bcAbsorb) : code;
+            }
+
             const uint32_t bcode = ph.detflag & 0xFu;
 
             /* SVMC (:2962-2966): the packet stepped into the empty lower part of a voxel (through a face or through the plane) */
             const bool svexit = svmc && (ph.idx1d != oldidx || hitintf) && !(nu.sv & 0x20000u) && sv_lower(nu.sv) == 0u && (!P.doreflect || ph.n1 == n0);
 
-            if ((ph.label == 0 && (bcode == bcAbsorb || (GEN && bcode == bcCyclic) || (bcode == bcReflect && ph.n1 == n0))) || ph.tof > P.twin1 ||
+            if ((ph.label == 0 && (bcode == bcAbsorb || (BC && bcode == bcCyclic) || (bcode == bcReflect && ph.n1 == n0))) || ph.tof > P.twin1 ||
                     (kLaunchInTail && ph.w != ph.w) || svexit) {
                 bool reentered = false;
 
-                if (GEN && ph.detflag == bcCyclic) {
+                if (BC && ph.detflag == bcCyclic) {
                     /* re-enter through the opposite face (:2970-2996) */
                     if (ph.face == 0) {
                         ph.px = nudge(rintf((ph.idx1d == kOutsideMin) ? P.fnx : 0.f), (ph.vx > 0.f) - (ph.vx < 0.f));
@@ -1840,7 +1853,7 @@ __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLO
                 }
 
                 if (!reentered) {
-                    detarg = (GEN && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
+                    detarg = (BC && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
                     relaunch = true;
                 }
             } else {
@@ -1922,13 +1935,13 @@ __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLO
                     /* SVMC compares with the properties looked up on the far side of the face (:2936-2941, 3143-3147) */
                     const float n2 = svmc ? ((ph.idx1d != oldidx) ? svprop.w : nmed)
                                      : ((ph.label == oldlabel) ? nmed : medium<MediaT>(P, tab, ph.label).w);
-                    const bool mirror = GEN && bcode == bcMirror;
+                    const bool mirror = BC && bcode == bcMirror;
                     bool handle = false;
 
                     if (mirror || ph.n1 != n2) {
-                        handle = ph.label ? (!GEN || P.doreflect)
-                                 : (GEN ? ((bcode == bcUnknown && P.doreflect) || bcode == bcReflect || bcode == bcMirror)
-                                        : (bcode == bcUnknown || bcode == bcReflect));
+                        handle = ph.label ? (!BC || P.doreflect)
+                                 : (BC ? ((bcode == bcUnknown && P.doreflect) || bcode == bcReflect || bcode == bcMirror)
+                                       : (bcode == bcUnknown || bcode == bcReflect));
                     }
 
                     if (handle) {
@@ -1942,7 +1955,7 @@ __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLO
                             refract(ph.vx, ph.vy, ph.vz, ph.n1, n2, ph.face);
 
                             if (ph.label == 0) {
-                                detarg = (GEN && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
+                                detarg = (BC && ((ph.idx1d == kOutsideMax && P.bc[9 + ph.face]) || (ph.idx1d == kOutsideMin && P.bc[6 + ph.face]))) ? kOutsideMin : olddet;
                                 relaunch = true;
                             }
 
