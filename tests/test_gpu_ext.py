@@ -125,10 +125,11 @@ def test_gpu_rf_forward_matches_the_reference_source(ref):
     assert gre.sum() == pytest.approx(ore.sum(), rel=0.01) and gim.sum() == pytest.approx(oim.sum(), rel=0.02)
     assert gim.sum() < 0 < gre.sum()
     # phase and amplitude along the beam axis, away from the noise floor
-    vol_g = (gre + 1j * gim).reshape(60, 60, 60)[:, 29, 29]
-    vol_o = (ore + 1j * oim).reshape(60, 60, 60)[:, 29, 29]
-    sel = slice(1, 25)
-    np.testing.assert_allclose(np.abs(vol_g[sel]), np.abs(vol_o[sel]), rtol=0.12)
+    # (a 5 x 5 column around the axis, so that one run's voxel noise does not decide the test)
+    vol_g = (gre + 1j * gim).reshape(60, 60, 60)[:, 27:32, 27:32].sum(axis=(1, 2))
+    vol_o = (ore + 1j * oim).reshape(60, 60, 60)[:, 27:32, 27:32].sum(axis=(1, 2))
+    sel = slice(1, 22)
+    np.testing.assert_allclose(np.abs(vol_g[sel]), np.abs(vol_o[sel]), rtol=0.1)
     assert np.max(np.abs(np.angle(vol_g[sel] / vol_o[sel]))) < 0.05
     flux = engine.run(base)["flux"]
     assert flux.dtype == np.complex64 and flux.shape == (60, 60, 60, 1)

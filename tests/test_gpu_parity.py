@@ -218,7 +218,8 @@ def test_scattering_queue_kernels_are_chosen_by_medium_and_agree_with_in_place_s
     a, b = out["1"][1], out["0"][1]
     assert abs(a["absorbed"] - b["absorbed"]) < 5 * np.hypot(absorbed_sigma(10 * n, a["absorbed"]), absorbed_sigma(10 * n, b["absorbed"]))
     assert abs(a["detected"] - b["detected"]) < 5 * np.sqrt(2.0 * b["detected"])
-    assert abs(a["detp"][:, 1].mean() - b["detp"][:, 1].mean()) < 0.03 * b["detp"][:, 1].mean()      # mean partial path of the detected photons
+    pa, pb = a["detp"][:, 1].astype(np.float64), b["detp"][:, 1].astype(np.float64)                 # partial paths of the detected photons
+    assert abs(pa.mean() - pb.mean()) < 5 * np.sqrt(pa.var() / len(pa) + pb.var() / len(pb))       # (about 9000 records each, sigma of the difference ~2 %)
 
 
 def test_generic_source_kernel_equals_specialised():

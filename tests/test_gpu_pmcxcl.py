@@ -138,8 +138,9 @@ def test_rf_forward_through_the_unchanged_front_end():
     flux = res["flux"]
     assert np.iscomplexobj(flux) and flux.shape[:3] == (60, 60, 60)
     mine = engine.run(cube60(isreflect=1, issavedet=0, nphoton=500000, omega=om))["flux"]
-    axis_a, axis_b = flux.reshape(60, 60, 60, -1)[29, 29, 1:25, 0], mine[29, 29, 1:25, 0]
-    np.testing.assert_allclose(np.abs(axis_a), np.abs(axis_b), rtol=0.12)
+    # two realisations of 5e5 packets: compared on a 5 x 5 column around the beam axis
+    axis_a, axis_b = flux.reshape(60, 60, 60, -1)[27:32, 27:32, 1:22, 0].sum(axis=(0, 1)), mine[27:32, 27:32, 1:22, 0].sum(axis=(0, 1))
+    np.testing.assert_allclose(np.abs(axis_a), np.abs(axis_b), rtol=0.1)
     assert np.max(np.abs(np.angle(axis_a / axis_b))) < 0.05
     ph = np.unwrap(np.angle(axis_a))
     assert ph[0] < 0 and ph[-1] < ph[0] - 0.2                           # lagging, and more so deeper in
