@@ -437,8 +437,8 @@ static bool is_common_config(const mcxb_config* cfg, bool savedet, uint32_t npha
     const bool is3d = cfg->dimx > 1 && cfg->dimy > 1 && cfg->dimz > 1;
     return is3d && nphase <= 2 && cfg->gscatter >= 1000000000u && cfg->issaveref == 0 && !(cfg->debuglevel & (MCXB_DEBUG_MOVE | MCXB_DEBUG_MOVE_ONLY)) &&
            cfg->issave2pt != 0 && cfg->replay_seed == nullptr && cfg->srcnum <= 1 &&
-           (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE ||
-            (cfg->outputtype >= MCXB_OT_ADJOINT && cfg->outputtype <= MCXB_OT_ADJOINT_MUA_MUSP));      /* adjoint types run as fluence */
+           (cfg->outputtype == MCXB_OT_FLUX || cfg->outputtype == MCXB_OT_FLUENCE || cfg->outputtype == MCXB_OT_ENERGY || cfg->outputtype == MCXB_OT_L ||
+            (cfg->outputtype >= MCXB_OT_ADJOINT && cfg->outputtype <= MCXB_OT_ADJOINT_MUA_MUSP));      /* adjoint types run as fluence; energy / length: BCODES kernels */
 }
 
 /* the reference's rule for compiling the reflection code in (src/mcx_host.cpp:945-956) */
@@ -1087,8 +1087,10 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         anybc = anybc || cfg->bc[i] != 0;
     }
 
-    const bool hasbc = anybc && getenv("MCXB_BC_GENERIC") == nullptr;
-    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32 && !s->ext && (!anybc || hasbc);
+    /* the same kernels serve the energy and path-length outputs of an otherwise common configuration */
+    const bool richot = cfg->outputtype == MCXB_OT_ENERGY || cfg->outputtype == MCXB_OT_L;
+    const bool hasbc = (anybc || richot) && getenv("MCXB_BC_GENERIC") == nullptr;
+    const bool common = is_common_config(cfg, savedet, nphase) && !s->media32 && !s->ext && (!(anybc || richot) || hasbc);
 
     const int detmode = savedet ? (flag == 0x5u ? 1 : 2) : 0;
     /* Scattering queue (photon_kernel.cuh): pays where a packet crosses several voxels per scattering event.  Measured on

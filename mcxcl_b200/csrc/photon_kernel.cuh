@@ -785,7 +785,8 @@ __device__ __forceinline__ void update_stokes(float& sI, float& sQ, float& sU, f
  *              3-D domain, Henyey-Greenstein phase function, no gscatter switch, flux or fluence
  *              output with save2pt on, no diffuse-reflectance output, and -- unless BCODES is set -- all six boundary
  *              codes "unknown" (i.e. governed by isreflect alone) and no detect-on-face flags;
- *   BCODES   common kernels that honour per-face boundary codes and detect-on-face flags (resolved in the tail block);
+ *   BCODES   common kernels that honour per-face boundary codes and detect-on-face flags (resolved in the tail block) and
+ *            also serve the energy and path-length output types (one uniform select in the deposit);
  *            true  = every option read from SimParam at run time.
  * ------------------------------------------------------------------------------------------------- */
 #ifndef MCXB_BLOCK
@@ -1587,7 +1588,11 @@ __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLO
             /* common configuration (flux / fluence, one volume per gate): ONE divergent region instead of three nested
              * ones -- every level of nesting costs a BSSY / BRA / BSYNC triple per warp-iteration */
             const bool moved = ph.idx1d != oldidx;
-            const float weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * mufu_rcp(mua));
+            float weight = (mua < kEps) ? (ph.w0 * ph.pathlen) : ((ph.w0 - ph.w) * mufu_rcp(mua));
+
+            if (BCODES) {       /* these kernels also serve the energy and path-length outputs (:2842-2843, 2862-2864), one uniform test */
+                weight = (P.outputtype == otEnergy) ? (ph.w0 - ph.w) : ((P.outputtype == otL) ? (ph.w0 * ph.pathlen) : weight);
+            }
 
             /* nothing is deposited into a label-0 voxel (:2816: "&& mediaidold") */
             if (moved && oldlabel && ph.tof >= P.twin0 && ph.tof < P.twin1 && fabsf(weight) > 0.f) {
