@@ -625,3 +625,35 @@ def test_digimouse_multisource_timegated_full_size_energy_balance():
     early = sum(f[s, 0].astype(np.float64).sum() for s in range(4))
     late = sum(f[s, 9].astype(np.float64).sum() for s in range(4))
     assert early > 50 * late > 0
+
+
+def test_boundary_codes_and_energy_outputs_run_in_common_kernels(monkeypatch):
+    """Per-face boundary codes, detect-on-face flags and the energy / path-length outputs are served by common kernels of
+    their own (the BCODES instantiations, photon_kernel.cuh); MCXB_BC_GENERIC=1 sends the same run through the generic
+    kernel: same physics (src/mcx_core.cl:2806-2808, 2842-2843, 2862-2864, 2957-3028), two independent code paths"""
+    def both(cfg):
+        out = {}
+        for generic in (False, True):
+            if generic:
+                monkeypatch.setenv("MCXB_BC_GENERIC", "1")
+            else:
+                monkeypatch.delenv("MCXB_BC_GENERIC", raising=False)
+            p = hostcfg.prepare(cfg)
+            with engine.Simulation(p) as sim:
+                assert sim.kernel_name.endswith("/bc") != generic, sim.kernel_name
+            out[generic] = engine.run_prepared(p)
+        return out[False], out[True]
+    n = 2000000
+    for over in (dict(bc="aarraa", isreflect=0), dict(bc="______111111", isreflect=0, maxdetphoton=3000000), dict(bc="mm_rca", isreflect=1),
+                 dict(outputtype="energy"), dict(outputtype="length", bc="ar_a_r")):
+        a, b = both(dict(benchmarks.get("cube60", n), **over))
+        sig = np.hypot(absorbed_sigma(n, a["absorbed"]), absorbed_sigma(n, b["absorbed"]))
+        assert abs(a["absorbed"] - b["absorbed"]) < 5 * sig, over
+        assert abs(a["detected"] - b["detected"]) < 6 * np.sqrt(a["detected"] + b["detected"] + 1), over
+        fa, fb = a["field"].astype(np.float64), b["field"].astype(np.float64)
+        assert fa.sum() == pytest.approx(fb.sum(), rel=5e-3), over
+        big = fb > 0.01 * fb.max()
+        assert np.corrcoef(fa[big], fb[big])[0, 1] > 0.995, over
+    # one cyclic face pair: packets leave through +x and come back through -x
+    a, b = both(dict(benchmarks.get("cube60", 200000), bc="c__c__", isreflect=0))
+    assert abs(a["absorbed"] - b["absorbed"]) < 0.01
