@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "boundary_codes_and_energy" > gpurun_out/r2_pytest_ext_full.log 2>&1
-grep -E "^E  |^tests/|Error|passed|failed" gpurun_out/r2_pytest_ext_full.log | head -40; tail -3 gpurun_out/r2_pytest_ext_full.log
+for i in 1 2 3 4 5 6; do timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ext.py tests/test_gpu_svmc.py -m gpu -q -p no:cacheprovider 2>&1 | tail -1; done
