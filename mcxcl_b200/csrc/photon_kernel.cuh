@@ -749,11 +749,9 @@ __device__ __forceinline__ void save_detected(const SimParam& P, const float4* _
 /* Stokes vector after a scattering event by polar angle theta and azimuth phi (updatestokes, src/mcx_core.cl:801-835):
  * rotate into the scattering plane, apply the Mueller matrix row of this medium and angle, rotate into the new
  * meridian plane, normalise to I = 1.  (ux,uy,uz) / (nx,ny,nz) = direction before / after the event. */
-__device__ __forceinline__ void update_stokes(float& sI, float& sQ, float& sU, float& sV, float theta, float phi, float uz, float nz,
-        const float4* __restrict__ sm, uint32_t label) {
-    float s2p, c2p;
-    __sincosf(2.f * phi, &s2p, &c2p);
-    const float costheta = __cosf(theta);
+__device__ __forceinline__ void update_stokes(float& sI, float& sQ, float& sU, float& sV, float theta, float costheta, float phi, float s2p, float c2p,
+        float uz, float nz, const float4* __restrict__ sm, uint32_t label) {
+    /* costheta and sin / cos(2 phi) come from the sampling step that drew the angles (the reference recomputes them) */
     const float qi = sQ * c2p + sU * s2p, ui = -sQ * s2p + sU * c2p;
     const float4 m = __ldg(sm + (size_t)kNAngles * (label - 1u) + (uint32_t)(theta * (float)kNAngles * (0.318309886183791f - kEps)));
     const float i1 = m.x * sI + m.y * qi, q1 = m.y * sI + m.x * qi, u1 = m.z * ui + m.w * sV, v1 = -m.w * ui + m.z * sV;
@@ -1348,7 +1346,7 @@ __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLO
                 /* (a packet that carries label 0 through an in-grid empty voxel has no Mueller matrix: the reference indexes its
                  * table with label - 1 there, :2455; here such a packet scatters by the scalar phase function) */
                 const bool polar = EXT && P.maxpolmedia != 0u && !flat && ph.label - 1u < P.maxpolmedia;
-                float theta = 0.f, phi = 0.f;
+                float theta = 0.f, phi = 0.f, s2p = 0.f, c2p = 1.f;
 
                 if (polar) {
                     /* polarised light (:2454-2468): polar angle and azimuth drawn together by rejection against the
@@ -1358,18 +1356,19 @@ __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLO
                     float i0, i1;
 
                     do {
-                        theta = acosf(2.f * rng_uniform(rng) - 1.f);
+                        ctheta = 2.f * rng_uniform(rng) - 1.f;
+                        theta = acosf(ctheta);
                         phi = kTwoPi * rng_uniform(rng);
-                        float s2p, c2p;
-                        __sincosf(2.f * phi, &s2p, &c2p);
+                        __sincosf(phi, &sphi, &cphi);
+                        s2p = 2.f * sphi * cphi;            /* sin / cos of 2 phi from the pair the rotation needs anyway */
+                        c2p = cphi * cphi - sphi * sphi;
                         const float4 m = __ldg(sm + (uint32_t)(theta * (float)kNAngles * (0.318309886183791f - kEps)));
                         const float qq = sQ * c2p + sU * s2p;
                         i0 = m0.x * sI + m0.y * qq;
                         i1 = m.x * sI + m.y * qq;
                     } while (rng_uniform(rng) * i0 >= i1);
 
-                    __sincosf(phi, &sphi, &cphi);
-                    __sincosf(theta, &stheta, &ctheta);
+                    stheta = fast_sqrt(fmaxf(0.f, 1.f - ctheta * ctheta));      /* sin(acos(c)) on [0, pi] */
                 } else if (!flat) {
                     mufu_sincos(kTwoPi * rng_uniform(rng), sphi, cphi);
                 }
@@ -1427,7 +1426,7 @@ __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLO
                 ph.nscat++;
 
                 if (polar) {
-                    update_stokes(sI, sQ, sU, sV, theta, phi, olduz, ph.vz, P.smatrix, ph.label);
+                    update_stokes(sI, sQ, sU, sV, theta, ctheta, phi, s2p, c2p, olduz, ph.vz, P.smatrix, ph.label);
                 }
 
                 if (GEN && P.trajdata) {      /* every scattering site (:2625-2632) */
