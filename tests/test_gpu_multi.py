@@ -57,7 +57,7 @@ def test_nccl_photon_shards_combine_on_rank0(tmp_path):
     assert res["shares"] == [300001, 100000]                        # workload 3:1, remainder to the first rank
     assert res["energytot"] == 400001                               # every packet launched exactly once over the two ranks
     one = engine.run(benchmarks.get("cube60b", 400001))["stat"]
-    assert abs(res["absorbed"] - one["absorbed"]) < 0.004
+    assert abs(res["absorbed"] - one["absorbed"]) < 0.008        # two runs of 4e5 packets: sigma of the difference 1.5e-3
     assert abs(res["detected"] - one["detected"]) < 6 * np.sqrt(2 * one["detected"])
     assert res["saved"] == res["detected"] == sum(res["ndet"]) == res["nseeds"] == res["uniqseeds"]
     assert res["rawsum"] * 0.005 == pytest.approx(res["energyabs"], rel=2e-3)      # sum(field)*mua == absorbed energy
@@ -88,7 +88,7 @@ def test_multi_gpu_call_behind_the_c_abi(exchange, monkeypatch):
     raw = r["field"].astype(np.float64) / r["normalizer"]
     assert raw.sum() * 0.005 == pytest.approx(r["energyabs"], rel=2e-3)      # sum(field) * mua == absorbed energy
     one = engine.run_prepared(p)
-    assert abs(r["absorbed"] - one["absorbed"]) < 0.004
+    assert abs(r["absorbed"] - one["absorbed"]) < 0.008
     assert abs(r["detected"] - one["detected"]) < 6 * np.sqrt(2 * one["detected"])
     assert r["normalizer"] == pytest.approx(one["normalizer"], rel=1e-6)
     # equal shares by default, records clipped at maxdetphoton like the reference (src/mcx_host.cpp:1207-1216)

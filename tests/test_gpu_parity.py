@@ -90,7 +90,10 @@ def test_quicktest_deck_matches_reference(ref):
     mean, std = f.mean(0), f.std(0, ddof=1)
     p, r = run_gpu(benchmarks.get("qtest", 1000000))
     assert r["energytot"] == 1000000
-    assert abs(r["absorbed"] - np.mean(absd)) / np.mean(absd) < 0.005
+    # the 0.5 % criterion on a run large enough that its own noise (0.05 %) does not decide it
+    big = run_gpu(benchmarks.get("qtest", 10000000))[1]
+    assert abs(big["absorbed"] - np.mean(absd)) / np.mean(absd) < 0.005
+    assert abs(r["absorbed"] - np.mean(absd)) < 5 * absorbed_sigma(1000000, r["absorbed"])
     want = np.mean(det) * 5
     assert abs(r["detected"] - want) < 5 * np.sqrt(want * (1 + 5.0 / runs))
     assert set(np.unique(r["detp"][:, 0]).astype(int)) == {1, 2, 3, 4} and r["reclen"] == 2
@@ -354,7 +357,7 @@ def test_russian_roulette_matches_reference(ref):
     cfg["minenergy"] = 0.01                                       # example/skinvessel/run_mcxyz_bench.sh: -e 0.01
     p, r = run_gpu(cfg)
     _, o = run_ref(ref, cfg)
-    assert abs(r["absorbed"] - o["absorbed"]) < 0.012
+    assert abs(r["absorbed"] - o["absorbed"]) < 5 * np.hypot(absorbed_sigma(cfg["nphoton"], r["absorbed"]), absorbed_sigma(cfg["nphoton"], o["absorbed"]))
     # compared as deposited ENERGY per medium (field * mua).  The raw field sum is not a usable statistic here: a
     # packet that survives the roulette has its weight multiplied by 10 without w0 being touched (reference
     # :3032-3034), so its next deposit is (w0 - 10 w)/mua < 0; when that happens inside the nearly transparent gel
@@ -435,7 +438,7 @@ def test_trajectories_match_reference(ref):
     assert abs(np.median(g["z"]) - np.median(w["z"])) < 0.05 * np.median(w["z"])
     assert abs(g["w_end"].mean() - w["w_end"].mean()) < 5 * np.hypot(g["w_end"].std(), w["w_end"].std()) / np.sqrt(n)
     # the volume is still produced with -D M ...
-    assert abs(r["absorbed"] - o["absorbed"]) < 0.03 and r["field"].sum() > 0
+    assert abs(r["absorbed"] - o["absorbed"]) < 5 * np.hypot(absorbed_sigma(n, r["absorbed"]), absorbed_sigma(n, o["absorbed"])) and r["field"].sum() > 0
     # ... and not with -D T; the buffer limit is honoured and the overflow reported
     p2, r2 = run_gpu(dict(cfg, debuglevel="T", maxjumpdebug=1000))
     assert r2["traj"].shape == (1000, 6) and r2["traj_recorded"] > 1000
@@ -461,7 +464,7 @@ def test_two_dimensional_domain(ref):
                isreflect=1, issavedet=0)
     p, r = run_gpu(cfg)
     _, o = run_ref(ref, cfg)
-    assert abs(r["absorbed"] - o["absorbed"]) < 0.012
+    assert abs(r["absorbed"] - o["absorbed"]) < 5 * np.hypot(absorbed_sigma(cfg["nphoton"], r["absorbed"]), absorbed_sigma(cfg["nphoton"], o["absorbed"]))
     assert ("%.1f" % (100 * o["absorbed"]))[0] == "6"               # the reference's pin: absorbed 6x.x%
     assert ("%.1f" % (100 * r["absorbed"]))[0] == "6"
 
@@ -473,7 +476,7 @@ def test_multi_source_modes(ref):
         p, r = run_gpu(cfg)
         _, o = run_ref(ref, cfg)
         assert p.nsrcvol == (3 if srcid < 0 else 1)
-        assert abs(r["absorbed"] - o["absorbed"]) < 0.008
+        assert abs(r["absorbed"] - o["absorbed"]) < 5 * np.hypot(absorbed_sigma(90000, r["absorbed"]), absorbed_sigma(90000, o["absorbed"]))
         gf = raw_field(p, r).reshape(p.nsrcvol, -1)
         of = o["field"].astype(np.float64).reshape(p.nsrcvol, -1)
         np.testing.assert_allclose(gf.sum(1), of.sum(1), rtol=0.04)
@@ -560,7 +563,7 @@ def test_fp32_and_fp64_accumulators_agree_at_moderate_counts():
     a = run_gpu(decks.cube(nphoton=300000, accum="f64"))[1]
     b = run_gpu(decks.cube(nphoton=300000, accum="f32"))[1]
     np.testing.assert_allclose(a["field"].astype(np.float64).sum(), b["field"].astype(np.float64).sum(), rtol=0.01)
-    assert abs(a["absorbed"] - b["absorbed"]) < 0.005
+    assert abs(a["absorbed"] - b["absorbed"]) < 5 * np.hypot(absorbed_sigma(300000, a["absorbed"]), absorbed_sigma(300000, b["absorbed"]))
 
 
 def test_full_size_properties_cube60b_1e8():
@@ -600,7 +603,7 @@ def test_digimouse_multisource_timegated_against_reference_source(ref):
     mua = p.keep["prop"][:, 0].astype(np.float64)[p.keep["vol"] & 0x7FFFFFFF]
     assert (g * mua).sum() == pytest.approx(r["energyabs"], rel=3e-3)     # deposits are (w0-w)/mua: the ledger balances
     o = ref.run(hostcfg.prepare(dict(cfg, nphoton=20000)), 2048, hostthreads=2)
-    assert abs(r["absorbed"] - o["absorbed"]) < 0.012
+    assert abs(r["absorbed"] - o["absorbed"]) < 5 * absorbed_sigma(20000, o["absorbed"])
     of = o["field"].astype(np.float64).reshape(2, 2, -1) * 10
     for s in range(2):
         for t in range(2):
