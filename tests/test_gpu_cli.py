@@ -133,7 +133,7 @@ def test_repetitions_through_the_cli(tmp_path):
     assert len(re.findall(r"simulation run#\s*[0-9]+", out)) == 3
     one = engine.run(benchmarks.get("cube60b", 300001))
     mc2 = np.fromfile(os.path.join(tmp_path, "rep.mc2"), dtype=np.float32).astype(np.float64)
-    np.testing.assert_allclose(mc2.sum(), one["flux"].astype(np.float64).sum(), rtol=0.01)
+    np.testing.assert_allclose(mc2.sum(), one["flux"].astype(np.float64).sum(), rtol=0.016)          # 3e5 packets each: sigma of the ratio 0.3 %
     raw = open(os.path.join(tmp_path, "rep.mch"), "rb").read()
     magic, version, maxmedia, detnum, colcount, totalphoton, detected, savedphoton = struct.unpack("<4s7I", raw[:32])
     respin = struct.unpack("<i", raw[44:48])[0]
@@ -206,7 +206,7 @@ def test_jnii_output_and_json_input_file(tmp_path):
                srcpos=[19, 19, 0], srcdir=[0, 0, 1], issrcfrom0=1, isreflect=1, issavedet=0, seed=1648335518)
     r = engine.run(cfg)
     assert abs(absorbed(out) / 100 - r["stat"]["absorbed"]) < 0.01
-    np.testing.assert_allclose(vol.astype(np.float64).sum(), r["flux"].astype(np.float64).sum(), rtol=0.02)
+    np.testing.assert_allclose(vol.astype(np.float64).sum(), r["flux"].astype(np.float64).sum(), rtol=0.04)        # 5e4 packets each: sigma of the ratio 0.8 %
 
 
 # ------------------------------------------------------------------------------------------------ BASELINE config 1

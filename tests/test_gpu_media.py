@@ -72,7 +72,7 @@ def test_continuous_media_equal_the_label_run_they_encode():
     _, b = run_gpu(dict(base, vol=np.full((1, 60, 60, 60), 0.005, np.float32)))
     sig = absorbed_sigma(N, a["absorbed"])
     assert abs(a["absorbed"] - b["absorbed"]) < 5 * np.sqrt(2.0) * sig
-    np.testing.assert_allclose(b["field"].astype(np.float64).sum(), a["field"].astype(np.float64).sum(), rtol=0.01)
+    np.testing.assert_allclose(b["field"].astype(np.float64).sum(), a["field"].astype(np.float64).sum(), rtol=0.02)     # 2e5 packets each: sigma of the ratio 0.4 %
 
 
 def test_continuous_media_with_detectors_and_refusals():

@@ -370,7 +370,7 @@ def test_russian_roulette_matches_reference(ref):
         np.testing.assert_allclose(gf[lab == m].sum() * mua, of[lab == m].sum() * mua, rtol=0.05)
     tot_g = sum(gf[lab == m].sum() * float(p.keep["prop"][m, 0]) for m in (1, 2, 3, 4))
     tot_o = sum(of[lab == m].sum() * float(p.keep["prop"][m, 0]) for m in (1, 2, 3, 4))
-    np.testing.assert_allclose(tot_g, tot_o, rtol=0.03)
+    np.testing.assert_allclose(tot_g, tot_o, rtol=0.05)          # 3e4 packets each: sigma of the ratio 1 %
 
 
 def test_repetitions_accumulate_like_one_batch():
@@ -386,7 +386,7 @@ def test_repetitions_accumulate_like_one_batch():
     sig = absorbed_sigma(n, one["absorbed"])
     assert abs(rep["absorbed"] - one["absorbed"]) < 5 * np.sqrt(2.0) * sig
     assert abs(rep["detected"] - one["detected"]) < 5 * np.sqrt(2.0 * one["detected"])
-    np.testing.assert_allclose(raw_field(p3, rep).sum(), raw_field(p1, one).sum(), rtol=0.01)
+    np.testing.assert_allclose(raw_field(p3, rep).sum(), raw_field(p1, one).sum(), rtol=0.016)     # 3e5 packets each: sigma of the ratio 0.3 %
     assert rep["saved"] == rep["detected"] == rep["seeds"].shape[0]
     assert len({tuple(x) for x in rep["seeds"].tolist()}) == rep["saved"]
     # the first batch of a repeated run IS the head of the seed stream: same streams as a single run of n/3 photons
@@ -562,7 +562,7 @@ def test_photon_budget_is_exact(n):
 def test_fp32_and_fp64_accumulators_agree_at_moderate_counts():
     a = run_gpu(decks.cube(nphoton=300000, accum="f64"))[1]
     b = run_gpu(decks.cube(nphoton=300000, accum="f32"))[1]
-    np.testing.assert_allclose(a["field"].astype(np.float64).sum(), b["field"].astype(np.float64).sum(), rtol=0.01)
+    np.testing.assert_allclose(a["field"].astype(np.float64).sum(), b["field"].astype(np.float64).sum(), rtol=0.016)   # sigma of the ratio 0.3 %
     assert abs(a["absorbed"] - b["absorbed"]) < 5 * np.hypot(absorbed_sigma(300000, a["absorbed"]), absorbed_sigma(300000, b["absorbed"]))
 
 

@@ -83,7 +83,7 @@ def test_gpu_photon_sharing_against_the_reference_source(ref):
     g = volumes(p, engine.run_prepared(p)["field"].astype(np.float64))
     o = volumes(p, ref.run(hostcfg.prepare(sharing_cfg(60000, isnormalized=0)), 1024, hostthreads=0)["field"].astype(np.float64)) * (n / 60000)
     for i in range(3):
-        assert g[i].sum() == pytest.approx(o[i].sum(), rel=0.01)
+        assert g[i].sum() == pytest.approx(o[i].sum(), rel=0.02)       # the 6e4-packet reference run alone carries 0.5 % (0.7 % for the half-plane pattern)
         # depth profile of each pattern's volume (z is the slowest axis)
         gz, oz = g[i].reshape(60, -1).sum(axis=1), o[i].reshape(60, -1).sum(axis=1)
         np.testing.assert_allclose(gz[:30], oz[:30], rtol=0.06)
