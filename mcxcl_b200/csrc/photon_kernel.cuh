@@ -209,13 +209,27 @@ __device__ __forceinline__ bool voxel_in_grid(const SimParam& P, int ix, int iy,
  * march a packet launched outside the volume (or inside a zero voxel) up to the first non-zero voxel
  * (src/mcx_core.cl:1350-1455).  Returns the linear index of the entry voxel or -1.
  * ------------------------------------------------------------------------------------------------- */
-#ifdef MCXB_EXP_NOCALL
-    #define MCXB_ENTER_INLINE __forceinline__
-#else
-    #define MCXB_ENTER_INLINE __noinline__
-#endif
+/* inlined in the common and the extended kernels: as a real call it made every launch from outside the volume pay the ABI
+ * (digimouse 353.1 -> 338.1 ms at 3e7 photons, cube60b 261.6 -> 258.1; profiles/r2_sweep_enter_inline.log).  The generic
+ * kernels keep the call: inlined, their register allocation got worse (cube60b gscatter deck 42.0 -> 43.1 ms).
+ * -DMCXB_ENTER_CALL restores the call everywhere (A/B). */
 template <typename MediaT>
-__device__ MCXB_ENTER_INLINE int enter_volume(const SimParam& P, const float4* __restrict__ tab, Photon& ph) {
+__device__ __forceinline__ int enter_volume_body(const SimParam& P, const float4* __restrict__ tab, Photon& ph);
+template <typename MediaT>
+__device__ __noinline__ int enter_volume_call(const SimParam& P, const float4* __restrict__ tab, Photon& ph) {
+    return enter_volume_body<MediaT>(P, tab, ph);
+}
+template <typename MediaT, bool CALL>
+__device__ __forceinline__ int enter_volume(const SimParam& P, const float4* __restrict__ tab, Photon& ph) {
+#ifdef MCXB_ENTER_CALL
+    return enter_volume_call<MediaT>(P, tab, ph);
+#else
+    if constexpr (CALL) return enter_volume_call<MediaT>(P, tab, ph);
+    else return enter_volume_body<MediaT>(P, tab, ph);
+#endif
+}
+template <typename MediaT>
+__device__ __forceinline__ int enter_volume_body(const SimParam& P, const float4* __restrict__ tab, Photon& ph) {
     const MediaT* __restrict__ media = static_cast<const MediaT*>(P.media);
     int count = 1;
     ph.ix = (int)(short)floorf(ph.px);
@@ -1183,10 +1197,10 @@ __global__ void __launch_bounds__(kBlock, EXT ? MCXB_EXT_MINBLOCKS : MCXB_MINBLO
                 }
 
                 if (rawlabel == 0) {
-                    /* the marcher takes the packet by reference and is not inlined: hand it a copy so that the
-                     * live packet state never has its address taken and stays in registers */
+                    /* the marcher takes the packet by reference: hand it a copy so that the live packet state never has its
+                     * address taken and stays in registers (inlined except in the generic kernels, see enter_volume) */
                     Photon tmp = ph;
-                    const int idx = enter_volume<MediaT>(P, tab, tmp);
+                    const int idx = enter_volume<MediaT, GEN && !EXT>(P, tab, tmp);
                     ph = tmp;
 
                     if (idx >= 0) {

@@ -6,4 +6,11 @@ for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); print('  %-45s %8.2f ms' % (d['case'], min(d['ms'])))
 "
-for i in 1 2 3; do timeout 900 python -m pytest tests/test_gpu_ext.py tests/test_gpu_pmcxcl.py tests/test_gpu_cli.py -m gpu -q -p no:cacheprovider -k "polar" 2>&1 | tail -1; done
+timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -2
+python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err; echo bench rc $?
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_final_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline'], d.get('parity'))
+for k,v in d.get('extra',{}).items(): print(k, v.get('value'), v.get('e2e',{}).get('value') if isinstance(v.get('e2e'),dict) else v.get('e2e'))
+PY
