@@ -54,6 +54,28 @@ int main(void) {
     assert offs == [getattr(abi.Output, f).offset for f in ("energytot", "kernel_launches", "stats")]
 
 
+def test_ctypes_mirror_matches_every_field_offset():
+    """every member of every struct the Python mirror declares sits where the C header puts it (offset and size), so a
+    field appended on one side only cannot go unnoticed"""
+    pairs = [("mcxb_config", abi.Config), ("mcxb_output", abi.Output), ("mcxb_gpuinfo", abi.GPUInfo), ("mcxb_trace_step", abi.TraceStep),
+             ("mcxb_source", abi.Source)]
+    body = []
+    for cname, cls in pairs:
+        for fname, _ in cls._fields_:
+            body.append('printf("%%zu %%zu\\n", offsetof(%s, %s), sizeof(((%s*)0)->%s));' % (cname, fname, cname, fname))
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "mcxb200.h"\nint main(void) {\n' + "\n".join(body) + "\nreturn 0;\n}\n"
+    with tempfile.TemporaryDirectory() as d:
+        cfile = os.path.join(d, "t.c")
+        open(cfile, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), cfile, "-o", exe])
+        got = [tuple(int(x) for x in ln.split()) for ln in subprocess.check_output([exe]).decode().split("\n") if ln]
+    want = [(getattr(cls, fname).offset, getattr(cls, fname).size) for _, cls in pairs for fname, _ in cls._fields_]
+    names = ["%s.%s" % (cname, fname) for cname, cls in pairs for fname, _ in cls._fields_]
+    assert len(got) == len(want)
+    assert [n for n, g, w in zip(names, got, want) if g != w] == []
+
+
 def test_seed_table_is_glibc_rand(lib):
     """src/mcx_host.cpp:696-700, 759-768: srand(seed); seeds[i] = rand().  Compared with the C library itself."""
     libc = C.CDLL("libc.so.6")
