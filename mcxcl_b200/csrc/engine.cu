@@ -150,7 +150,10 @@ struct BufferPool {
             if (e != cudaSuccess) {
                 /* make room and try once more */
                 cudaGetLastError();
-                drop_locked();
+                int cur = 0;
+                cudaGetDevice(&cur);
+                drop_locked();              /* frees on every device it holds buffers of */
+                cudaSetDevice(cur);
                 e = host ? cudaMallocHost(out, bytes) : cudaMalloc(out, bytes);
 
                 if (e != cudaSuccess) {

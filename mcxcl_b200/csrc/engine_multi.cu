@@ -85,7 +85,8 @@ Nccl& nccl() {
         }
 
         if (!x->handle) {
-            x->why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "");
+            const char* why = dlerror();        /* a second call would return NULL: dlerror() clears the message it hands out */
+            x->why = std::string("libnccl.so.2 not found: ") + (why ? why : "");
             return x;
         }
 
@@ -152,6 +153,7 @@ int get_comms(const std::vector<int>& devs, CommSet** out) {
 
         if (cudaStreamCreateWithFlags(&cs->stream[i], cudaStreamNonBlocking) != cudaSuccess ||
                 cudaMalloc(&cs->counts[i], sizeof(uint32_t) * devs.size()) != cudaSuccess) {
+            /* the communicators stay alive (ncclCommDestroy on a half-built set can hang); the set is simply not cached */
             return fail(MCXB_ERR_NOMEM, "cannot allocate the multi-GPU exchange buffers on device %d", devs[i]);
         }
     }
