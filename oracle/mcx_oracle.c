@@ -1,5 +1,6 @@
 /*
- * mcx_oracle.c -- plain-C restatement of MCX-CL's photon-transport kernel for label media
+ * mcx_oracle.c -- plain-C restatement of MCX-CL's photon-transport kernel for label media and the continuous media
+ * formats (Config.mediabyte 99-104)
  * (TEST INFRASTRUCTURE ONLY: nothing under mcxcl_b200/ may load, link or call this file; only
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do).
  *
@@ -8,6 +9,7 @@
  *   detector search / records  :838-926
  *   mcx_nextafterf, hitgrid    :965-995        (OpenCL branch of hitgrid, :988-989)
  *   rotate*, transmit, Fresnel :997-1075
+ *   updateproperty             :1079-1193      label rows and the word decoders of MED_TYPE 99-104
  *   skipvoid                   :1350-1455
  *   launchnewphoton            :1466-2275      all 18 source types, multi-source pick, launch-angle table,
  *                                              focal-length / isotropic / Lambertian launch
@@ -15,7 +17,7 @@
  *                                              spill, termination, cyclic bc, roulette, reflection
  *   host side                  src/mcx_host.cpp:494-524, 674-700, 759-768, 1011-1012 (parameter block, seeding,
  *                              threadphoton/oddphoton), :1252-1306 (fold shadow half, energy sums)
- * Not restated (outside SURVEY.md section 8a): SVMC and continuous media formats, polarised light, replay /
+ * Not restated (outside SURVEY.md section 8a): SVMC and two-word media, polarised light, replay /
  * Jacobian / RF outputs, adjoint sources, trajectory debug, issaveref > 1.
  *
  * Numeric contract: IEEE binary32, no FMA contraction (build with -ffp-contract=off), the OpenCL native_*
@@ -71,6 +73,7 @@ typedef struct {
     int oddphoton;
     uint32_t debuglevel, savedetflag, reclen, partialdata, w0offset, gscatter, is2d, srcnum, extrasrclen;
     uint32_t nphase, nphaselen, nangle, nanglelen;
+    uint32_t mediaformat;                        /* MED_TYPE of the reference's build: 1 (labels) or 99..104 (:541-546) */
     int doreflection;                            /* MCX_DO_REFLECTION compiled in (src/mcx_host.cpp:945-956) */
     unsigned char bc[12];
     const f4* gproperty;                         /* media rows, then 4 rows per extra source (src/mcx_host.cpp:746-751) */
@@ -452,6 +455,86 @@ static int skipvoid(const param_t* g, sink_t* s, f4* p, f4* v, f4* f, s4* flipdi
 /* -------------------------------------------------------------------- launchnewphoton :1466-2275 */
 
 /* launch-time media lookup shared by the area sources (:1752-1758) */
+/* binary16 storage bits widened exactly to binary32 (what vload_half / convert_float of cl_khr_fp16 do) */
+static float half_bits_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1Fu, m = h & 0x3FFu, out;
+
+    if (e == 0x1Fu) {
+        out = sign | 0x7F800000u | (m << 13);
+    } else if (e) {
+        out = sign | ((e + 112u) << 23) | (m << 13);
+    } else if (m) {
+        e = 113u;
+
+        while (!(m & 0x400u)) {
+            m <<= 1;
+            e--;
+        }
+
+        out = sign | (e << 23) | ((m & 0x3FFu) << 13);
+    } else {
+        out = sign;
+    }
+
+    float f;
+    memcpy(&f, &out, 4);
+    return f;
+}
+
+/* updateproperty (:1079-1193): the optical properties of a voxel from its media word.  Label volumes read a row of the
+ * table; the continuous formats decode the word and leave the members they do not carry as they are (prop starts as
+ * row 1 at every launch, :2213) */
+static void update_property(const param_t* g, f4* prop, uint32_t mediaid) {
+    const uint32_t w = mediaid & MED_MASK;
+    float mf;
+
+    switch (g->mediaformat) {
+        case 101:      /* MEDIA_MUA_FLOAT (:1093-1096) */
+            memcpy(&mf, &mediaid, 4);
+            prop->x = fabsf(mf);
+            prop->w = g->gproperty[w != 0].w;
+            break;
+
+        case 100:      /* MEDIA_AS_F2H */
+        case 102:      /* MEDIA_AS_HALF (:1103-1123) */
+            prop->x = fabsf(half_bits_to_float((uint16_t)(w & 0xFFFFu)));
+            prop->y = fabsf(half_bits_to_float((uint16_t)(w >> 16)));
+            prop->w = g->gproperty[w != 0].w;
+            break;
+
+        case 99: {     /* MEDIA_LABEL_HALF (:1130-1151): a label row with one member replaced */
+            const uint32_t lo = w & 0xFFFFu;
+            float member[4];
+            *prop = g->gproperty[lo & 0x3FFFu];
+            memcpy(member, prop, sizeof(member));
+            member[(lo & 0xC000u) >> 14] = fabsf(half_bits_to_float((uint16_t)(w >> 16)));
+            memcpy(prop, member, sizeof(member));
+            break;
+        }
+
+        case 103: {    /* MEDIA_ASGN_BYTE (:1157-1169): bytes scale between rows 1 and 2 */
+            const f4 lo = g->gproperty[1], hi = g->gproperty[2];
+            prop->x = (float)(w & 0xFFu) * (1.f / 255.f) * (hi.x - lo.x) + lo.x;
+            prop->y = (float)((w >> 8) & 0xFFu) * (1.f / 255.f) * (hi.y - lo.y) + lo.y;
+            prop->z = (float)((w >> 16) & 0xFFu) * (1.f / 255.f) * (hi.z - lo.z) + lo.z;
+            prop->w = (float)((w >> 24) & 0xFFu) * (1.f / 127.f) * (hi.w - lo.w) + lo.w;
+            break;
+        }
+
+        case 104: {    /* MEDIA_AS_SHORT (:1176-1186) */
+            const f4 lo = g->gproperty[1], hi = g->gproperty[2];
+            prop->x = (float)(w & 0xFFFFu) * (1.f / 65535.f) * (hi.x - lo.x) + lo.x;
+            prop->y = (float)(w >> 16) * (1.f / 65535.f) * (hi.y - lo.y) + lo.y;
+            prop->w = g->gproperty[w != 0].w;
+            break;
+        }
+
+        default:       /* label volumes (:1086) */
+            *prop = g->gproperty[w];
+    }
+}
+
 static void locate(const param_t* g, item_t* it) {
     it->idx1d = (uint32_t)((int)floorf(it->p.z)) * g->dimxy + (uint32_t)((int)floorf(it->p.y)) * g->dimx + (uint32_t)((int)floorf(it->p.x));
     it->mediaid = outside_f(g, &it->p) ? 0u : g->media[it->idx1d];
@@ -897,7 +980,8 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
 
     /* :2212-2255 */
     f->w += 1.f;
-    *prop = g->gproperty[it->mediaid & MED_MASK];
+    *prop = g->gproperty[1];
+    update_property(g, prop, it->mediaid);
     ppath[1] += p->w;
     it->w0 = p->w;
     ppath[2] = (g->srcnum > 1) ? ppath[2] : p->w;
@@ -1026,7 +1110,7 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
 
         /* ---- one ray segment (:2652-2765) ---- */
         n1 = prop->w;
-        *prop = g->gproperty[it.mediaid & MED_MASK];
+        update_property(g, prop, it.mediaid);
         f->z = hitgrid(s, p, v, flipdir);
         float slen = f->z * prop->y * (v->w + 1.f > (float)g->gscatter ? (1.f - prop->z) : 1.f);
         slen = fminf(slen, f->x);
@@ -1165,11 +1249,13 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
 
         /* ---- refractive-index mismatch (:3063-3297), compiled in under MCX_DO_REFLECTION ---- */
         if (g->doreflection) {
-            *prop = g->gproperty[it.mediaid & MED_MASK];
+            update_property(g, prop, it.mediaid);
+            /* the index on the far side: the decoded one up to format 99, row 1 (row 0 outside) of the table from 100 on (:3147) */
+            const float nfar = (g->mediaformat < 100) ? prop->w : g->gproperty[it.mediaid > 0 ? 1 : 0].w;
 
             if (((it.mediaid && g->doreflect)
                     || (it.mediaid == 0 && (((isdet & 0xF) == bcUnknown && g->doreflect) || ((isdet & 0xF) == bcReflect || (isdet & 0xF) == bcMirror))))
-                    && (((isdet & 0xF) == bcMirror) || n1 != prop->w)) {
+                    && (((isdet & 0xF) == bcMirror) || n1 != nfar)) {
                 float Rtotal = 1.f;
                 float cphi, sphi, stheta, ctheta;
                 const float tmp0 = n1 * n1;
@@ -1218,7 +1304,7 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
 
                     it.idx1d = idx1dold;
                     it.mediaid = g->media[it.idx1d] & MED_MASK;
-                    *prop = g->gproperty[it.mediaid & MED_MASK];
+                    update_property(g, prop, it.mediaid);
                     n1 = prop->w;
                 }
             }
@@ -1281,8 +1367,15 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
         return -3;      /* photon replay is not restated here: oracle/_ref (the reference source itself) checks it */
     }
 
-    if (cfg->mediaformat > 4 || cfg->polmedianum || cfg->omega > 0.f || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
-        return -3;      /* continuous / split-voxel media, polarised light, RF and adjoint runs: checked by oracle/_ref only */
+    const int continuous = cfg->mediaformat >= 99 && cfg->mediaformat <= 104;
+
+    if ((cfg->mediaformat > 4 && !continuous) || cfg->polmedianum || cfg->omega > 0.f || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
+        return -3;      /* split-voxel / two-word media, polarised light, RF and adjoint runs: checked by oracle/_ref only */
+    }
+
+    if (continuous && ((cfg->issavedet && (cfg->savedetflag & 0x0Eu)) || cfg->isspecular > 0 || cfg->srcnum > 1 ||
+                       ((cfg->mediaformat == 103 || cfg->mediaformat == 104) && cfg->medianum < 3))) {
+        return -3;      /* the reference indexes per-medium rows with the media WORD there (:1425, 2515, 2787): nothing defined to restate */
     }
 
     param_t g;
@@ -1292,6 +1385,7 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
     g.dimxy = cfg->dimx * cfg->dimy;
     g.dimxyz = g.dimxy * cfg->dimz;
     g.maxgate = (uint32_t)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);       /* src/mcx_host.cpp:647 */
+    g.mediaformat = continuous ? cfg->mediaformat : 1u;
     g.srcnum = cfg->srcnum ? cfg->srcnum : 1;
     const uint32_t nsrcvol = (cfg->srctype == MCXB_SRC_PATTERN || cfg->srctype == MCXB_SRC_PATTERN3D) ? g.srcnum
                              : ((cfg->srcid < 0) ? (cfg->extrasrclen + 1) : 1);

@@ -3,7 +3,7 @@ conditions, gates, detectors).  The physics follows the reference's own test com
 (test/testmcx.sh:60-132) and example decks where one exists."""
 import numpy as np
 
-from mcxcl_b200 import benchmarks
+from mcxcl_b200 import benchmarks, hostcfg
 
 
 def cube(nphoton=1e5, **kw):
@@ -103,3 +103,39 @@ def many_labels(nphoton=1e5, **kw):
     cfg.update(vol=vol, prop=prop)
     cfg.update(kw)
     return cfg
+
+
+# ---- continuous media (Config.mediabyte 99-104): volumes whose words encode the optical properties, packed by hostcfg like pmcxcl ----
+MEDIA_PROP2 = [[0, 0, 1, 1], [0.005, 1.0, 0.01, 1.37]]
+MEDIA_PROP3 = [[0, 0, 1, 1], [0.0, 0.0, 0.01, 1.0], [0.02, 5.0, 0.9, 1.5]]          # rows 1 and 2 = the range of the scaled formats
+
+
+def media_two_regions():
+    """mua / mus maps: a 60^3 cube with a more absorbing, more scattering slab at z = 20..39"""
+    mua = np.full((60, 60, 60), 0.005, np.float32)
+    mus = np.full((60, 60, 60), 1.0, np.float32)
+    mua[:, :, 20:40] = 0.015
+    mus[:, :, 20:40] = 2.5
+    return mua, mus
+
+
+def media_volumes():
+    mua, mus = media_two_regions()
+    out = {}
+    out["mua_float"] = (mua[None], MEDIA_PROP2, hostcfg.MEDIA_MUA_FLOAT)
+    out["as_f2h"] = (np.stack([mua, mus]), MEDIA_PROP2, hostcfg.MEDIA_AS_F2H)
+    lh = np.zeros((3, 60, 60, 60), np.float32)            # {value, slot, label}: mua of label 1 replaced inside the slab
+    lh[0], lh[1], lh[2] = mua, 0, 1
+    out["label_half"] = (lh, MEDIA_PROP2, hostcfg.MEDIA_LABEL_HALF)
+    b = np.zeros((4, 60, 60, 60), np.uint8)                # bytes scale between PROP3 rows 1 and 2
+    b[0] = np.round(mua / 0.02 * 255)
+    b[1] = np.round(mus / 5.0 * 255)
+    b[2] = 0
+    b[3] = 94                                              # n = 1 + 94/127 * 0.5 = 1.37
+    b[3, :, :, 20:40] = 127                                # ... and 1.5 inside the slab: interior Fresnel faces
+    out["asgn_byte"] = (b, MEDIA_PROP3, hostcfg.MEDIA_ASGN_BYTE)
+    sh = np.zeros((2, 60, 60, 60), np.uint16)
+    sh[0] = np.round(mua / 0.02 * 65535)
+    sh[1] = np.round(mus / 5.0 * 65535)
+    out["as_short"] = (sh, [[0, 0, 1, 1], [0.0, 0.0, 0.01, 1.37], [0.02, 5.0, 0.01, 1.37]], hostcfg.MEDIA_AS_SHORT)
+    return out

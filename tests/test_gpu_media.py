@@ -4,44 +4,13 @@ with the same -DMED_TYPE (oracle/_ref).  The words are packed like pmcxcl packs 
 import numpy as np
 import pytest
 
+import decks
 from mcxcl_b200 import benchmarks, engine, hostcfg
 from util import absorbed_sigma, run_gpu, run_ref
 
 pytestmark = pytest.mark.gpu
 N = 200000
-PROP2 = [[0, 0, 1, 1], [0.005, 1.0, 0.01, 1.37]]
-PROP3 = [[0, 0, 1, 1], [0.0, 0.0, 0.01, 1.0], [0.02, 5.0, 0.9, 1.5]]          # rows 1 and 2 = the range of the scaled formats
-
-
-def two_regions():
-    """mua / mus maps: a 60^3 cube with a more absorbing, more scattering slab at z = 20..39"""
-    mua = np.full((60, 60, 60), 0.005, np.float32)
-    mus = np.full((60, 60, 60), 1.0, np.float32)
-    mua[:, :, 20:40] = 0.015
-    mus[:, :, 20:40] = 2.5
-    return mua, mus
-
-
-def volumes():
-    mua, mus = two_regions()
-    out = {}
-    out["mua_float"] = (mua[None], PROP2, hostcfg.MEDIA_MUA_FLOAT)
-    out["as_f2h"] = (np.stack([mua, mus]), PROP2, hostcfg.MEDIA_AS_F2H)
-    lh = np.zeros((3, 60, 60, 60), np.float32)            # {value, slot, label}: mua of label 1 replaced inside the slab
-    lh[0], lh[1], lh[2] = mua, 0, 1
-    out["label_half"] = (lh, PROP2, hostcfg.MEDIA_LABEL_HALF)
-    b = np.zeros((4, 60, 60, 60), np.uint8)                # bytes scale between PROP3 rows 1 and 2
-    b[0] = np.round(mua / 0.02 * 255)
-    b[1] = np.round(mus / 5.0 * 255)
-    b[2] = 0
-    b[3] = 94                                              # n = 1 + 94/127 * 0.5 = 1.37
-    b[3, :, :, 20:40] = 127                                # ... and 1.5 inside the slab: interior Fresnel faces
-    out["asgn_byte"] = (b, PROP3, hostcfg.MEDIA_ASGN_BYTE)
-    sh = np.zeros((2, 60, 60, 60), np.uint16)
-    sh[0] = np.round(mua / 0.02 * 65535)
-    sh[1] = np.round(mus / 5.0 * 65535)
-    out["as_short"] = (sh, [[0, 0, 1, 1], [0.0, 0.0, 0.01, 1.37], [0.02, 5.0, 0.01, 1.37]], hostcfg.MEDIA_AS_SHORT)
-    return out
+PROP2, PROP3, two_regions, volumes = decks.MEDIA_PROP2, decks.MEDIA_PROP3, decks.media_two_regions, decks.media_volumes
 
 
 @pytest.mark.parametrize("name", ["mua_float", "as_f2h", "label_half", "asgn_byte", "as_short"])

@@ -179,6 +179,30 @@ def test_port_bit_identical_features(ref, port, case):
             assert a["field"].size == 3 * 216000 and all(a["field"].reshape(3, -1).sum(axis=1) > 0)
 
 
+# continuous media: oracle/_ref is the reference source built with -DMED_TYPE=99..104, the port decodes the words itself
+@pytest.mark.parametrize("name", ["mua_float", "as_f2h", "label_half", "asgn_byte", "as_short"])
+@pytest.mark.parametrize("reflect,det", [(0, 0), (1, 0), (1, 1)])
+def test_port_bit_identical_continuous_media(ref, port, name, reflect, det):
+    """updateproperty (src/mcx_core.cl:1079-1193) and the far-side index of the mismatch test (:3147) restated in C"""
+    vol, prop, fmt = decks.media_volumes()[name]
+    cfg = dict(benchmarks.get("cube60b", 3000), vol=vol, prop=prop, isreflect=reflect, issavedet=det, savedetflag="dxvw")
+    p, a, b = both(ref, port, cfg)
+    assert p.c.mediaformat == fmt and a["energytot"] == 3000
+    assert_identical(a, b)
+
+
+def test_port_bit_identical_continuous_media_with_a_cavity(ref, port):
+    """zero words are background: a packet crossing an air gap inside a float-mua volume takes n from row 0 there (:1095)
+    and is launched through the void in front of the tissue (skipvoid)"""
+    mua = np.full((1, 60, 60, 60), 0.01, np.float32)
+    mua[0, 20:40, 20:40, 25:32] = 0.0           # cavity
+    mua[0, :, :, :4] = 0.0                      # air in front of the tissue: the pencil beam starts in it
+    cfg = dict(benchmarks.get("cube60b", 3000), vol=mua, prop=decks.MEDIA_PROP2, isreflect=1, issavedet=0)
+    p, a, b = both(ref, port, cfg)
+    assert p.c.mediaformat == hostcfg.MEDIA_MUA_FLOAT and a["energytot"] == 3000
+    assert_identical(a, b)
+
+
 def test_port_parallel_run_matches_serial_totals(port):
     p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
     a = port.run(p, 512, hostthreads=1)
