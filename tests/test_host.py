@@ -16,6 +16,7 @@ from mcxcl_b200 import abi, benchmarks, hostcfg
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "mcxb200.h")
+ERR_ARG = -1            # MCXB_ERR_ARG
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -186,6 +187,55 @@ def test_engine_refuses_to_run_without_a_gpu(lib):
         engine.run(benchmarks.get("cube60", 100))
     assert "failed" in str(e.value)
     assert engine.gpuinfo() == []
+
+
+def _create_error(lib, cfg):
+    import ctypes as C
+    p = hostcfg.prepare(cfg) if isinstance(cfg, dict) else cfg
+    sim = C.c_void_p()
+    rc = lib.mcxb_sim_create(C.byref(p.c), 0, C.byref(sim))
+    assert not sim.value
+    return rc, (lib.mcxb_last_error() or b"").decode()
+
+
+def test_c_abi_argument_errors_are_reported_before_any_device_work(lib):
+    """the refusals of include/mcxb200.h are argument checks: code MCXB_ERR_ARG (-1) and a message that names the reason,
+    with or without a GPU (the messages follow the reference's where it has one: src/mcx_utils.c:1633-1636, 1660,
+    src/mcx_host.cpp:723)"""
+    import ctypes as C
+    base = benchmarks.get("cube60", 100)
+    # the host mirror (like mcx_validatecfg) refuses most of these first: set the struct members behind its back
+    cases = [
+        (dict(respin=-2), "respin"),
+        (dict(tstep=0.0), "time gate"),
+        (dict(outputtype=3), "replay"),              # MCXB_OT_JACOBIAN
+        (dict(debuglevel=abi.DEBUG_MOVE, maxjumpdebug=0), "maxjumpdebug"),
+        (dict(srctype=99), "source type"),
+        (dict(srcnum=2), "photon sharing"),
+        (dict(extrasrclen=1), "srcdata"),
+        (dict(dimx=40000), "grid dimensions"),
+    ]
+    for fields, word in cases:
+        p = hostcfg.prepare(base)
+        for k, v in fields.items():
+            setattr(p.c, k, v)
+        rc, msg = _create_error(lib, p)
+        assert rc == ERR_ARG and word in msg, (fields, rc, msg)
+    p = hostcfg.prepare(base)
+    p.c.abi_version = abi.ABI_VERSION - 1
+    rc, msg = _create_error(lib, p)
+    assert rc == ERR_ARG and "abi_version" in msg
+    # the multi-device call: device list checks
+    p = hostcfg.prepare(base)
+    out = abi.Output()
+    for devs, word in (([], "devices"), ([0, 1, 0], "listed twice"), (list(range(abi.MAX_DEVICES + 1)), "devices")):
+        arr = (C.c_int * max(1, len(devs)))(*devs)
+        rc = lib.mcxb_run_simulation_multi(C.byref(p.c), arr, len(devs), None, C.byref(out), None)
+        assert rc == ERR_ARG and word in (lib.mcxb_last_error() or b"").decode()
+    # adjoint products: volumes of at least one source and one detector
+    buf = np.zeros(8, np.float32)
+    rc = lib.mcxb_adjoint_products(0, buf.ctypes.data, None, 2, 2, 2, 1, 0, 1, 0, buf.ctypes.data)
+    assert rc == ERR_ARG and "at least one source" in (lib.mcxb_last_error() or b"").decode()
 
 
 def test_photon_split_of_the_multi_gpu_call_matches_the_host_mirror(lib):
