@@ -1,6 +1,6 @@
 /*
  * mcx_oracle.c -- plain-C restatement of MCX-CL's photon-transport kernel for label media and the continuous media
- * formats (Config.mediabyte 99-104)
+ * formats (Config.mediabyte 99-104), with real or complex (RF forward, omega > 0) packet weights
  * (TEST INFRASTRUCTURE ONLY: nothing under mcxcl_b200/ may load, link or call this file; only
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do).
  *
@@ -18,7 +18,7 @@
  *   host side                  src/mcx_host.cpp:494-524, 674-700, 759-768, 1011-1012 (parameter block, seeding,
  *                              threadphoton/oddphoton), :1252-1306 (fold shadow half, energy sums)
  * Not restated (outside SURVEY.md section 8a): SVMC and two-word media, polarised light, replay /
- * Jacobian / RF outputs, adjoint sources, trajectory debug, issaveref > 1.
+ * Jacobian / RF replay outputs, adjoint sources, trajectory debug, issaveref > 1.
  *
  * Numeric contract: IEEE binary32, no FMA contraction (build with -ffp-contract=off), the OpenCL native_*
  * functions taken as the libm float functions and rsqrt(x) as 1/sqrtf(x) -- the same contract under which
@@ -73,6 +73,7 @@ typedef struct {
     int oddphoton;
     uint32_t debuglevel, savedetflag, reclen, partialdata, w0offset, gscatter, is2d, srcnum, extrasrclen;
     uint32_t nphase, nphaselen, nangle, nanglelen;
+    float omega;                                 /* > 0: RF forward run, complex packet weights (:2427-2430) */
     uint32_t mediaformat;                        /* MED_TYPE of the reference's build: 1 (labels) or 99..104 (:541-546) */
     int doreflection;                            /* MCX_DO_REFLECTION compiled in (src/mcx_host.cpp:945-956) */
     unsigned char bc[12];
@@ -85,7 +86,7 @@ typedef struct {
 
 /* buffers private to one host thread */
 typedef struct {
-    float* field;            /* 2*fieldlen: primary half + shadow half */
+    float* field;            /* 2*fieldlen: primary half + shadow half (4*fieldlen in RF forward runs: + imaginary primary / shadow) */
     float* detp;
     uint64_t* detseed;
     uint32_t detcount;
@@ -1005,6 +1006,8 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
     it.threadid = idx;
     uint32_t idx1dold, mediaidold = 0, isdet = 0;
     float pathlen = 0.f, n1;
+    float w_re = 0.f, w_im = 0.f, w0_re = 0.f, w0_im = 0.f;      /* complex weight of an RF forward run (:2338) */
+    const int rf = g->omega > 0.f;
     f4* p = &it.p;
     f4* v = &it.v;
     f4* f = &it.f;
@@ -1040,6 +1043,11 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
 
     isdet = it.mediaid & DET_MASK;
     it.mediaid &= MED_MASK;
+
+    if (rf) {      /* :2427-2430 */
+        w_re = w0_re = p->w;
+        w_im = w0_im = 0.f;
+    }
 
     while (f->w <= (float)(g->threadphoton + (idx < g->oddphoton))) {
         /* ---- scattering (:2446-2649) ---- */
@@ -1132,7 +1140,19 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
             flipdir->z += (slen == f->x) ? 0 : (v->z > 0.f ? 1 : -1);
         }
 
-        p->w *= expf(-prop->x * f->z);
+        if (rf) {
+            /* w <- w exp[-(mua + i omega n / c0) ds]; the magnitude drives roulette and the ledger (:2750-2760) */
+            const float rf_atten = expf(-prop->x * f->z);
+            const float ang = g->omega * prop->w * g->oneoverc0 * f->z;
+            const float rf_sin = sinf(ang), rf_cos = cosf(ang);
+            const float tmp_re = rf_atten * (w_re * rf_cos + w_im * rf_sin);
+            const float tmp_im = rf_atten * (-w_re * rf_sin + w_im * rf_cos);
+            w_re = tmp_re;
+            w_im = tmp_im;
+            p->w = sqrtf(w_re * w_re + w_im * w_im);
+        } else {
+            p->w *= expf(-prop->x * f->z);
+        }
         f->x -= slen;
         f->y += f->z * prop->w * g->oneoverc0;
 
@@ -1159,10 +1179,17 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
         /* ---- deposit on leaving a voxel (:2816-2929) ---- */
         if (it.idx1d != idx1dold && idx1dold < g->dimxyz && mediaidold) {
             if (g->save2pt && f->y >= g->twin0 && f->y < g->twin1) {
-                float weight = 0.f;
+                float weight = 0.f, weight_im = 0.f;
                 int tshift = (int)floorf((f->y - g->twin0) * g->Rtstep);
 
-                if (g->outputtype == otEnergy) {
+                if (rf) {
+                    /* the complex quotient (w0 - w) / (mua + i omega n / c0) (:2833-2841) */
+                    const float dw_re = w0_re - w_re, dw_im = w0_im - w_im;
+                    const float a_im = g->omega * prop->w * g->oneoverc0;
+                    const float a_mag2 = prop->x * prop->x + a_im * a_im;
+                    weight = (a_mag2 < EPS) ? (w0_re * pathlen) : (dw_re * prop->x + dw_im * a_im) / a_mag2;
+                    weight_im = (a_mag2 < EPS) ? (w0_im * pathlen) : (dw_im * prop->x - dw_re * a_im) / a_mag2;
+                } else if (g->outputtype == otEnergy) {
                     weight = it.w0 - p->w;
                 } else if (g->outputtype == otFluence || g->outputtype == otFlux) {
                     weight = (prop->x < EPS) ? (it.w0 * pathlen) : ((it.w0 - p->w) / (prop->x));
@@ -1176,7 +1203,27 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
 
                 if (fabsf(weight) > 0.f) {
                     if (g->srctype != MCXB_SRC_PATTERN && g->srctype != MCXB_SRC_PATTERN3D) {
-                        deposit(g, s, (size_t)(idx1dold + (uint32_t)tshift * g->dimxyz), weight);
+                        const size_t at = (size_t)(idx1dold + (uint32_t)tshift * g->dimxyz);
+
+                        if (!rf) {
+                            deposit(g, s, at, weight);
+                        } else {
+                            /* :2882-2893 as written: the imaginary part goes to the third quarter of the buffer in the ELSE
+                             * branch of the real part's spill, so the step that spills the real part loses it */
+                            const float oldval = atomicadd(s, s->field + at, weight);
+
+                            if (fabsf(oldval) > MAX_ACCUM) {
+                                atomicadd(s, s->field + at, (oldval > 0.f) ? -MAX_ACCUM : MAX_ACCUM);
+                                atomicadd(s, s->field + at + g->fieldlen, (oldval > 0.f) ? MAX_ACCUM : -MAX_ACCUM);
+                            } else {
+                                const float oldim = atomicadd(s, s->field + at + 2 * (size_t)g->fieldlen, weight_im);
+
+                                if (fabsf(oldim) > MAX_ACCUM) {
+                                    atomicadd(s, s->field + at + 2 * (size_t)g->fieldlen, (oldim > 0.f) ? -MAX_ACCUM : MAX_ACCUM);
+                                    atomicadd(s, s->field + at + 3 * (size_t)g->fieldlen, (oldim > 0.f) ? MAX_ACCUM : -MAX_ACCUM);
+                                }
+                            }
+                        }
                     } else {
                         for (uint32_t i = 0; i < g->srcnum; i++) {
                             if (fabsf(ppath[g->w0offset + i]) > 0.f) {
@@ -1189,6 +1236,12 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
             }
 
             it.w0 = p->w;
+
+            if (rf) {
+                w0_re = w_re;
+                w0_im = w_im;
+            }
+
             pathlen = 0.f;
         } else {
             it.mediaid = mediaidold;     /* note: carries the detector / boundary bits of isdet along (:2928) */
@@ -1229,6 +1282,12 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
 
             isdet = it.mediaid & DET_MASK;
             it.mediaid &= MED_MASK;
+
+            if (rf) {      /* :3011-3014 */
+                w_re = w0_re = p->w;
+                w_im = w0_im = 0.f;
+            }
+
             continue;
         }
 
@@ -1236,6 +1295,13 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
         if (fabsf(p->w) < g->minenergy) {
             if (rand_uniform01(t) * ROULETTE_SIZE <= 1.f) {
                 p->w *= ROULETTE_SIZE;
+
+                if (rf) {
+                    w_re *= ROULETTE_SIZE;
+                    w_im *= ROULETTE_SIZE;
+                    w0_re *= ROULETTE_SIZE;
+                    w0_im *= ROULETTE_SIZE;
+                }
             } else {
                 if (launchnewphoton(g, s, &it, mediaidold & DET_MASK)) {
                     break;
@@ -1243,6 +1309,12 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
 
                 isdet = it.mediaid & DET_MASK;
                 it.mediaid &= MED_MASK;
+
+                if (rf) {
+                    w_re = w0_re = p->w;
+                    w_im = w0_im = 0.f;
+                }
+
                 continue;
             }
         }
@@ -1283,6 +1355,12 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
 
                         isdet = it.mediaid & DET_MASK;
                         it.mediaid &= MED_MASK;
+
+                        if (rf) {      /* :3191-3194 */
+                            w_re = w0_re = p->w;
+                            w_im = w0_im = 0.f;
+                        }
+
                         continue;
                     }
                 } else {
@@ -1369,8 +1447,14 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
 
     const int continuous = cfg->mediaformat >= 99 && cfg->mediaformat <= 104;
 
-    if ((cfg->mediaformat > 4 && !continuous) || cfg->polmedianum || cfg->omega > 0.f || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
-        return -3;      /* split-voxel / two-word media, polarised light, RF and adjoint runs: checked by oracle/_ref only */
+    if ((cfg->mediaformat > 4 && !continuous) || cfg->polmedianum || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
+        return -3;      /* split-voxel / two-word media, polarised light, RF replay and adjoint runs: checked by oracle/_ref only */
+    }
+
+    const int rfforward = cfg->omega > 0.f;
+
+    if (rfforward && (cfg->srctype == MCXB_SRC_PATTERN || cfg->srctype == MCXB_SRC_PATTERN3D || (cfg->debuglevel & 1u))) {
+        return -3;      /* the pattern builds of the reference have no imaginary deposit (:2902-2913) */
     }
 
     if (continuous && ((cfg->issavedet && (cfg->savedetflag & 0x0Eu)) || cfg->isspecular > 0 || cfg->srcnum > 1 ||
@@ -1386,6 +1470,7 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
     g.dimxyz = g.dimxy * cfg->dimz;
     g.maxgate = (uint32_t)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);       /* src/mcx_host.cpp:647 */
     g.mediaformat = continuous ? cfg->mediaformat : 1u;
+    g.omega = cfg->omega;
     g.srcnum = cfg->srcnum ? cfg->srcnum : 1;
     const uint32_t nsrcvol = (cfg->srctype == MCXB_SRC_PATTERN || cfg->srctype == MCXB_SRC_PATTERN3D) ? g.srcnum
                              : ((cfg->srcid < 0) ? (cfg->extrasrclen + 1) : 1);
@@ -1483,7 +1568,7 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
         const int tid = 0;
 #endif
         sink_t* s = sinks + tid;
-        s->field = (float*)calloc(fieldlen * 2, sizeof(float));
+        s->field = (float*)calloc(fieldlen * (rfforward ? 4 : 2), sizeof(float));
 
         if (cfg->issavedet) {
             s->detp = (float*)calloc((size_t)g.maxdetphoton * (g.reclen ? g.reclen : 1), sizeof(float));
@@ -1505,11 +1590,11 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
 
     /* fold the shadow half and sum host threads (src/mcx_host.cpp:1252-1258, 1292-1296) */
     if (res->field) {
-        if (res->fieldlen < fieldlen) {
+        if (res->fieldlen < fieldlen * (rfforward ? 2 : 1)) {
             rc = -2;
         } else {
             for (size_t i = 0; i < fieldlen; i++) {
-                float acc = 0.f;
+                float acc = 0.f, acc_im = 0.f;
 
                 for (int t = 0; t < hostthreads; t++) {
                     float val = sinks[t].field[i];
@@ -1519,14 +1604,22 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
                     }
 
                     acc += val;
+
+                    if (rfforward) {        /* third + fourth quarter: imaginary primary + shadow (src/mcx_host.cpp:1263-1276) */
+                        acc_im += sinks[t].field[i + 2 * fieldlen] + sinks[t].field[i + 3 * fieldlen];
+                    }
                 }
 
                 res->field[i] = acc;
+
+                if (rfforward) {
+                    res->field[i + fieldlen] = acc_im;
+                }
             }
         }
     }
 
-    res->fieldlen = fieldlen;
+    res->fieldlen = fieldlen * (rfforward ? 2 : 1);
     /* src/mcx_host.cpp:1303-1306 */
     double etot = 0.0, eesc = 0.0;
 

@@ -203,6 +203,28 @@ def test_port_bit_identical_continuous_media_with_a_cavity(ref, port):
     assert_identical(a, b)
 
 
+@pytest.mark.parametrize("case", ["cube60b", "no_reflection", "gates", "roulette", "hot_voxel"])
+def test_port_bit_identical_rf_forward(ref, port, case):
+    """complex packet weights of a forward run with a modulation frequency (src/mcx_core.cl:2427-2430, 2750-2760,
+    2833-2841, 3035-3040), including the reference's quirk that the step whose real deposit spills past MAX_ACCUM loses
+    its imaginary deposit (:2884-2893; `hot_voxel` crosses the limit several times)"""
+    omega = 2 * np.pi * 100e6
+    cfg = {
+        "cube60b": dict(benchmarks.get("cube60b", 3000), omega=omega),
+        "no_reflection": dict(benchmarks.get("cube60", 3000), omega=omega),
+        "gates": dict(decks.two_layer(3000, tend=2e-9, tstep=2e-10), omega=omega),
+        "roulette": dict(benchmarks.get("cube60b", 2000), omega=omega, minenergy=0.01, prop=[[0, 0, 1, 1], [0.05, 1.0, 0.01, 1.37]]),
+        "hot_voxel": dict(benchmarks.get("cube60b", 6000), omega=omega, prop=[[0, 0, 1, 1], [0.0005, 1.0, 0.01, 1.37]]),
+    }[case]
+    p, a, b = both(ref, port, cfg)
+    n = a["field"].size // 2
+    assert p.rfplanes == 2 and a["field"].size == p.fieldlen
+    assert a["field"][:n].sum() > 0 > a["field"][n:].sum()
+    if case == "hot_voxel":
+        assert a["field"][:n].max() > 2000.0
+    assert_identical(a, b)
+
+
 def test_port_parallel_run_matches_serial_totals(port):
     p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
     a = port.run(p, 512, hostthreads=1)
