@@ -1,11 +1,12 @@
 /*
  * mcx_oracle.c -- plain-C restatement of MCX-CL's photon-transport kernel for label media and the continuous media
- * formats (Config.mediabyte 99-104), with real or complex (RF forward, omega > 0) packet weights
+ * formats (Config.mediabyte 99-104), with real or complex (RF forward, omega > 0) packet weights and polarised light
  * (TEST INFRASTRUCTURE ONLY: nothing under mcxcl_b200/ may load, link or call this file; only
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do).
  *
  * What it restates (reference = fangq/mcxcl, all line numbers are src/mcx_core.cl unless noted):
  *   RNG                        :684-727        xorshift128+, [0,1) floats, scattering-length draw
+ *   rotsphi, updatestokes      :792-835        Stokes vector through one scattering event
  *   detector search / records  :838-926
  *   mcx_nextafterf, hitgrid    :965-995        (OpenCL branch of hitgrid, :988-989)
  *   rotate*, transmit, Fresnel :997-1075
@@ -17,7 +18,7 @@
  *                                              spill, termination, cyclic bc, roulette, reflection
  *   host side                  src/mcx_host.cpp:494-524, 674-700, 759-768, 1011-1012 (parameter block, seeding,
  *                              threadphoton/oddphoton), :1252-1306 (fold shadow half, energy sums)
- * Not restated (outside SURVEY.md section 8a): SVMC and two-word media, polarised light, replay /
+ * Not restated (outside SURVEY.md section 8a): SVMC and two-word media, replay /
  * Jacobian / RF replay outputs, adjoint sources, trajectory debug, issaveref > 1.
  *
  * Numeric contract: IEEE binary32, no FMA contraction (build with -ffp-contract=off), the OpenCL native_*
@@ -44,6 +45,8 @@
 #define EPS                FLT_EPSILON          /* :476-478 */
 #define ONE_PI             3.1415926535897932f
 #define TWO_PI             6.28318530717959f
+#define R_PI               0.318309886183791f   /* :457 */
+#define NANGLES            181                  /* :519 */
 #define JUST_BELOW_ONE     0.9998f
 #define R_C0               3.335640951981520e-12f
 #define ROULETTE_SIZE      10.f                 /* :507 */
@@ -73,6 +76,9 @@ typedef struct {
     int oddphoton;
     uint32_t debuglevel, savedetflag, reclen, partialdata, w0offset, gscatter, is2d, srcnum, extrasrclen;
     uint32_t nphase, nphaselen, nangle, nanglelen;
+    uint32_t maxpolmedia;                        /* > 0: polarised run, one Mueller-matrix table per medium (:658) */
+    f4 s0;                                       /* incident Stokes vector (:660) */
+    const f4* smatrix;                           /* [maxpolmedia][NANGLES] {S11, S12, S33, S43} */
     float omega;                                 /* > 0: RF forward run, complex packet weights (:2427-2430) */
     uint32_t mediaformat;                        /* MED_TYPE of the reference's build: 1 (labels) or 99..104 (:541-546) */
     int doreflection;                            /* MCX_DO_REFLECTION compiled in (src/mcx_host.cpp:945-956) */
@@ -99,6 +105,7 @@ typedef struct {
     s4 flipdir;
     uint32_t idx1d, mediaid;
     float w0, Lmove;
+    float si, sq, su, sv;    /* Stokes vector of the packet (:603-605, 2341) */
     uint64_t t[2];           /* RNG state */
     uint64_t photonseed[2];  /* RNG state at launch (issaveseed) */
     float* ppath;            /* w0offset + srcnum floats (:2396-2399) */
@@ -358,6 +365,13 @@ static void savedetphoton(const param_t* g, sink_t* s, const item_t* it, const f
     if (flag & 0x40u) {
         *rec++ = ppath[g->w0offset - 2];
     }
+
+    if (flag & 0x80u) {      /* :917-922 */
+        *rec++ = it->si;
+        *rec++ = it->sq;
+        *rec++ = it->su;
+        *rec++ = it->sv;
+    }
 }
 
 /* one fluence deposit with the reference's accumulation-precision guard (:2882-2887) */
@@ -536,6 +550,36 @@ static void update_property(const param_t* g, f4* prop, uint32_t mediaid) {
     }
 }
 
+/* rotsphi + updatestokes (:792-835): rotate the Stokes vector into the scattering plane, apply the Mueller matrix of the
+ * medium at the scattering angle, rotate back into the new meridian plane, renormalise to I = 1 */
+static void updatestokes(const param_t* g, item_t* it, float theta, float phi, const f4* u, const f4* u2) {
+    const float costheta = cosf(theta);
+    const float sin2phi = sinf(2.f * phi), cos2phi = cosf(2.f * phi);
+    float i2 = it->si, q2 = it->sq * cos2phi + it->su * sin2phi, u2s = -it->sq * sin2phi + it->su * cos2phi, v2 = it->sv;
+    const uint32_t imedia = NANGLES * ((it->mediaid & MED_MASK) - 1);
+    const uint32_t ithedeg = (uint32_t)(theta * NANGLES * (R_PI - EPS));
+    const f4 m = g->smatrix[imedia + ithedeg];
+    it->si = m.x * i2 + m.y * q2;
+    it->sq = m.y * i2 + m.x * q2;
+    it->su = m.z * u2s + m.w * v2;
+    it->sv = -m.w * u2s + m.z * v2;
+    float temp = (u2->z > -1.f && u2->z < 1.f) ? rsqrt_((1.f - costheta * costheta) * (1.f - u2->z * u2->z)) : 0.f;
+    float cosi = (temp == 0.f) ? 0.f : (((phi > ONE_PI && phi < TWO_PI) ? 1.f : -1.f) * (u2->z * costheta - u->z) * temp);
+    cosi = fmaxf(-1.f, fminf(cosi, 1.f));
+    const float sini = sqrtf(1.f - cosi * cosi);
+    const float cos22 = 2.f * cosi * cosi - 1.f;
+    const float sin22 = 2.f * sini * cosi;
+    i2 = it->si;
+    q2 = it->sq * cos22 - it->su * sin22;
+    u2s = it->sq * sin22 + it->su * cos22;
+    v2 = it->sv;
+    temp = 1.f / i2;
+    it->sq = q2 * temp;
+    it->su = u2s * temp;
+    it->sv = v2 * temp;
+    it->si = 1.f;
+}
+
 static void locate(const param_t* g, item_t* it) {
     it->idx1d = (uint32_t)((int)floorf(it->p.z)) * g->dimxy + (uint32_t)((int)floorf(it->p.y)) * g->dimx + (uint32_t)((int)floorf(it->p.x));
     it->mediaid = outside_f(g, &it->p) ? 0u : g->media[it->idx1d];
@@ -631,6 +675,14 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
         f->z = g->minaccumtime;
         it->idx1d = as_uint(p2.z);
         it->mediaid = as_uint(p2.w);
+
+        if (g->maxpolmedia > 0) {      /* :1633-1638 */
+            it->si = g->s0.x;
+            it->sq = g->s0.y;
+            it->su = g->s0.z;
+            it->sv = g->s0.w;
+        }
+
         prop->x = pos.x;
         prop->y = pos.y;
         prop->z = pos.z;
@@ -996,6 +1048,7 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
 static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, float* genergy, uint32_t global_size) {
     item_t it;
     memset(&it, 0, sizeof(it));
+    it.si = 1.f;             /* Stokes s = {1, 0, 0, 0} (:2341) */
     float ppath_store[64];
     const uint32_t ppathlen = g->w0offset + g->srcnum;
     float* ppath = (ppathlen <= 64) ? ppath_store : (float*)malloc(sizeof(float) * ppathlen);
@@ -1058,6 +1111,26 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                 float cphi = 1.f, sphi = 0.f, theta, stheta, ctheta;
                 float tmp0 = 0.f;
 
+                if (g->maxpolmedia > 0 && !g->is2d) {
+                    /* rejection sampling of (theta, phi) from the phase function of the CURRENT Stokes vector (:2454-2468) */
+                    const uint32_t ipol = (uint32_t)NANGLES * ((it.mediaid & MED_MASK) - 1);
+                    float I0, I, sin2phi, cos2phi;
+
+                    do {
+                        theta = acosf(2.f * rand_uniform01(t) - 1.f);
+                        tmp0 = TWO_PI * rand_uniform01(t);
+                        sin2phi = sinf(2.f * tmp0);
+                        cos2phi = cosf(2.f * tmp0);
+                        I0 = g->smatrix[ipol].x * it.si + g->smatrix[ipol].y * (it.sq * cos2phi + it.su * sin2phi);
+                        const uint32_t ithedeg = (uint32_t)(theta * NANGLES * (R_PI - EPS));
+                        I = g->smatrix[ipol + ithedeg].x * it.si + g->smatrix[ipol + ithedeg].y * (it.sq * cos2phi + it.su * sin2phi);
+                    } while (rand_uniform01(t) * I0 >= I);
+
+                    sphi = sinf(tmp0);
+                    cphi = cosf(tmp0);
+                    stheta = sinf(theta);
+                    ctheta = cosf(theta);
+                } else {
                 if (!g->is2d) {
                     tmp0 = TWO_PI * rand_uniform01(t);
                     sphi = sinf(tmp0);
@@ -1090,6 +1163,7 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                         ctheta = cosf(theta);
                     }
                 }
+                }
 
                 if (g->savedet) {
                     if (g->savedetflag & 0x02u) {
@@ -1104,6 +1178,8 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                     }
                 }
 
+                const f4 olddir = *v;
+
                 if (g->is2d) {
                     rotatevector2d(v, (rand_uniform01(t) > 0.5f ? stheta : -stheta), ctheta, (int)g->is2d);
                 } else {
@@ -1111,6 +1187,10 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                 }
 
                 v->w += 1.f;
+
+                if (g->maxpolmedia > 0) {      /* :2562-2565 */
+                    updatestokes(g, &it, theta, tmp0, &olddir, v);
+                }
             }
 
             v->w = (float)(int)v->w;
@@ -1447,8 +1527,8 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
 
     const int continuous = cfg->mediaformat >= 99 && cfg->mediaformat <= 104;
 
-    if ((cfg->mediaformat > 4 && !continuous) || cfg->polmedianum || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
-        return -3;      /* split-voxel / two-word media, polarised light, RF replay and adjoint runs: checked by oracle/_ref only */
+    if ((cfg->mediaformat > 4 && !continuous) || (cfg->polmedianum && (!cfg->smatrix || continuous || cfg->medianum != cfg->polmedianum + 1)) || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
+        return -3;      /* split-voxel / two-word media, RF replay and adjoint runs: checked by oracle/_ref only */
     }
 
     const int rfforward = cfg->omega > 0.f;
@@ -1471,6 +1551,12 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
     g.maxgate = (uint32_t)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);       /* src/mcx_host.cpp:647 */
     g.mediaformat = continuous ? cfg->mediaformat : 1u;
     g.omega = cfg->omega;
+    g.maxpolmedia = cfg->smatrix ? cfg->polmedianum : 0;     /* src/mcx_host.cpp:522-523 */
+    g.smatrix = (const f4*)cfg->smatrix;
+    g.s0.x = cfg->srciquv.x;
+    g.s0.y = cfg->srciquv.y;
+    g.s0.z = cfg->srciquv.z;
+    g.s0.w = cfg->srciquv.w;
     g.srcnum = cfg->srcnum ? cfg->srcnum : 1;
     const uint32_t nsrcvol = (cfg->srctype == MCXB_SRC_PATTERN || cfg->srctype == MCXB_SRC_PATTERN3D) ? g.srcnum
                              : ((cfg->srcid < 0) ? (cfg->extrasrclen + 1) : 1);

@@ -3,7 +3,7 @@ conditions, gates, detectors).  The physics follows the reference's own test com
 (test/testmcx.sh:60-132) and example decks where one exists."""
 import numpy as np
 
-from mcxcl_b200 import benchmarks, hostcfg
+from mcxcl_b200 import abi, benchmarks, hostcfg
 
 
 def cube(nphoton=1e5, **kw):
@@ -139,3 +139,25 @@ def media_volumes():
     sh[1] = np.round(mus / 5.0 * 65535)
     out["as_short"] = (sh, [[0, 0, 1, 1], [0.0, 0.0, 0.01, 1.37], [0.02, 5.0, 0.01, 1.37]], hostcfg.MEDIA_AS_SHORT)
     return out
+
+
+# ---- polarised light: Mueller-matrix tables on the 181-point polar grid ----
+def rayleigh(nmed):
+    """Mueller matrix of a Rayleigh scatterer on the 181-point polar grid mcx_prep_polarized uses (src/mcx_utils.c:1483-1519):
+    rows {S11, S12, S33, S43}"""
+    c = np.cos(np.pi * np.arange(abi.NANGLES) / (abi.NANGLES - 1))
+    m = np.stack([0.75 * (1 + c * c), -0.75 * (1 - c * c), 1.5 * c, 0 * c], axis=1).astype(np.float32)
+    return np.repeat(m[None], nmed, axis=0)
+
+
+def isotropic_matrix(nmed):
+    m = np.zeros((abi.NANGLES, 4), np.float32)
+    m[:, 0] = 1.0
+    m[:, 2] = 1.0
+    return np.repeat(m[None], nmed, axis=0)
+
+
+def pol_cfg(n, **kw):
+    cfg = dict(benchmarks.get("cube60b", n), prop=[[0, 0, 1, 1], [0.005, 1.0, 0.0, 1.37]], savedetflag="dpxvwi", smatrix=rayleigh(1), srciquv=[1, 1, 0, 0])
+    cfg.update(kw)
+    return cfg

@@ -12,31 +12,14 @@ import ctypes as C
 import numpy as np
 import pytest
 
+import decks
 from mcxcl_b200 import abi, benchmarks, engine, hostcfg
 from test_replay import replay_cfg
 
 OMEGA = 2 * np.pi * 100e6       # 100 MHz modulation
 
 
-def rayleigh(nmed):
-    """Mueller matrix of a Rayleigh scatterer on the 181-point polar grid mcx_prep_polarized uses (src/mcx_utils.c:1483-1519):
-    rows {S11, S12, S33, S43}"""
-    c = np.cos(np.pi * np.arange(abi.NANGLES) / (abi.NANGLES - 1))
-    m = np.stack([0.75 * (1 + c * c), -0.75 * (1 - c * c), 1.5 * c, 0 * c], axis=1).astype(np.float32)
-    return np.repeat(m[None], nmed, axis=0)
-
-
-def isotropic_matrix(nmed):
-    m = np.zeros((abi.NANGLES, 4), np.float32)
-    m[:, 0] = 1.0
-    m[:, 2] = 1.0
-    return np.repeat(m[None], nmed, axis=0)
-
-
-def pol_cfg(n, **kw):
-    cfg = dict(benchmarks.get("cube60b", n), prop=[[0, 0, 1, 1], [0.005, 1.0, 0.0, 1.37]], savedetflag="dpxvwi", smatrix=rayleigh(1), srciquv=[1, 1, 0, 0])
-    cfg.update(kw)
-    return cfg
+rayleigh, isotropic_matrix, pol_cfg = decks.rayleigh, decks.isotropic_matrix, decks.pol_cfg
 
 
 # ------------------------------------------------------------------------------------------- CPU: host logic and the oracle

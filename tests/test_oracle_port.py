@@ -225,6 +225,26 @@ def test_port_bit_identical_rf_forward(ref, port, case):
     assert_identical(a, b)
 
 
+@pytest.mark.parametrize("case", ["rayleigh", "circular", "isotropic", "no_reflection", "two_layer", "rf_and_polarised"])
+def test_port_bit_identical_polarised_light(ref, port, case):
+    """Stokes vectors (src/mcx_core.cl:792-835): rejection sampling of the scattering angles from the Mueller matrix of the
+    medium (:2454-2468), the vector rotated and renormalised at every event (:2562-2565), {I, Q, U, V} in the records
+    (:917-922)"""
+    two = decks.two_layer(3000)
+    cfg = {
+        "rayleigh": decks.pol_cfg(3000),
+        "circular": decks.pol_cfg(3000, srciquv=[1, 0, 0, 1]),
+        "isotropic": decks.pol_cfg(3000, smatrix=decks.isotropic_matrix(1)),
+        "no_reflection": decks.pol_cfg(3000, isreflect=0),
+        "two_layer": dict(two, smatrix=decks.rayleigh(len(two["prop"]) - 1), srciquv=[1, 0, 1, 0], issavedet=1, savedetflag="dpi",
+                          detpos=[[30, 30, 0, 4]], maxdetphoton=3000),
+        "rf_and_polarised": decks.pol_cfg(2000, omega=2 * np.pi * 100e6),
+    }[case]
+    p, a, b = both(ref, port, cfg)
+    assert p.c.polmedianum >= 1 and a["detected"] > 0 and (a["detp"][:, -4] == 1.0).all()
+    assert_identical(a, b)
+
+
 def test_port_parallel_run_matches_serial_totals(port):
     p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
     a = port.run(p, 512, hostthreads=1)
