@@ -1,6 +1,7 @@
 /*
  * mcx_oracle.c -- plain-C restatement of MCX-CL's photon-transport kernel for label media and the continuous media
- * formats (Config.mediabyte 99-104), with real or complex (RF forward, omega > 0) packet weights and polarised light
+ * formats (Config.mediabyte 99-104), with real or complex (RF forward, omega > 0) packet weights, polarised light and
+ * photon replay
  * (TEST INFRASTRUCTURE ONLY: nothing under mcxcl_b200/ may load, link or call this file; only
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do).
  *
@@ -18,8 +19,9 @@
  *                                              spill, termination, cyclic bc, roulette, reflection
  *   host side                  src/mcx_host.cpp:494-524, 674-700, 759-768, 1011-1012 (parameter block, seeding,
  *                              threadphoton/oddphoton), :1252-1306 (fold shadow half, energy sums)
- * Not restated (outside SURVEY.md section 8a): SVMC and two-word media, replay /
- * Jacobian / RF replay outputs, adjoint sources, trajectory debug, issaveref > 1.
+ *   photon replay              :1590-1596, 2568-2612, 2845-2858   stream restart, Jacobian / WP / DCS / WLTOF / WPTOF
+ * Not restated (outside SURVEY.md section 8a): SVMC and two-word media, the RF replay
+ * outputs, adjoint sources, trajectory debug, issaveref > 1.
  *
  * Numeric contract: IEEE binary32, no FMA contraction (build with -ffp-contract=off), the OpenCL native_*
  * functions taken as the libm float functions and rsqrt(x) as 1/sqrtf(x) -- the same contract under which
@@ -58,7 +60,7 @@
 #define NO_LAUNCH          9999
 
 enum { bcUnknown, bcReflect, bcAbsorb, bcMirror, bcCyclic };
-enum { otFlux, otFluence, otEnergy, otL = 7 };
+enum { otFlux, otFluence, otEnergy, otJacobian, otWP, otDCS, otRF, otL, otRFmus, otWLTOF, otWPTOF };      /* :666 */
 
 typedef struct { float x, y, z, w; } f4;
 typedef struct { short x, y, z, w; } s4;
@@ -76,6 +78,11 @@ typedef struct {
     int oddphoton;
     uint32_t debuglevel, savedetflag, reclen, partialdata, w0offset, gscatter, is2d, srcnum, extrasrclen;
     uint32_t nphase, nphaselen, nangle, nanglelen;
+    int replay, replaydet;                       /* seed == SEED_FROM_FILE: packets restart from recorded RNG states (:1590-1596) */
+    const uint64_t* rseed;
+    const float* rweight;
+    const float* rtof;
+    const int32_t* rdetid;
     uint32_t maxpolmedia;                        /* > 0: polarised run, one Mueller-matrix table per medium (:658) */
     f4 s0;                                       /* incident Stokes vector (:660) */
     const f4* smatrix;                           /* [maxpolmedia][NANGLES] {S11, S12, S33, S43} */
@@ -642,6 +649,12 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
         return 1;                                            /* :1581 */
     }
 
+    if (g->replay) {      /* :1590-1596, the record index exactly as written */
+        const int rec = it->threadid * (int)g->threadphoton + (it->threadid < g->oddphoton - 1 ? it->threadid : g->oddphoton - 1) + ((int)f->w > 0 ? (int)f->w : 0);
+        t[0] = g->rseed[2 * (size_t)rec];
+        t[1] = g->rseed[2 * (size_t)rec + 1];
+    }
+
     if (g->issaveseed) {
         it->photonseed[0] = t[0];
         it->photonseed[1] = t[1];
@@ -658,6 +671,10 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
                 src = (const mcxb_source*)(g->gproperty + g->maxmedia + 1 + ((int)(ppath[g->w0offset - 1] - 2.f)) * 4);
             }
         }
+    }
+
+    if (g->replay && g->srcid >= 1) {      /* :1614-1616 */
+        (void)rand_uniform01(t);
     }
 
     ppath += g->partialdata;
@@ -1191,6 +1208,40 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                 if (g->maxpolmedia > 0) {      /* :2562-2565 */
                     updatestokes(g, &it, theta, tmp0, &olddir, v);
                 }
+
+                /* replay: weighted scattering counts / momentum transfer at the scattering site (:2568-2612), with the record
+                 * index as the reference writes it (f.w, not f.w - 1) and its way of moving an overflowing sum to the shadow half */
+                if (g->outputtype == otWP || g->outputtype == otDCS || g->outputtype == otWPTOF) {
+                    const int rec = idx * (int)g->threadphoton + (idx < g->oddphoton - 1 ? idx : g->oddphoton - 1) + (int)f->w;
+                    int tshift = rec;
+                    tmp0 = (g->outputtype == otDCS) ? (1.f - ctheta) : 1.f;
+
+                    if (g->outputtype == otWPTOF) {
+                        tmp0 = g->rtof[rec];
+                        tmp0 *= g->rweight[rec];
+                    } else {
+                        tmp0 *= g->rweight[rec];
+                    }
+
+                    tshift = (int)floorf((g->rtof[tshift] - g->twin0) * g->Rtstep) +
+                             ((g->replaydet == -1) ? (((g->rdetid[tshift] & 0xFFFF) - 1) * (int)g->maxgate) : 0);
+
+                    if (g->extrasrclen * (g->srcid < 0)) {
+                        tshift += ((int)ppath[g->w0offset - 1] - 1) * (int)((g->replaydet == -1) ? g->detnum : 1u) * (int)g->maxgate;
+                    }
+
+                    tshift = ((int)g->maxgate - 1 < tshift) ? (int)g->maxgate - 1 : tshift;
+                    float* at = s->field + it.idx1d + (size_t)tshift * g->dimxyz;
+                    const float oldval = atomicadd(s, at, tmp0);
+
+                    if (fabsf(oldval) > MAX_ACCUM) {
+                        if (atomicadd(s, at, -oldval) < 0.f) {
+                            atomicadd(s, at, oldval);
+                        } else {
+                            atomicadd(s, at + g->fieldlen, oldval);
+                        }
+                    }
+                }
             }
 
             v->w = (float)(int)v->w;
@@ -1273,12 +1324,24 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                     weight = it.w0 - p->w;
                 } else if (g->outputtype == otFluence || g->outputtype == otFlux) {
                     weight = (prop->x < EPS) ? (it.w0 * pathlen) : ((it.w0 - p->w) / (prop->x));
+                } else if (g->replay) {
+                    if (g->outputtype == otJacobian || g->outputtype == otWLTOF) {
+                        /* w_i L binned by the DETECTED time of flight of record i (:2845-2858) */
+                        const int rec = idx * (int)g->threadphoton + (idx < g->oddphoton - 1 ? idx : g->oddphoton - 1) + (int)f->w - 1;
+                        weight = g->rweight[rec] * pathlen;
+                        tshift = (int)floorf((g->rtof[rec] - g->twin0) * g->Rtstep) +
+                                 ((g->replaydet == -1) ? (((g->rdetid[rec] & 0xFFFF) - 1) * (int)g->maxgate) : 0);
+
+                        if (g->outputtype == otWLTOF) {
+                            weight = weight * g->rtof[rec];
+                        }
+                    }
                 } else if (g->outputtype == otL) {
                     weight = it.w0 * pathlen;
                 }
 
                 if (g->extrasrclen * (g->srcid < 0)) {
-                    tshift += ((int)ppath[g->w0offset - 1] - 1) * (int)g->maxgate;
+                    tshift += ((int)ppath[g->w0offset - 1] - 1) * (int)((g->replaydet == -1) ? g->detnum : 1u) * (int)g->maxgate;
                 }
 
                 if (fabsf(weight) > 0.f) {
@@ -1521,8 +1584,19 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
         return -1;
     }
 
-    if (cfg->replay_seed) {
-        return -3;      /* photon replay is not restated here: oracle/_ref (the reference source itself) checks it */
+    const int replay = cfg->replay_seed != NULL;
+    const int sens = cfg->outputtype == otJacobian || cfg->outputtype == otWP || cfg->outputtype == otDCS || cfg->outputtype == otWLTOF ||
+                     cfg->outputtype == otWPTOF;
+
+    if ((sens && (!replay || !cfg->replay_weight || !cfg->replay_tof || (cfg->replaydet == -1 && !cfg->replay_detid))) ||
+            (replay && (cfg->omega > 0.f || cfg->srcnum > 1))) {
+        return -3;      /* the sensitivity outputs belong to a replay; RF replay is checked by oracle/_ref only (its phase factors are lost there) */
+    }
+
+    if (replay) {
+        /* the reference maps work-item t to record t*threadphoton + min(t, oddphoton-1) + k (:1591): the identity only when a
+         * work-item owns at most one photon, so a replay runs with nphoton + 1 work-items (like oracle/ref_driver.cpp) */
+        nthread = (uint32_t)cfg->nphoton + 1;
     }
 
     const int continuous = cfg->mediaformat >= 99 && cfg->mediaformat <= 104;
@@ -1551,6 +1625,12 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
     g.maxgate = (uint32_t)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);       /* src/mcx_host.cpp:647 */
     g.mediaformat = continuous ? cfg->mediaformat : 1u;
     g.omega = cfg->omega;
+    g.replay = replay;
+    g.replaydet = cfg->replaydet;
+    g.rseed = (const uint64_t*)cfg->replay_seed;
+    g.rweight = cfg->replay_weight;
+    g.rtof = cfg->replay_tof;
+    g.rdetid = cfg->replay_detid;
     g.maxpolmedia = cfg->smatrix ? cfg->polmedianum : 0;     /* src/mcx_host.cpp:522-523 */
     g.smatrix = (const f4*)cfg->smatrix;
     g.s0.x = cfg->srciquv.x;
@@ -1560,7 +1640,9 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
     g.srcnum = cfg->srcnum ? cfg->srcnum : 1;
     const uint32_t nsrcvol = (cfg->srctype == MCXB_SRC_PATTERN || cfg->srctype == MCXB_SRC_PATTERN3D) ? g.srcnum
                              : ((cfg->srcid < 0) ? (cfg->extrasrclen + 1) : 1);
-    const size_t fieldlen = (size_t)g.dimxyz * g.maxgate * nsrcvol;
+    /* src/mcx_host.cpp:684-689: one volume per detector when every detector is replayed at once */
+    const uint32_t nrepvol = (replay && cfg->replaydet == -1) ? (cfg->detnum ? cfg->detnum : 1) : 1;
+    const size_t fieldlen = (size_t)g.dimxyz * g.maxgate * nsrcvol * nrepvol;
     g.fieldlen = (uint32_t)fieldlen;
     g.maxidx.x = (float)cfg->dimx;
     g.maxidx.y = (float)cfg->dimy;
@@ -1630,8 +1712,14 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
 
     g.sharedtab = sharedtab;
 
-    uint32_t* seeds = (uint32_t*)malloc(sizeof(uint32_t) * 4 * (size_t)nthread);
-    mcxo_seeds(cfg->seed, cfg->seed_skip, nthread, seeds);
+    uint32_t* seeds = (uint32_t*)calloc(4 * (size_t)nthread + 4, sizeof(uint32_t));
+
+    if (replay) {
+        /* gseed holds the recorded RNG states (src/mcx_host.cpp:724); gpu_rng_init still reads one record per work-item */
+        memcpy(seeds, cfg->replay_seed, 16 * (size_t)cfg->nphoton);
+    } else {
+        mcxo_seeds(cfg->seed, cfg->seed_skip, nthread, seeds);
+    }
     float* genergy = (float*)calloc(2 * (size_t)nthread, sizeof(float));
 
 #ifdef _OPENMP
@@ -1717,7 +1805,7 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
     res->energytot = etot;
     res->energyesc = eesc;
 
-    if (res->energy) {
+    if (res->energy && !replay) {       /* the caller sized this buffer for ITS work-item count */
         memcpy(res->energy, genergy, sizeof(float) * 2 * nthread);
     }
 

@@ -245,6 +245,33 @@ def test_port_bit_identical_polarised_light(ref, port, case):
     assert_identical(a, b)
 
 
+@pytest.fixture(scope="module")
+def replay_base(ref):
+    import test_replay
+    cfg = test_replay.baseline_cfg(60000)
+    return cfg, ref.run(hostcfg.prepare(cfg), 1024, hostthreads=0)
+
+
+@pytest.mark.parametrize("replaydet", [0, -1])
+@pytest.mark.parametrize("ot", ["flux", "jacobian", "wltof", "wp", "wm", "wptof"])
+def test_port_bit_identical_replay(ref, port, replay_base, ot, replaydet):
+    """photon replay restated (src/mcx_core.cl:1590-1596 stream restart, :2568-2612 scattering-site outputs, :2845-2858
+    absorption Jacobian), record indices exactly as the reference writes them -- including `f.w` instead of `f.w - 1` at
+    scattering sites, which is why those outputs are handed tables padded by one element (tests/test_replay.py)"""
+    import test_replay
+    cfg, base = replay_base
+    assert base["detected"] > 100
+    p = hostcfg.prepare(test_replay.replay_cfg(cfg, base["detp"], base["seeds"], outputtype=ot, isnormalized=0, issaveseed=1, replaydet=replaydet))
+    if ot in ("wp", "wm", "wptof"):
+        test_replay.shift_records_for_the_reference(p)
+    a = ref.run(p, 1, hostthreads=1)
+    b = port.run(p, 1, hostthreads=1)
+    assert a["field"].size == p.fieldlen and a["detected"] == p.c.nphoton
+    assert a["energytot"] == b["energytot"] and a["energyesc"] == b["energyesc"]
+    assert (bits(a["field"]) == bits(b["field"])).all() and np.abs(a["field"]).sum() > 0
+    assert a["detected"] == b["detected"] and (bits(a["detp"]) == bits(b["detp"])).all() and (a["seeds"] == b["seeds"]).all()
+
+
 def test_port_parallel_run_matches_serial_totals(port):
     p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
     a = port.run(p, 512, hostthreads=1)
