@@ -1605,6 +1605,10 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
         return -3;      /* split-voxel / two-word media, RF replay and adjoint runs: checked by oracle/_ref only */
     }
 
+    if ((cfg->debuglevel & (2u | 8u)) || cfg->srcid < -1 || cfg->issaveref > 1) {
+        return -3;      /* trajectory records (-D M / -D T), detectors launched as disk sources (srcid == -2) and issaveref > 1 are not restated */
+    }
+
     const int rfforward = cfg->omega > 0.f;
 
     if (rfforward && (cfg->srctype == MCXB_SRC_PATTERN || cfg->srctype == MCXB_SRC_PATTERN3D || (cfg->debuglevel & 1u))) {
