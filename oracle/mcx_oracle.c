@@ -1,6 +1,6 @@
 /*
- * mcx_oracle.c -- plain-C restatement of MCX-CL's photon-transport kernel for label media and the continuous media
- * formats (Config.mediabyte 99-104), with real or complex (RF forward, omega > 0) packet weights, polarised light and
+ * mcx_oracle.c -- plain-C restatement of MCX-CL's photon-transport kernel for label media, split-voxel media (97) and the
+ * continuous media formats (Config.mediabyte 99-104), with real or complex (RF forward, omega > 0) packet weights, polarised light and
  * photon replay
  * (TEST INFRASTRUCTURE ONLY: nothing under mcxcl_b200/ may load, link or call this file; only
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do).
@@ -12,6 +12,7 @@
  *   mcx_nextafterf, hitgrid    :965-995        (OpenCL branch of hitgrid, :988-989)
  *   rotate*, transmit, Fresnel :997-1075
  *   updateproperty             :1079-1193      label rows and the word decoders of MED_TYPE 99-104
+ *   split-voxel media          :1231-1344      updateproperty_svmc, ray_plane_intersect, reflectray_svmc
  *   skipvoid                   :1350-1455
  *   launchnewphoton            :1466-2275      all 18 source types, multi-source pick, launch-angle table,
  *                                              focal-length / isotropic / Lambertian launch
@@ -20,7 +21,7 @@
  *   host side                  src/mcx_host.cpp:494-524, 674-700, 759-768, 1011-1012 (parameter block, seeding,
  *                              threadphoton/oddphoton), :1252-1306 (fold shadow half, energy sums)
  *   photon replay              :1590-1596, 2568-2612, 2845-2858   stream restart, Jacobian / WP / DCS / WLTOF / WPTOF
- * Not restated (outside SURVEY.md section 8a): SVMC and two-word media, the RF replay
+ * Not restated (outside SURVEY.md section 8a): two-word media (96), the RF replay
  * outputs, adjoint sources, trajectory debug, issaveref > 1.
  *
  * Numeric contract: IEEE binary32, no FMA contraction (build with -ffp-contract=off), the OpenCL native_*
@@ -113,6 +114,8 @@ typedef struct {
     uint32_t idx1d, mediaid;
     float w0, Lmove;
     float si, sq, su, sv;    /* Stokes vector of the packet (:603-605, 2341) */
+    float svnx, svny, svnz, svpd;   /* split-voxel state MCXsp (:594-598): interface normal, plane offset ... */
+    uint32_t svbits;                /* ... and {lower label, upper label, is-split, is-upper} (:577-587) */
     uint64_t t[2];           /* RNG state */
     uint64_t photonseed[2];  /* RNG state at launch (issaveseed) */
     float* ppath;            /* w0offset + srcnum floats (:2396-2399) */
@@ -441,14 +444,16 @@ static int skipvoid(const param_t* g, sink_t* s, f4* p, f4* v, f4* f, s4* flipdi
 
                 /* the reference reads media[idx1d] here without a bounds check (:1420-1429); after a failed
                  * refinement the index may lie outside the grid, where this restatement reads label 0 */
-                const uint32_t lab = ((uint32_t)idx1d < g->dimxyz) ? (g->media[idx1d] & MED_MASK) : 0u;
-                const float nin = g->gproperty[lab].w;
+                if (g->isspecular) {      /* label media only: the word itself is the table index here (:1424-1431) */
+                    const uint32_t lab = ((uint32_t)idx1d < g->dimxyz) ? (g->media[idx1d] & MED_MASK) : 0u;
+                    const float nin = g->gproperty[lab].w;
 
-                if (g->isspecular && nin != g->gproperty[0].w) {
-                    p->w *= 1.f - reflectcoeff(v, g->gproperty[0].w, nin, flipdir->w);
+                    if (nin != g->gproperty[0].w) {
+                        p->w *= 1.f - reflectcoeff(v, g->gproperty[0].w, nin, flipdir->w);
 
-                    if (p->w > EPS) {
-                        transmit(v, g->gproperty[0].w, nin, flipdir->w);
+                        if (p->w > EPS) {
+                            transmit(v, g->gproperty[0].w, nin, flipdir->w);
+                        }
                     }
                 }
 
@@ -477,6 +482,142 @@ static int skipvoid(const param_t* g, sink_t* s, f4* p, f4* v, f4* f, s4* flipdi
 /* -------------------------------------------------------------------- launchnewphoton :1466-2275 */
 
 /* launch-time media lookup shared by the area sources (:1752-1758) */
+#define SV_LOWER(sv)       ((uint32_t)((sv) & 0xFFu))
+#define SV_UPPER(sv)       ((uint32_t)(((sv) >> 8) & 0xFFu))
+#define SV_ISSPLIT(sv)     (((sv) >> 16) & 1u)
+#define SV_ISUPPER(sv)     (((sv) >> 17) & 1u)
+#define SV_CURLABEL(sv)    (SV_ISUPPER(sv) ? SV_UPPER(sv) : SV_LOWER(sv))
+
+static float dot3(float ax, float ay, float az, float bx, float by, float bz) {      /* :961-963 */
+    return ax * bx + ay * by + az * bz;
+}
+
+/* updateproperty_svmc (:1231-1279): split-voxel media, two words per voxel -- {lower, upper, px, py} in the first,
+ * {pz, nx, ny, nz} in the second (dimxyz words further on).  Decides from the packet's position which side of the
+ * interface it is on and orients the normal towards the other side */
+static void update_property_svmc(const param_t* g, item_t* it, f4* prop, uint32_t mediaid, uint32_t idx1d, const f4* p) {
+    if (idx1d == OUTSIDE_VOLUME_MIN || idx1d == OUTSIDE_VOLUME_MAX) {
+        *prop = g->gproperty[0];
+        return;
+    }
+
+    const uint32_t w0 = g->media[idx1d + g->dimxyz], w1 = mediaid & MED_MASK;
+    const uint32_t c0 = w0 & 0xFFu, c1 = (w0 >> 8) & 0xFFu, c2 = (w0 >> 16) & 0xFFu, c3 = w0 >> 24;
+    const uint32_t c4 = w1 & 0xFFu, c5 = (w1 >> 8) & 0xFFu, c6 = (w1 >> 16) & 0xFFu, c7 = w1 >> 24;
+    uint32_t svpacked = c7 | (c6 << 8);
+
+    if (c6) {
+        const float rx = (float)c5 * (1.f / 255.f) + (float)it->flipdir.x;
+        const float ry = (float)c4 * (1.f / 255.f) + (float)it->flipdir.y;
+        const float rz = (float)c3 * (1.f / 255.f) + (float)it->flipdir.z;
+        it->svnx = (float)c2 * (2.f / 255.f) - 1.f;
+        it->svny = (float)c1 * (2.f / 255.f) - 1.f;
+        it->svnz = (float)c0 * (2.f / 255.f) - 1.f;
+        const float r = rsqrt_(dot3(it->svnx, it->svny, it->svnz, it->svnx, it->svny, it->svnz));
+        it->svnx = it->svnx * r;
+        it->svny = it->svny * r;
+        it->svnz = it->svnz * r;
+        it->svpd = dot3(rx, ry, rz, it->svnx, it->svny, it->svnz);
+
+        if (dot3(p->x, p->y, p->z, it->svnx, it->svny, it->svnz) > it->svpd) {
+            *prop = g->gproperty[SV_UPPER(svpacked)];
+            svpacked |= 0x20000u;
+            it->svnx = -it->svnx;
+            it->svny = -it->svny;
+            it->svnz = -it->svnz;
+            it->svpd = -it->svpd;
+        } else {
+            *prop = g->gproperty[SV_LOWER(svpacked)];
+            svpacked &= ~0x20000u;
+        }
+
+        svpacked |= 0x10000u;
+    } else {
+        *prop = g->gproperty[c7];
+        svpacked &= 0xFFFFu;
+    }
+
+    it->svbits = svpacked;
+}
+
+/* ray_plane_intersect (:1281-1302): does the segment of length *len reach the interface?  If so it ends there */
+static int ray_plane_intersect(const param_t* g, const item_t* it, const f4* prop, float* len, float* slen) {
+    const f4* p0 = &it->p;
+    const f4* v = &it->v;
+    const float vdotn = dot3(v->x, v->y, v->z, it->svnx, it->svny, it->svnz);
+
+    if (vdotn <= 0.f) {
+        return 0;
+    }
+
+    const float d0 = dot3(p0->x, p0->y, p0->z, it->svnx, it->svny, it->svnz) - it->svpd;
+    const float d1 = d0 + (*len) * vdotn;
+
+    if (d0 * d1 > 0.f) {
+        return 0;
+    }
+
+    const float len0 = ((*len) * d0) / (d0 - d1);
+    *len = (len0 > 0.f) ? len0 : *len;
+    *slen = (*len) * prop->y * (v->w + 1.f > (float)g->gscatter ? (1.f - prop->z) : 1.f);
+    return 1;
+}
+
+/* reflectray_svmc (:1304-1344): Fresnel reflection or refraction at the interface inside a split voxel; returns 1 when the
+ * packet is transmitted into an empty (label 0) part */
+static int reflectray_svmc(const param_t* g, item_t* it, float n1, float c0[3], f4* prop) {
+    float Re, Im, Rtotal, tmp0, tmp1, tmp2;
+    const float Icos = fabsf(dot3(c0[0], c0[1], c0[2], it->svnx, it->svny, it->svnz));
+    const float n2 = SV_ISUPPER(it->svbits) ? g->gproperty[SV_UPPER(it->svbits)].w : g->gproperty[SV_LOWER(it->svbits)].w;
+    tmp0 = n1 * n1;
+    tmp1 = n2 * n2;
+    tmp2 = 1.f - tmp0 / tmp1 * (1.f - Icos * Icos);
+
+    if (tmp2 > 0.f) {
+        Re = tmp0 * Icos * Icos + tmp1 * tmp2;
+        tmp2 = sqrtf(tmp2);
+        Im = 2.f * n1 * n2 * Icos * tmp2;
+        Rtotal = (Re - Im) / (Re + Im);
+        Re = tmp1 * Icos * Icos + tmp0 * tmp2 * tmp2;
+        Rtotal = (Rtotal + (Re - Im) / (Re + Im)) * 0.5f;
+
+        if (rand_uniform01(it->t) <= Rtotal) {
+            c0[0] += (-2.f * Icos) * it->svnx;
+            c0[1] += (-2.f * Icos) * it->svny;
+            c0[2] += (-2.f * Icos) * it->svnz;
+            it->svbits ^= 0x20000u;
+        } else {
+            c0[0] += (-Icos) * it->svnx;
+            c0[1] += (-Icos) * it->svny;
+            c0[2] += (-Icos) * it->svnz;
+            c0[0] = tmp2 * it->svnx + (n1 / n2) * c0[0];
+            c0[1] = tmp2 * it->svny + (n1 / n2) * c0[1];
+            c0[2] = tmp2 * it->svnz + (n1 / n2) * c0[2];
+            it->svnx = -it->svnx;
+            it->svny = -it->svny;
+            it->svnz = -it->svnz;
+            it->svpd = -it->svpd;
+
+            if (SV_CURLABEL(it->svbits) == 0) {
+                return 1;
+            }
+
+            *prop = g->gproperty[SV_CURLABEL(it->svbits)];
+        }
+    } else {
+        c0[0] += (-2.f * Icos) * it->svnx;
+        c0[1] += (-2.f * Icos) * it->svny;
+        c0[2] += (-2.f * Icos) * it->svnz;
+        it->svbits ^= 0x20000u;
+    }
+
+    tmp0 = rsqrt_(dot3(c0[0], c0[1], c0[2], c0[0], c0[1], c0[2]));
+    c0[0] = c0[0] * tmp0;
+    c0[1] = c0[1] * tmp0;
+    c0[2] = c0[2] * tmp0;
+    return 0;
+}
+
 /* binary16 storage bits widened exactly to binary32 (what vload_half / convert_float of cl_khr_fp16 do) */
 static float half_bits_to_float(uint16_t h) {
     const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
@@ -634,7 +775,7 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
             }
         }
 
-        if (g->savedet && (isdet & DET_MASK) == DET_MASK && it->mediaid == 0 && g->issaveref < 2) {
+        if (g->savedet && (isdet & DET_MASK) == DET_MASK && (it->mediaid == 0 || (g->mediaformat == 97 && SV_CURLABEL(it->svbits) == 0)) && g->issaveref < 2) {      /* :1556-1561 */
             savedetphoton(g, s, it, ppath, isdet);
         }
     }
@@ -692,6 +833,10 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
         f->z = g->minaccumtime;
         it->idx1d = as_uint(p2.z);
         it->mediaid = as_uint(p2.w);
+
+        if (g->mediaformat == 97) {
+            it->svbits = 0u;           /* SV_CLEAR, :1640-1642 */
+        }
 
         if (g->maxpolmedia > 0) {      /* :1633-1638 */
             it->si = g->s0.x;
@@ -1051,7 +1196,13 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
     /* :2212-2255 */
     f->w += 1.f;
     *prop = g->gproperty[1];
-    update_property(g, prop, it->mediaid);
+
+    if (g->mediaformat == 97) {
+        update_property_svmc(g, it, prop, it->mediaid, it->idx1d, p);
+    } else {
+        update_property(g, prop, it->mediaid);
+    }
+
     ppath[1] += p->w;
     it->w0 = p->w;
     ppath[2] = (g->srcnum > 1) ? ppath[2] : p->w;
@@ -1078,6 +1229,8 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
     float pathlen = 0.f, n1;
     float w_re = 0.f, w_im = 0.f, w0_re = 0.f, w0_im = 0.f;      /* complex weight of an RF forward run (:2338) */
     const int rf = g->omega > 0.f;
+    const int svmc = g->mediaformat == 97;      /* MEDIA_2LABEL_SPLIT */
+    int testint = 0, hitintf = 0;               /* :2345-2346 */
     f4* p = &it.p;
     f4* v = &it.v;
     f4* f = &it.f;
@@ -1183,15 +1336,18 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                 }
 
                 if (g->savedet) {
-                    if (g->savedetflag & 0x02u) {
+                    /* split-voxel media count by the part of the voxel the packet is in, and not at all in an empty part (:2504-2545) */
+                    const uint32_t lab = svmc ? SV_CURLABEL(it.svbits) : (it.mediaid & MED_MASK);
+
+                    if ((g->savedetflag & 0x02u) && (!svmc || lab > 0)) {
                         uint32_t c;
-                        memcpy(&c, ppath + (it.mediaid & MED_MASK) - 1, 4);
+                        memcpy(&c, ppath + lab - 1, 4);
                         c++;
-                        memcpy(ppath + (it.mediaid & MED_MASK) - 1, &c, 4);
+                        memcpy(ppath + lab - 1, &c, 4);
                     }
 
-                    if (g->savedetflag & 0x08u) {
-                        ppath[g->maxmedia * ((g->savedetflag >> 1 & 1u) + (g->savedetflag >> 2 & 1u)) + (it.mediaid & MED_MASK) - 1] += 1.f - ctheta;
+                    if ((g->savedetflag & 0x08u) && (!svmc || lab > 0)) {
+                        ppath[g->maxmedia * ((g->savedetflag >> 1 & 1u) + (g->savedetflag >> 2 & 1u)) + lab - 1] += 1.f - ctheta;
                     }
                 }
 
@@ -1245,30 +1401,49 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
             }
 
             v->w = (float)(int)v->w;
+
+            if (svmc) {
+                testint = 1;           /* :2638-2648 */
+            }
         }
 
         /* ---- one ray segment (:2652-2765) ---- */
         n1 = prop->w;
-        update_property(g, prop, it.mediaid);
+
+        if (svmc) {
+            update_property_svmc(g, &it, prop, it.mediaid, it.idx1d, p);
+        } else {
+            update_property(g, prop, it.mediaid);
+        }
+
         f->z = hitgrid(s, p, v, flipdir);
         float slen = f->z * prop->y * (v->w + 1.f > (float)g->gscatter ? (1.f - prop->z) : 1.f);
         slen = fminf(slen, f->x);
         f->z = slen / (prop->y * (v->w + 1.f > (float)g->gscatter ? (1.f - prop->z) : 1.f));
+
+        if (svmc && SV_ISSPLIT(it.svbits) && testint) {       /* :2684-2699 */
+            float tmplen = f->z;
+            hitintf = ray_plane_intersect(g, &it, prop, &tmplen, &slen);
+            f->z = tmplen;
+        } else {
+            hitintf = 0;
+        }
+
         pathlen += f->z;
         p->x = p->x + f->z * v->x;
         p->y = p->y + f->z * v->y;
         p->z = p->z + f->z * v->z;
 
         if (flipdir->w == 0) {
-            flipdir->x += (slen == f->x) ? 0 : (v->x > 0.f ? 1 : -1);
+            flipdir->x += (slen == f->x || hitintf) ? 0 : (v->x > 0.f ? 1 : -1);
         }
 
         if (flipdir->w == 1) {
-            flipdir->y += (slen == f->x) ? 0 : (v->y > 0.f ? 1 : -1);
+            flipdir->y += (slen == f->x || hitintf) ? 0 : (v->y > 0.f ? 1 : -1);
         }
 
         if (flipdir->w == 2) {
-            flipdir->z += (slen == f->x) ? 0 : (v->z > 0.f ? 1 : -1);
+            flipdir->z += (slen == f->x || hitintf) ? 0 : (v->z > 0.f ? 1 : -1);
         }
 
         if (rf) {
@@ -1288,7 +1463,11 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
         f->y += f->z * prop->w * g->oneoverc0;
 
         if (g->savedet && (g->savedetflag & 0x04u)) {
-            ppath[g->maxmedia * (g->savedetflag >> 1 & 1u) + (it.mediaid & MED_MASK) - 1] += f->z;
+            if (!svmc) {
+                ppath[g->maxmedia * (g->savedetflag >> 1 & 1u) + (it.mediaid & MED_MASK) - 1] += f->z;
+            } else if (SV_CURLABEL(it.svbits) > 0) {      /* :2772-2782 */
+                ppath[g->maxmedia * (g->savedetflag >> 1 & 1u) + SV_CURLABEL(it.svbits) - 1] += f->z;
+            }
         }
 
         /* ---- new voxel (:2796-2811) ---- */
@@ -1308,7 +1487,7 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
         }
 
         /* ---- deposit on leaving a voxel (:2816-2929) ---- */
-        if (it.idx1d != idx1dold && idx1dold < g->dimxyz && mediaidold) {
+        if ((it.idx1d != idx1dold || hitintf) && idx1dold < g->dimxyz && mediaidold) {
             if (g->save2pt && f->y >= g->twin0 && f->y < g->twin1) {
                 float weight = 0.f, weight_im = 0.f;
                 int tshift = (int)floorf((f->y - g->twin0) * g->Rtstep);
@@ -1390,8 +1569,25 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
             it.mediaid = mediaidold;     /* note: carries the detector / boundary bits of isdet along (:2928) */
         }
 
+        if (svmc) {
+            /* the tissue on the far side of a voxel face or of the interface (:2931-2949) */
+            if (it.idx1d != idx1dold) {
+                update_property_svmc(g, &it, prop, it.mediaid, it.idx1d, p);
+                testint = 1;
+            } else if (hitintf) {
+                it.svnx = -it.svnx;
+                it.svny = -it.svny;
+                it.svnz = -it.svnz;
+                it.svpd = -it.svpd;
+                it.svbits ^= 0x20000u;
+                testint = 0;
+            }
+        }
+
         /* ---- leave the domain, time out, or wrap around (:2957-3028) ---- */
         if ((it.mediaid == 0 && ((isdet & 0xF) == bcAbsorb || (isdet & 0xF) == bcCyclic || ((isdet & 0xF) == bcReflect && n1 == g->gproperty[0].w)))
+                || (svmc && ((it.idx1d != idx1dold || hitintf) && !SV_ISUPPER(it.svbits) && !SV_LOWER(it.svbits)
+                             && (!g->doreflect || n1 == g->gproperty[0].w)))
                 || f->y > g->twin1) {
             if (isdet == bcCyclic) {
                 if (flipdir->w == 0) {
@@ -1431,6 +1627,10 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                 w_im = w0_im = 0.f;
             }
 
+            if (svmc) {
+                testint = 1;           /* :3016-3026 */
+            }
+
             continue;
         }
 
@@ -1464,7 +1664,44 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
 
         /* ---- refractive-index mismatch (:3063-3297), compiled in under MCX_DO_REFLECTION ---- */
         if (g->doreflection) {
-            update_property(g, prop, it.mediaid);
+            if (svmc && hitintf) {
+                /* Fresnel reflection / refraction at the interface inside a split voxel (:3074-3111) */
+                if (g->gproperty[SV_LOWER(it.svbits)].w != g->gproperty[SV_UPPER(it.svbits)].w) {
+                    it.svnx = -it.svnx;
+                    it.svny = -it.svny;
+                    it.svnz = -it.svnz;
+                    it.svpd = -it.svpd;
+                    float c0[3] = { v->x, v->y, v->z };
+
+                    if (reflectray_svmc(g, &it, n1, c0, prop)) {
+                        if (launchnewphoton(g, s, &it, mediaidold & DET_MASK)) {
+                            break;
+                        }
+
+                        isdet = it.mediaid & DET_MASK;
+                        it.mediaid &= MED_MASK;
+
+                        if (rf) {
+                            w_re = w0_re = p->w;
+                            w_im = w0_im = 0.f;
+                        }
+
+                        testint = 1;
+                        continue;
+                    }
+
+                    v->x = c0[0];
+                    v->y = c0[1];
+                    v->z = c0[2];
+                } else {
+                    *prop = g->gproperty[SV_CURLABEL(it.svbits)];
+                }
+
+            } else {
+            if (!svmc) {
+                update_property(g, prop, it.mediaid);
+            }
+
             /* the index on the far side: the decoded one up to format 99, row 1 (row 0 outside) of the table from 100 on (:3147) */
             const float nfar = (g->mediaformat < 100) ? prop->w : g->gproperty[it.mediaid > 0 ? 1 : 0].w;
 
@@ -1524,10 +1761,36 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                     }
 
                     it.idx1d = idx1dold;
-                    it.mediaid = g->media[it.idx1d] & MED_MASK;
-                    update_property(g, prop, it.mediaid);
+                    /* the reference reads media[idx1dold] unguarded (:3212-3213); with split-voxel media idx1dold can be an
+                     * OUTSIDE_VOLUME marker in rare walks (undefined there), where this restatement reads an empty word */
+                    it.mediaid = (it.idx1d < g->dimxyz) ? (g->media[it.idx1d] & MED_MASK) : 0u;
+
+                    if (svmc) {
+                        /* back in the voxel it came from: which part of it? (:3215-3244) */
+                        update_property_svmc(g, &it, prop, it.mediaid, it.idx1d, p);
+
+                        if (SV_CURLABEL(it.svbits) == 0) {
+                            if (launchnewphoton(g, s, &it, mediaidold & DET_MASK)) {
+                                break;
+                            }
+
+                            isdet = it.mediaid & DET_MASK;
+                            it.mediaid &= MED_MASK;
+
+                            if (rf) {
+                                w_re = w0_re = p->w;
+                                w_im = w0_im = 0.f;
+                            }
+
+                            continue;
+                        }
+                    } else {
+                        update_property(g, prop, it.mediaid);
+                    }
+
                     n1 = prop->w;
                 }
+            }
             }
         }
     }
@@ -1600,8 +1863,13 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
     }
 
     const int continuous = cfg->mediaformat >= 99 && cfg->mediaformat <= 104;
+    const int splitvox = cfg->mediaformat == 97;       /* MEDIA_2LABEL_SPLIT */
 
-    if ((cfg->mediaformat > 4 && !continuous) || (cfg->polmedianum && (!cfg->smatrix || continuous || cfg->medianum != cfg->polmedianum + 1)) || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
+    if (splitvox && (cfg->isspecular > 0 || cfg->srcnum > 1 || cfg->polmedianum || cfg->replay_seed)) {
+        return -3;      /* the reference indexes its media table with the whole media word under isspecular (:1425); the rest is untested there */
+    }
+
+    if ((cfg->mediaformat > 4 && !continuous && !splitvox) || (cfg->polmedianum && (!cfg->smatrix || continuous || cfg->medianum != cfg->polmedianum + 1)) || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
         return -3;      /* split-voxel / two-word media, RF replay and adjoint runs: checked by oracle/_ref only */
     }
 
@@ -1627,7 +1895,7 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
     g.dimxy = cfg->dimx * cfg->dimy;
     g.dimxyz = g.dimxy * cfg->dimz;
     g.maxgate = (uint32_t)((cfg->tend - cfg->tstart) / cfg->tstep + 0.5);       /* src/mcx_host.cpp:647 */
-    g.mediaformat = continuous ? cfg->mediaformat : 1u;
+    g.mediaformat = (continuous || splitvox) ? cfg->mediaformat : 1u;
     g.omega = cfg->omega;
     g.replay = replay;
     g.replaydet = cfg->replaydet;

@@ -272,6 +272,27 @@ def test_port_bit_identical_replay(ref, port, replay_base, ot, replaydet):
     assert a["detected"] == b["detected"] and (bits(a["detp"]) == bits(b["detp"])).all() and (a["seeds"] == b["seeds"]).all()
 
 
+@pytest.mark.parametrize("case", ["matched", "mismatched", "no_reflection", "tilted_surface", "detectors", "rf"])
+def test_port_bit_identical_split_voxel_media(ref, port, case):
+    """SVMC (MED_TYPE 97): updateproperty_svmc / ray_plane_intersect / reflectray_svmc (src/mcx_core.cl:1231-1344) and their
+    call sites in the photon loop restated; the checker is the reference source built with -DMED_TYPE=97"""
+    import test_gpu_svmc as sv
+    surface = dict(vol=sv.tilted_slab(z0=30.4, sx=0.2, sy=0.1, below=1, above=0), prop=[[0, 0, 1, 1], [0.01, 1.0, 0.5, 1.37]])
+    over = {
+        "matched": dict(),
+        "mismatched": dict(prop=[[0, 0, 1, 1], [0.02, 1.0, 0.8, 1.37], [0.005, 2.0, 0.9, 1.55]]),
+        "no_reflection": dict(isreflect=0),
+        "tilted_surface": surface,
+        "detectors": dict(surface, issavedet=1, detpos=[[20, 20, 30.4, 4], [10, 20, 28.4, 3]], savedetflag="dsp", maxdetphoton=30000),
+        "rf": dict(omega=2 * np.pi * 100e6),
+    }[case]
+    p, a, b = both(ref, port, sv.deck(4000, **over))
+    assert p.c.mediaformat == 97 and a["energytot"] == 4000
+    if case == "detectors":
+        assert a["detected"] > 10
+    assert_identical(a, b)
+
+
 def test_port_parallel_run_matches_serial_totals(port):
     p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
     a = port.run(p, 512, hostthreads=1)
