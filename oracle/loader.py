@@ -88,7 +88,7 @@ class Checker:
                 seeds = np.zeros((p.c.maxdetphoton, 2), dtype=np.uint64)
                 res.seeddata = seeds.ctypes.data_as(C.POINTER(C.c_uint64))
         traj = None
-        if (p.c.debuglevel & 0xA) and self.kind == "reference":          # MCX_DEBUG_MOVE / MCX_DEBUG_MOVE_ONLY
+        if p.c.debuglevel & 0xA:          # MCX_DEBUG_MOVE / MCX_DEBUG_MOVE_ONLY
             traj = np.zeros((p.c.maxjumpdebug, 6), dtype=np.float32)
             res.traj = traj.ctypes.data_as(C.POINTER(C.c_float))
             res.trajcap = p.c.maxjumpdebug

@@ -9,6 +9,7 @@
  *   RNG                        :684-727        xorshift128+, [0,1) floats, scattering-length draw
  *   rotsphi, updatestokes      :792-835        Stokes vector through one scattering event
  *   detector search / records  :838-926
+ *   trajectory records         :929-948        -D M / -D T
  *   mcx_nextafterf, hitgrid    :965-995        (OpenCL branch of hitgrid, :988-989)
  *   rotate*, transmit, Fresnel :997-1075
  *   updateproperty             :1079-1193      label rows and the word decoders of MED_TYPE 99-104
@@ -22,7 +23,7 @@
  *                              threadphoton/oddphoton), :1252-1306 (fold shadow half, energy sums)
  *   photon replay              :1590-1596, 2568-2612, 2845-2858   stream restart, Jacobian / WP / DCS / WLTOF / WPTOF
  * Not restated (outside SURVEY.md section 8a): two-word media (96), the RF replay
- * outputs, adjoint sources, trajectory debug, issaveref > 1.
+ * outputs, detectors launched as adjoint disk sources, issaveref > 1.
  *
  * Numeric contract: IEEE binary32, no FMA contraction (build with -ffp-contract=off), the OpenCL native_*
  * functions taken as the libm float functions and rsqrt(x) as 1/sqrtf(x) -- the same contract under which
@@ -79,6 +80,7 @@ typedef struct {
     int oddphoton;
     uint32_t debuglevel, savedetflag, reclen, partialdata, w0offset, gscatter, is2d, srcnum, extrasrclen;
     uint32_t nphase, nphaselen, nangle, nanglelen;
+    uint32_t maxjumpdebug;                       /* capacity of the trajectory buffer (:929-944) */
     int replay, replaydet;                       /* seed == SEED_FROM_FILE: packets restart from recorded RNG states (:1590-1596) */
     const uint64_t* rseed;
     const float* rweight;
@@ -104,6 +106,8 @@ typedef struct {
     float* detp;
     uint64_t* detseed;
     uint32_t detcount;
+    float* traj;             /* maxjumpdebug x 6 trajectory records of this host thread (-D M / -D T) */
+    uint32_t trajcount;
     uint64_t n_segment, n_atomic, n_log;
 } sink_t;
 
@@ -728,6 +732,21 @@ static void updatestokes(const param_t* g, item_t* it, float theta, float phi, c
     it->si = 1.f;
 }
 
+/* savedebugdata (:929-948): one trajectory record {packet id, x, y, z, weight, source id} through one counter */
+static void savedebugdata(const param_t* g, sink_t* s, const f4* p, uint32_t id, int srcid) {
+    const uint32_t pos = s->trajcount++;
+
+    if (pos < g->maxjumpdebug && s->traj) {
+        float* rec = s->traj + (size_t)pos * 6;
+        memcpy(rec, &id, 4);
+        rec[1] = p->x;
+        rec[2] = p->y;
+        rec[3] = p->z;
+        rec[4] = p->w;
+        rec[5] = (float)srcid;
+    }
+}
+
 static void locate(const param_t* g, item_t* it) {
     it->idx1d = (uint32_t)((int)floorf(it->p.z)) * g->dimxy + (uint32_t)((int)floorf(it->p.y)) * g->dimx + (uint32_t)((int)floorf(it->p.x));
     it->mediaid = outside_f(g, &it->p) ? 0u : g->media[it->idx1d];
@@ -748,6 +767,11 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
     /* retire the current packet (:1494-1569) */
     if (fabsf(p->w) >= 0.f) {
         ppath[g->partialdata] += p->w;
+
+        if (g->debuglevel & (2u | 8u)) {       /* the end of a trajectory (:1497-1503) */
+            savedebugdata(g, s, p, (uint32_t)f->w + (uint32_t)it->threadid * g->threadphoton + (uint32_t)(it->threadid < g->oddphoton ? it->threadid : g->oddphoton),
+                          (int)ppath[g->w0offset - 1]);
+        }
 
         if (it->mediaid == 0 && it->idx1d != OUTSIDE_VOLUME_MIN && it->idx1d != OUTSIDE_VOLUME_MAX && g->issaveref && p->w > 0.f) {
             if (g->issaveref == 1) {
@@ -1203,6 +1227,10 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
         update_property(g, prop, it->mediaid);
     }
 
+    if (g->debuglevel & (2u | 8u)) {           /* the start of a trajectory (:2243-2249) */
+        savedebugdata(g, s, p, (uint32_t)f->w + (uint32_t)it->threadid * g->threadphoton + (uint32_t)(it->threadid < g->oddphoton ? it->threadid : 0), (int)ppath[3]);
+    }
+
     ppath[1] += p->w;
     it->w0 = p->w;
     ppath[2] = (g->srcnum > 1) ? ppath[2] : p->w;
@@ -1397,6 +1425,10 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                             atomicadd(s, at + g->fieldlen, oldval);
                         }
                     }
+                }
+
+                if (g->debuglevel & (2u | 8u)) {   /* every scattering site (:2625-2632) */
+                    savedebugdata(g, s, p, (uint32_t)f->w + (uint32_t)idx * g->threadphoton + (uint32_t)(idx < g->oddphoton ? idx : 0), (int)ppath[g->w0offset - 1]);
                 }
             }
 
@@ -1792,6 +1824,10 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                 }
             }
             }
+
+            if ((g->debuglevel & 8u) && (it.mediaid == 0 || it.idx1d == OUTSIDE_VOLUME_MIN || it.idx1d == OUTSIDE_VOLUME_MAX)) {
+                goto done;       /* "should never happen" (:3287-3291): the work-item returns without its energy write-back */
+            }
         }
     }
 
@@ -1873,8 +1909,8 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
         return -3;      /* split-voxel / two-word media, RF replay and adjoint runs: checked by oracle/_ref only */
     }
 
-    if ((cfg->debuglevel & (2u | 8u)) || cfg->srcid < -1 || cfg->issaveref > 1) {
-        return -3;      /* trajectory records (-D M / -D T), detectors launched as disk sources (srcid == -2) and issaveref > 1 are not restated */
+    if (cfg->srcid < -1 || cfg->issaveref > 1) {
+        return -3;      /* detectors launched as disk sources (srcid == -2) and issaveref > 1 are not restated */
     }
 
     const int rfforward = cfg->omega > 0.f;
@@ -1942,7 +1978,8 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
     g.outputtype = (uint32_t)cfg->outputtype;
     g.threadphoton = (uint32_t)(cfg->nphoton / nthread);                       /* src/mcx_host.cpp:1011-1012 */
     g.oddphoton = (int)(cfg->nphoton - (uint64_t)g.threadphoton * nthread);
-    g.debuglevel = cfg->debuglevel & 1u;
+    g.debuglevel = cfg->debuglevel & (1u | 2u | 8u);       /* -D R, -D M, -D T */
+    g.maxjumpdebug = cfg->maxjumpdebug;
     g.savedetflag = cfg->issavedet ? cfg->savedetflag : 0;
     g.partialdata = (cfg->medianum - 1) * ((g.savedetflag >> 1 & 1u) + (g.savedetflag >> 2 & 1u) + (g.savedetflag >> 3 & 1u));
     g.w0offset = g.partialdata + 4;
@@ -2016,6 +2053,10 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
         sink_t* s = sinks + tid;
         s->field = (float*)calloc(fieldlen * (rfforward ? 4 : 2), sizeof(float));
 
+        if ((g.debuglevel & (2u | 8u)) && res->traj && g.maxjumpdebug) {
+            s->traj = (float*)calloc((size_t)g.maxjumpdebug * 6, sizeof(float));
+        }
+
         if (cfg->issavedet) {
             s->detp = (float*)calloc((size_t)g.maxdetphoton * (g.reclen ? g.reclen : 1), sizeof(float));
 
@@ -2083,6 +2124,7 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
 
     res->reclen = g.reclen;
     res->detected = 0;
+    res->trajcount = 0;
     res->n_segment = res->n_deposit = res->n_scatter = 0;
     uint32_t saved = 0;
 
@@ -2100,10 +2142,18 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
             }
         }
 
+        /* trajectory records of the host threads one after the other (oracle/ref_driver.cpp does the same) */
+        const uint32_t ntraj = s->trajcount < g.maxjumpdebug ? s->trajcount : g.maxjumpdebug;
+
+        for (uint32_t k = 0; s->traj && k < ntraj && res->trajcount < res->trajcap; k++, res->trajcount++) {
+            memcpy(res->traj + (size_t)res->trajcount * 6, s->traj + (size_t)k * 6, sizeof(float) * 6);
+        }
+
         res->n_segment += s->n_segment;
         res->n_deposit += s->n_atomic;
         res->n_scatter += s->n_log;
         free(s->field);
+        free(s->traj);
         free(s->detp);
         free(s->detseed);
     }

@@ -31,7 +31,7 @@ typedef struct mcxo_result {
     uint64_t  n_scatter;    /* scattering-length draws    */
     uint64_t  n_launch;     /* photons launched           */
     double    runtime_ms;
-    /* trajectories (MCX_DEBUG_MOVE, reference build only): caller-allocated trajcap * 6 floats or NULL */
+    /* trajectories (MCX_DEBUG_MOVE / MCX_DEBUG_MOVE_ONLY): caller-allocated trajcap * 6 floats or NULL */
     float*    traj;
     uint32_t  trajcap;
     uint32_t  trajcount;    /* out: records stored */

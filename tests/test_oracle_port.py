@@ -293,6 +293,22 @@ def test_port_bit_identical_split_voxel_media(ref, port, case):
     assert_identical(a, b)
 
 
+@pytest.mark.parametrize("case", ["M", "M_odd_split", "T_capped", "M_multisource"])
+def test_port_bit_identical_trajectories(ref, port, case):
+    """-D M / -D T: one record at the launch, at every scattering site and at the end of every packet (src/mcx_core.cl:
+    929-948, 1497-1503, 2243-2249, 2625-2632), ids numbered exactly as the reference numbers them"""
+    cfg = {
+        "M": dict(benchmarks.get("cube60b", 3000), debuglevel="M", maxjumpdebug=500000),
+        "M_odd_split": dict(benchmarks.get("cube60b", 3001), debuglevel="M", maxjumpdebug=500000),
+        "T_capped": dict(benchmarks.get("cube60b", 3000), debuglevel="T", maxjumpdebug=1000),
+        "M_multisource": dict(decks.cube(3000, srcpos=[[29.0, 29.0, 0.0, 1.0], [10.0, 40.0, 0.0, 1.0]], srcid=-1), debuglevel="M", maxjumpdebug=500000),
+    }[case]
+    p, a, b = both(ref, port, cfg)
+    assert_identical(a, b)
+    assert a["traj"].shape == b["traj"].shape and a["traj"].shape[0] == min(p.c.maxjumpdebug, a["traj"].shape[0]) >= 1000
+    assert (bits(a["traj"]) == bits(b["traj"])).all()
+
+
 def test_port_parallel_run_matches_serial_totals(port):
     p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
     a = port.run(p, 512, hostthreads=1)
