@@ -22,8 +22,8 @@
  *   host side                  src/mcx_host.cpp:494-524, 674-700, 759-768, 1011-1012 (parameter block, seeding,
  *                              threadphoton/oddphoton), :1252-1306 (fold shadow half, energy sums)
  *   photon replay              :1590-1596, 2568-2612, 2845-2858   stream restart, Jacobian / WP / DCS / WLTOF / WPTOF
- * Not restated (outside SURVEY.md section 8a): two-word media (96), the RF replay
- * outputs, detectors launched as adjoint disk sources, issaveref > 1.
+ * Not restated: two-word media (96, unreachable from the reference's front-ends), the RF replay outputs (their phase
+ * factors are lost in the reference), issaveref > 1 (a data race in the reference).
  *
  * Numeric contract: IEEE binary32, no FMA contraction (build with -ffp-contract=off), the OpenCL native_*
  * functions taken as the libm float functions and rsqrt(x) as 1/sqrtf(x) -- the same contract under which
@@ -842,6 +842,8 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
         (void)rand_uniform01(t);
     }
 
+    /* :1619, as written: a bitwise AND of the source count with the truth value of srcid < 0 */
+    const int cur_src_id = (g->extrasrclen & (uint32_t)(g->srcid < 0)) ? (int)ppath[g->w0offset - 1] : 0;
     ppath += g->partialdata;
     const f4 pos = {src->pos.x, src->pos.y, src->pos.z, src->pos.w};
     const f4 dir = {src->dir.x, src->dir.y, src->dir.z, src->dir.w};
@@ -1199,6 +1201,33 @@ static int launchnewphoton(const param_t* g, sink_t* s, item_t* it, uint32_t isd
             }
         }
 
+        /* adjoint runs (and srcid == -2) launch the detectors appended to the source list as disks of their radius around
+         * the detector position, perpendicular to the launch direction (:2155-2183) */
+        if ((g->outputtype >= 11 || g->srcid == -2) && cur_src_id > (int)(g->extrasrclen + 1) - (int)g->detnum) {
+            const float phi_adj = TWO_PI * rand_uniform01(t);
+            const float sphi_adj = sinf(phi_adj), cphi_adj = cosf(phi_adj);
+            const float r_adj = sqrtf(rand_uniform01(t)) * p1.x;
+
+            if (v->z > -1.f + EPS && v->z < 1.f - EPS) {
+                const float tmp0_adj = 1.f - v->z * v->z;
+                const float tmp1_adj = r_adj * rsqrt_(tmp0_adj);
+                p->x += tmp1_adj * (v->x * v->z * cphi_adj - v->y * sphi_adj);
+                p->y += tmp1_adj * (v->y * v->z * cphi_adj + v->x * sphi_adj);
+                p->z -= tmp1_adj * tmp0_adj * cphi_adj;
+            } else {
+                p->x += r_adj * cphi_adj;
+                p->y += r_adj * sphi_adj;
+            }
+
+            it->idx1d = (uint32_t)((int)floorf(p->z) * (int)g->dimxy + (int)floorf(p->y) * (int)g->dimx + (int)floorf(p->x));
+
+            if (p->x < 0.f || p->y < 0.f || p->z < 0.f || p->x >= g->maxidx.x || p->y >= g->maxidx.y || p->z >= g->maxidx.z) {
+                it->mediaid = 0;
+            } else {
+                it->mediaid = g->media[it->idx1d];
+            }
+        }
+
         /* a packet launched in a zero voxel is marched to the surface (:2188-2195) */
         if ((it->mediaid & MED_MASK) == 0) {
             const int idx = skipvoid(g, s, p, v, f, &it->flipdir);
@@ -1533,7 +1562,7 @@ static void work_item(const param_t* g, sink_t* s, int idx, uint32_t* n_seed, fl
                     weight_im = (a_mag2 < EPS) ? (w0_im * pathlen) : (dw_im * prop->x - dw_re * a_im) / a_mag2;
                 } else if (g->outputtype == otEnergy) {
                     weight = it.w0 - p->w;
-                } else if (g->outputtype == otFluence || g->outputtype == otFlux) {
+                } else if (g->outputtype == otFluence || g->outputtype == otFlux || g->outputtype >= 11) {      /* 11..16: the adjoint types (:2844) */
                     weight = (prop->x < EPS) ? (it.w0 * pathlen) : ((it.w0 - p->w) / (prop->x));
                 } else if (g->replay) {
                     if (g->outputtype == otJacobian || g->outputtype == otWLTOF) {
@@ -1905,12 +1934,12 @@ int mcxo_run(const mcxb_config* cfg, uint32_t nthread, int hostthreads, mcxo_res
         return -3;      /* the reference indexes its media table with the whole media word under isspecular (:1425); the rest is untested there */
     }
 
-    if ((cfg->mediaformat > 4 && !continuous && !splitvox) || (cfg->polmedianum && (!cfg->smatrix || continuous || cfg->medianum != cfg->polmedianum + 1)) || cfg->outputtype > 10 || cfg->outputtype == 6 || cfg->outputtype == 8) {
+    if ((cfg->mediaformat > 4 && !continuous && !splitvox) || (cfg->polmedianum && (!cfg->smatrix || continuous || cfg->medianum != cfg->polmedianum + 1)) || cfg->outputtype > 16 || cfg->outputtype == 6 || cfg->outputtype == 8) {
         return -3;      /* split-voxel / two-word media, RF replay and adjoint runs: checked by oracle/_ref only */
     }
 
-    if (cfg->srcid < -1 || cfg->issaveref > 1) {
-        return -3;      /* detectors launched as disk sources (srcid == -2) and issaveref > 1 are not restated */
+    if (cfg->srcid < -2 || cfg->issaveref > 1) {
+        return -3;      /* issaveref > 1 is a data race in the reference (:852-865): nothing to restate */
     }
 
     const int rfforward = cfg->omega > 0.f;

@@ -309,6 +309,28 @@ def test_port_bit_identical_trajectories(ref, port, case):
     assert (bits(a["traj"]) == bits(b["traj"])).all()
 
 
+@pytest.mark.parametrize("case", ["adjoint", "tilted", "srcid_minus_2", "adjoint_musp", "disk_over_the_edge"])
+def test_port_bit_identical_adjoint_disk_sources(ref, port, case):
+    """adjoint forward runs (and srcid == -2): the sources appended for the detectors start from a disk of the detector's
+    radius (src/mcx_core.cl:1619, 2155-2183); the adjoint output types deposit like fluence (:2844)"""
+    base = dict(benchmarks.get("cube60", 4000), issavedet=0, srcpos=[[30, 30, 1, 1], [30, 42, 1, 1]], srcdir=[[0, 0, 1, 0], [0, 0, 1, 0]],
+                srcparam1=[[0, 0, 0, 0], [4, 0, 0, 0]], detpos=[[30, 42, 1, 4]], srcid=-1, outputtype="adjoint", isnormalized=0)
+    cfg = {
+        "adjoint": base,
+        "tilted": dict(base, srcdir=[[0, 0, 1, 0], [0.3, -0.2, 0.93273790530888, 0]]),
+        "srcid_minus_2": dict(base, srcid=-2, outputtype="fluence"),
+        "adjoint_musp": dict(base, outputtype="adjoint_musp"),
+        "disk_over_the_edge": dict(base, srcpos=[[30, 30, 1, 1], [2, 2, 1, 1]], detpos=[[2, 2, 1, 4]]),
+    }[case]
+    p, a, b = both(ref, port, cfg)
+    vols = a["field"].reshape(2, 60, 60, 60)
+    assert p.nsrcvol == 2 and vols[0].sum() > 0 and vols[1].sum() > 0
+    if case == "adjoint":
+        # the detector's volume enters through a disk, the source's through one voxel
+        assert (vols[1, 0] > 0).sum() > 5 * (vols[0, 0] > 0.2 * vols[0, 0].max()).sum()
+    assert_identical(a, b)
+
+
 def test_port_parallel_run_matches_serial_totals(port):
     p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
     a = port.run(p, 512, hostthreads=1)
