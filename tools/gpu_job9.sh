@@ -1,4 +1,5 @@
 #!/bin/bash
+# validation of the shipped build (marcher inlined in the common / extended kernels): extended-mode timings, whole GPU suite, default bench line
 mkdir -p gpurun_out
 python tools/ext_sweep.py 1e7 2>&1 | python -c "
 import sys,json
