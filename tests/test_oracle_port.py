@@ -331,6 +331,18 @@ def test_port_bit_identical_adjoint_disk_sources(ref, port, case):
     assert_identical(a, b)
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_port_bit_identical_on_random_combinations(ref, port, seed):
+    """tools/oracle_fuzz.py: random combinations of source type, boundary codes, media, gates, detector flags and physics
+    modes (RF forward, polarised light, trajectories, continuous media) -- 40 per seed, every output bit for bit"""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "oracle_fuzz.py"), "40", str(seed)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert " 0 differ" in out.stdout
+
+
 def test_port_parallel_run_matches_serial_totals(port):
     p = hostcfg.prepare(benchmarks.get("cube60b", 2e4))
     a = port.run(p, 512, hostthreads=1)
