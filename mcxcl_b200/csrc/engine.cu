@@ -984,6 +984,21 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
 
         for (uint32_t i = 0; i < cfg->medianum; i++) {
             tab[i] = make_float4(cfg->prop[i].x, cfg->prop[i].y, cfg->prop[i].z, cfg->prop[i].w);
+
+            /* mcx_validatecfg (src/mcx_utils.c:1647-1652): a scattering coefficient of exactly 0 becomes EPS, so that a segment
+             * length slen / mus is never 0 / 0.  The reference's front-ends have done this already; a direct caller of the C
+             * ABI may not have */
+            if (tab[i].y == 0.f && !polarized) {
+                tab[i].y = 1e-10f;
+            }
+        }
+
+        /* With gscatter active the reduced coefficient is mus (1 - g), and the conventional background row {0, 0, 1, 1} has
+         * g = 1: a packet that lives on inside a label-0 voxel of the grid (reflection compiled out, or matched indices)
+         * would then step by 0 / 0 and never leave -- the reference's kernel does not return from that (found by
+         * tools/oracle_fuzz.py).  Row 0's g only ever matters for such a packet; it is read as 0 here. */
+        if (cfg->gscatter < 1000000000u && tab[0].z >= 1.f) {
+            tab[0].z = 0.f;
         }
 
         auto put = [&](uint32_t at, const mcxb_source & src) {
