@@ -22,9 +22,12 @@ def bits(x):
 
 
 def random_case(rs):
+    mode = rs.choice(["plain", "plain", "rf", "polarised", "traj", "continuous", "svmc", "multisrc", "adjoint"])
     name = rs.choice(sorted(decks.SOURCES))
-    src = dict(decks.SOURCES[name])
     base = rs.choice(["cube", "two_layer"])
+    if mode in ("svmc", "adjoint"):            # the reference builds of MED_TYPE 97 exist for the pencil source only
+        name, base = "pencil", "cube"
+    src = dict(decks.SOURCES[name])
     cfg = decks.cube(int(rs.choice([500, 1000, 1501]))) if base == "cube" else decks.two_layer(int(rs.choice([500, 1000])))
     cfg.update(src)
     tag = [base, name]
@@ -64,7 +67,6 @@ def random_case(rs):
     if rs.rand() < 0.15:
         cfg.update(gscatter=3)
         tag.append("gscatter")
-    mode = rs.choice(["plain", "plain", "rf", "polarised", "traj", "continuous"])
     pattern = cfg.get("srctype") in ("pattern", "pattern3d")
     if mode == "rf" and not pattern:
         cfg.update(omega=2 * np.pi * float(rs.choice([50e6, 200e6])))
@@ -85,6 +87,26 @@ def random_case(rs):
         if cfg.get("issavedet"):
             cfg["savedetflag"] = "".join(f for f in cfg["savedetflag"] if f not in "spm") or "d"
         tag.append(fmt)
+    elif mode == "svmc" and base == "cube" and "prop" not in b and not cfg.get("isspecular") and name == "pencil":
+        import test_gpu_svmc as sv
+        cfg.update(vol=sv.tilted_slab(z0=float(rs.uniform(10, 30)), sx=float(rs.uniform(-0.3, 0.3)), sy=float(rs.uniform(-0.3, 0.3))),
+                   prop=[[0, 0, 1, 1], [0.02, 1.0, 0.8, 1.37], [0.005, 2.0, 0.9, float(rs.choice([1.37, 1.5]))]], srcpos=[20, 20, 0])
+        if cfg.get("issavedet"):
+            cfg.update(detpos=[[20, 20, 0, 6], [30, 10, 0, 3]])
+        tag.append("svmc")
+    elif mode in ("multisrc", "adjoint") and not pattern and base == "cube":
+        # extra sources of the same type: the main source's parameters with shifted positions
+        pos = list(cfg.get("srcpos", [29.0, 29.0, 0.0]))[:3]
+        cfg["srcpos"] = [pos + [1.0], [pos[0] + 6.0, pos[1] - 5.0, pos[2], 1.0], [pos[0] - 7.0, pos[1] + 4.0, pos[2], 0.5]]
+        for key in ("srcdir", "srcparam1", "srcparam2"):
+            if key in cfg:
+                row = list(cfg[key]) + [0.0] * (4 - len(cfg[key]))
+                cfg[key] = [row, row, row]
+        cfg["srcid"] = int(rs.choice([0, -1, 2]))
+        tag.append("multisrc srcid=%d" % cfg["srcid"])
+        if mode == "adjoint" and cfg["srcid"] == -1 and name == "pencil":
+            cfg.update(outputtype="adjoint", detpos=[[pos[0] - 7.0, pos[1] + 4.0, pos[2], 3.0]], srcparam1=[[0, 0, 0, 0], [0, 0, 0, 0], [3.0, 0, 0, 0]])
+            tag.append("adjoint")
     return cfg, " ".join(tag)
 
 
