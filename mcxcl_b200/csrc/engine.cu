@@ -690,6 +690,16 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         return fail(MCXB_ERR_ARG, "volume and media table are required");
     }
 
+    for (uint32_t i = 0; i < cfg->medianum; i++) {
+        /* a NaN / infinite optical property or a refractive index <= 0 turns positions into NaN, and a packet at NaN never
+         * leaves the persistent kernel: refused here rather than hanging the device (the reference does not check) */
+        const mcxb_f4& m = cfg->prop[i];
+
+        if (!std::isfinite(m.x) || !std::isfinite(m.y) || !std::isfinite(m.z) || !std::isfinite(m.w) || !(m.w > 0.f)) {
+            return fail(MCXB_ERR_ARG, "media row %u {mua %g, mus %g, g %g, n %g} must be finite with n > 0", i, m.x, m.y, m.z, m.w);
+        }
+    }
+
     if (cfg->dimx > 32767 || cfg->dimy > 32767 || cfg->dimz > 32767 || (uint64_t)cfg->dimx * cfg->dimy * cfg->dimz >= 0x7FFFFFFFull) {
         return fail(MCXB_ERR_ARG, "grid dimensions exceed the 16-bit voxel coordinates of the photon kernel");
     }

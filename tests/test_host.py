@@ -221,6 +221,13 @@ def test_c_abi_argument_errors_are_reported_before_any_device_work(lib):
             setattr(p.c, k, v)
         rc, msg = _create_error(lib, p)
         assert rc == ERR_ARG and word in msg, (fields, rc, msg)
+    # optical properties the kernel cannot leave again: refused instead of hanging the device
+    for row in ([0.005, float("nan"), 0.01, 1.37], [0.005, 1.0, 0.01, 0.0], [float("inf"), 1.0, 0.01, 1.37]):
+        p = hostcfg.prepare(base)
+        p.keep["badprop"] = np.array([[0, 0, 1, 1], row], np.float32)
+        p.c.prop = p.keep["badprop"].ctypes.data_as(type(p.c.prop))
+        rc, msg = _create_error(lib, p)
+        assert rc == ERR_ARG and "media row 1" in msg, (row, rc, msg)
     p = hostcfg.prepare(base)
     p.c.abi_version = abi.ABI_VERSION - 1
     rc, msg = _create_error(lib, p)
