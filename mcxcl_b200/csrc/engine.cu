@@ -822,6 +822,17 @@ static int sim_create_impl(const mcxb_config* cfg, int device, mcxb_sim* s) {
         return fail(MCXB_ERR_ARG, "detnum>0 but detpos is NULL");
     }
 
+    /* positions and directions index the volume: a NaN there is an out-of-bounds voxel address on the device.  (dir.w is
+     * the focal length and may be NaN / -inf on purpose: isotropic / Lambertian launch, src/mcx_core.cl:2095-2146) */
+    for (uint32_t i = 0; i <= cfg->extrasrclen; i++) {
+        const mcxb_source& sr = i ? cfg->srcdata[i - 1] : cfg->src;
+
+        if (!std::isfinite(sr.pos.x) || !std::isfinite(sr.pos.y) || !std::isfinite(sr.pos.z) || !std::isfinite(sr.pos.w) ||
+                !std::isfinite(sr.dir.x) || !std::isfinite(sr.dir.y) || !std::isfinite(sr.dir.z)) {
+            return fail(MCXB_ERR_ARG, "source %u: position, weight and direction must be finite", i);
+        }
+    }
+
     int ndev = 0;
     CU_TRY(cudaGetDeviceCount(&ndev));
 

@@ -229,6 +229,10 @@ def test_c_abi_argument_errors_are_reported_before_any_device_work(lib):
         rc, msg = _create_error(lib, p)
         assert rc == ERR_ARG and "media row 1" in msg, (row, rc, msg)
     p = hostcfg.prepare(base)
+    p.c.src.pos.y = float("nan")
+    rc, msg = _create_error(lib, p)
+    assert rc == ERR_ARG and "source 0" in msg
+    p = hostcfg.prepare(base)
     p.c.abi_version = abi.ABI_VERSION - 1
     rc, msg = _create_error(lib, p)
     assert rc == ERR_ARG and "abi_version" in msg
