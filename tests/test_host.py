@@ -77,6 +77,74 @@ def test_ctypes_mirror_matches_every_field_offset():
     assert [n for n, g, w in zip(names, got, want) if g != w] == []
 
 
+def _cli_dump(name):
+    """the reference's own CLI, relinked (integration/_build/mcxcl): `--dumpjson -` prints the configuration AFTER
+    mcx_validatecfg / mcx_preprocess (src/mcx_utils.c:1447-1712), without touching a device"""
+    import json
+    exe = os.path.join(ROOT, "integration", "_build", "mcxcl")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build/mcxcl not built (python integration/build_cli.py needs /root/reference)")
+    decks = {"digimouse": "example/digimouse/digimouse.json", "qtest": "example/quicktest/qtest.inp"}      # not built in: the shipped decks
+    if name in decks:
+        path = os.path.join("/root/reference", decks[name])
+        if not os.path.exists(path):
+            pytest.skip("the reference tree is not here")
+        args, cwd = ["-f", os.path.basename(path)], os.path.dirname(path)
+    else:
+        args, cwd = ["--bench", name], None
+    out = subprocess.run([exe] + args + ["--dumpjson", "-", "-n", "1000"], capture_output=True, text=True, timeout=300, cwd=cwd)
+    assert out.returncode == 0, out.stderr[-500:]
+    return json.loads(out.stdout)
+
+
+@pytest.mark.parametrize("name", ["cube60", "cube60b", "cube60planar", "skinvessel", "colin27", "digimouse", "qtest"])
+def test_host_mirror_matches_the_reference_clis_own_preprocessing(name):
+    """mcxcl_b200.hostcfg + mcxcl_b200.benchmarks (what the GPU tests and bench.py feed the engine) against the reference's
+    code itself: built-in benchmark -> mcx_validatecfg -> mcx_preprocess -> JSON dump.  Source records (launch voxel and
+    label bit patterns in Param2 included), media table, gates, detectors and flags agree bit for bit; colin27's volume
+    voxel for voxel."""
+    import base64
+    import zlib
+    d = _cli_dump(name)
+    cfg = benchmarks.get(name, 1000)
+    p = hostcfg.prepare(cfg)
+    c = p.c
+    bits = lambda x: np.asarray(x, np.float32).view(np.uint32)          # noqa: E731
+    src, ses = d["Optode"]["Source"], d["Session"]
+    assert ses["Photons"] == c.nphoton
+    if name != "digimouse":            # the shipped digimouse deck asks for seed 2147483647; the bench uses one seed for every deck
+        assert ses["RNGSeed"] == c.seed
+    assert hostcfg.SRCTYPES.index(src["Type"]) == c.srctype
+    assert np.array_equal(bits(src["Pos"]), bits([c.src.pos.x, c.src.pos.y, c.src.pos.z]))
+    assert np.array_equal(bits(src["Dir"]), bits([c.src.dir.x, c.src.dir.y, c.src.dir.z, c.src.dir.w]))
+    assert np.array_equal(bits(src["Param1"]), bits([c.src.param1.x, c.src.param1.y, c.src.param1.z, c.src.param1.w]))
+    assert np.array_equal(bits(src["Param2"]), bits([c.src.param2.x, c.src.param2.y, c.src.param2.z, c.src.param2.w]))
+    assert list(d["Domain"]["Dim"]) == list(p.dims)
+    assert np.array_equal(bits([d["Forward"]["T0"], d["Forward"]["T1"], d["Forward"]["Dt"]]), bits([c.tstart, c.tend, c.tstep]))
+    assert np.float32(d["Domain"]["LengthUnit"]) == np.float32(c.unitinmm)
+    # the dump writes mua / mus per mm again (divided by the voxel size); the table at the boundary is per voxel edge
+    med = np.array([[m["mua"], m["mus"], m["g"], m["n"]] for m in d["Domain"]["Media"]], np.float64)
+    mine = np.array([[c.prop[i].x, c.prop[i].y, c.prop[i].z, c.prop[i].w] for i in range(c.medianum)], np.float64)
+    assert med.shape == mine.shape
+    med[:, :2] *= float(np.float32(c.unitinmm))
+    if c.unitinmm == 1.0:
+        assert np.array_equal(bits(med), bits(mine))
+    else:
+        np.testing.assert_allclose(mine, med, rtol=3e-7)
+    det = d["Optode"].get("Detector", [])
+    assert len(det) == c.detnum
+    for i, row in enumerate(det):
+        assert np.array_equal(bits(list(row["Pos"]) + [row["R"]]), bits([c.detpos[i].x, c.detpos[i].y, c.detpos[i].z, c.detpos[i].w]))
+    assert bool(ses["DoMismatch"]) == bool(c.isreflect) and bool(ses["DoPartialPath"]) == bool(c.issavedet)
+    assert bool(ses["DoSpecular"]) == (c.isspecular > 0) and bool(ses["DoNormalize"]) == bool(c.isnormalized)
+    if c.issavedet:
+        assert ses["SaveDataMask"] == c.savedetflag
+    sh = d.get("Shapes")
+    if isinstance(sh, dict) and "_ArrayZipData_" in sh:                 # volume benchmarks carry the volume as a JData array
+        raw = np.frombuffer(zlib.decompress(base64.b64decode(sh["_ArrayZipData_"])), dtype=np.dtype(sh["_ArrayType_"]))
+        assert np.array_equal(raw.reshape(sh["_ArraySize_"]), np.asarray(cfg["vol"]))
+
+
 def test_seed_table_is_glibc_rand(lib):
     """src/mcx_host.cpp:696-700, 759-768: srand(seed); seeds[i] = rand().  Compared with the C library itself."""
     libc = C.CDLL("libc.so.6")
