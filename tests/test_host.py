@@ -145,6 +145,65 @@ def test_host_mirror_matches_the_reference_clis_own_preprocessing(name):
         assert np.array_equal(raw.reshape(sh["_ArraySize_"]), np.asarray(cfg["vol"]))
 
 
+def _json_number(x):
+    """JData spelling of the non-finite floats the reference's JSON reader understands"""
+    x = float(x)
+    if np.isnan(x):
+        return "_NaN_"
+    if np.isinf(x):
+        return "_Inf_" if x > 0 else "-_Inf_"
+    return x
+
+
+def _from_json_number(x):
+    if isinstance(x, str):
+        return float(x.replace("-_Inf_", "-inf").replace("_Inf_", "inf").replace("_NaN_", "nan"))
+    return x
+
+
+@pytest.mark.parametrize("name", sorted(__import__("decks").SOURCES))
+def test_source_records_match_the_reference_clis_own_preprocessing(name, tmp_path):
+    """every source deck of tests/decks.py written as a JSON input file, read by the reference's parser (mcx_loadjson) and
+    preprocessed by its own code (src/mcx_utils.c:1447-1712: direction normalisation, 0-based positions, launch voxel and
+    label, the per-type parameter conventions), against what hostcfg.prepare() hands the engine: bit for bit"""
+    import decks
+    import json
+    exe = os.path.join(ROOT, "integration", "_build", "mcxcl")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build/mcxcl not built (python integration/build_cli.py needs /root/reference)")
+    cfg = decks.cube(1000, **decks.SOURCES[name])
+    pad = lambda v: [float(x) for x in v] + [0.0] * (4 - len(v))          # noqa: E731
+    src = {"Type": cfg.get("srctype", "pencil"), "Pos": [float(x) for x in cfg["srcpos"]], "Dir": [_json_number(x) for x in cfg.get("srcdir", [0, 0, 1])]}
+    for key, field in (("srcparam1", "Param1"), ("srcparam2", "Param2")):
+        if key in cfg:
+            src[field] = pad(cfg[key])
+    if "srcpattern" in cfg:
+        pat = np.asarray(cfg["srcpattern"], np.float32)
+        src["Pattern"] = dict(zip(("Nx", "Ny", "Nz"), pat.shape), Data=[float(x) for x in pat.ravel(order="F")])
+    deck = {"Session": {"ID": "deck", "Photons": 1000, "RNGSeed": int(cfg["seed"]), "DoMismatch": bool(cfg["isreflect"]), "DoSpecular": bool(cfg.get("isspecular", 0))},
+            "Forward": {"T0": cfg["tstart"], "T1": cfg["tend"], "Dt": cfg["tstep"]},
+            "Domain": {"OriginType": 1, "LengthUnit": 1, "Dim": [60, 60, 60],
+                       "Media": [dict(zip(("mua", "mus", "g", "n"), [float(x) for x in row])) for row in cfg["prop"]]},
+            "Optode": {"Source": src, "Detector": [{"Pos": [float(x) for x in d[:3]], "R": float(d[3])} for d in cfg["detpos"]]},
+            "Shapes": [{"Grid": {"Tag": 1, "Size": [60, 60, 60]}}]}
+    with open(os.path.join(tmp_path, "deck.json"), "w") as f:
+        json.dump(deck, f)
+    out = subprocess.run([exe, "-f", "deck.json", "--dumpjson", "-"], capture_output=True, text=True, cwd=tmp_path, timeout=120)
+    assert out.returncode == 0, out.stderr[-500:]
+    got = json.loads(out.stdout)["Optode"]["Source"]
+    c = hostcfg.prepare(cfg).c
+    bits = lambda x: np.asarray([_from_json_number(v) for v in x], np.float32).view(np.uint32)          # noqa: E731
+    assert hostcfg.SRCTYPES.index(got["Type"]) == c.srctype
+    assert np.array_equal(bits(got["Pos"]), bits([c.src.pos.x, c.src.pos.y, c.src.pos.z]))
+    mydir = [c.src.dir.x, c.src.dir.y, c.src.dir.z, c.src.dir.w]
+    if got["Dir"][3] is None:           # the dump has no spelling for NaN / -inf (isotropic / Lambertian launch): compare the vector part
+        assert not np.isfinite(mydir[3]) and np.array_equal(bits(got["Dir"][:3]), bits(mydir[:3]))
+    else:
+        assert np.array_equal(bits(got["Dir"]), bits(mydir))
+    assert np.array_equal(bits(got["Param1"]), bits([c.src.param1.x, c.src.param1.y, c.src.param1.z, c.src.param1.w]))
+    assert np.array_equal(bits(got["Param2"]), bits([c.src.param2.x, c.src.param2.y, c.src.param2.z, c.src.param2.w]))
+
+
 def test_seed_table_is_glibc_rand(lib):
     """src/mcx_host.cpp:696-700, 759-768: srand(seed); seeds[i] = rand().  Compared with the C library itself."""
     libc = C.CDLL("libc.so.6")
