@@ -204,6 +204,38 @@ def test_source_records_match_the_reference_clis_own_preprocessing(name, tmp_pat
     assert np.array_equal(bits(got["Param2"]), bits([c.src.param2.x, c.src.param2.y, c.src.param2.z, c.src.param2.w]))
 
 
+@pytest.mark.parametrize("name", ["cube60b", "colin27", "qtest"])
+def test_detector_mask_matches_the_reference_clis_own(name, tmp_path):
+    """mcx_maskdet (src/mcx_utils.c:4050-4190) marks the tissue voxels on the surface under every detector with the top bit;
+    `-M 1` makes the reference's CLI write the masked volume and exit.  hostcfg.maskdet marks the same voxels."""
+    import base64
+    import json
+    import zlib
+    exe = os.path.join(ROOT, "integration", "_build", "mcxcl")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build/mcxcl not built (python integration/build_cli.py needs /root/reference)")
+    if name == "qtest":
+        src = "/root/reference/example/quicktest"
+        if not os.path.exists(src):
+            pytest.skip("the reference tree is not here")
+        for f in ("qtest.inp", "cubic60.json"):
+            open(os.path.join(tmp_path, f), "w").write(open(os.path.join(src, f)).read())
+        args = ["-f", "qtest.inp", "-s", "qtest"]
+    else:
+        args = ["--bench", name]
+    out = subprocess.run([exe] + args + ["-n", "1000", "-M", "1"], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert out.returncode == 0 and "volume mask is saved" in out.stdout, (out.stdout[-300:], out.stderr[-300:])
+    files = [f for f in os.listdir(tmp_path) if f.endswith("_vol.jnii")]
+    assert len(files) == 1
+    nd = json.load(open(os.path.join(tmp_path, files[0])))["NIFTIData"]
+    theirs = np.frombuffer(zlib.decompress(base64.b64decode(nd["_ArrayZipData_"])), dtype=np.dtype(nd["_ArrayType_"])).reshape(nd["_ArraySize_"])
+    p = hostcfg.prepare(benchmarks.get(name, 1000))
+    nx, ny, nz = p.dims
+    mine = np.asarray(p.keep["vol"], np.uint32).reshape(nz, ny, nx).transpose(2, 1, 0)         # x fastest at the boundary
+    assert theirs.shape == mine.shape
+    assert (theirs >> 31).sum() > 8 and np.array_equal(theirs, mine)
+
+
 def test_seed_table_is_glibc_rand(lib):
     """src/mcx_host.cpp:696-700, 759-768: srand(seed); seeds[i] = rand().  Compared with the C library itself."""
     libc = C.CDLL("libc.so.6")
