@@ -236,6 +236,28 @@ def test_detector_mask_matches_the_reference_clis_own(name, tmp_path):
     assert (theirs >> 31).sum() > 8 and np.array_equal(theirs, mine)
 
 
+def test_flag_parsers_match_the_reference_clis_own():
+    """-w (saveflag[], src/mcx_utils.c:134), -D (debugflag[]) and -O (outputtype[]) as the reference's CLI reads them, against
+    the host mirror's parsers"""
+    import json
+    exe = os.path.join(ROOT, "integration", "_build", "mcxcl")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build/mcxcl not built (python integration/build_cli.py needs /root/reference)")
+
+    def session(args):
+        out = subprocess.run([exe, "--bench", "cube60b", "-n", "1000", "--dumpjson", "-"] + args, capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr[-300:]
+        return json.loads(out.stdout)["Session"]
+
+    base = benchmarks.get("cube60b", 1000)
+    for w in ("DP", "DSPMXVW", "dxv", "W", "SP", "DPXVW", "M"):
+        assert session(["-w", w])["SaveDataMask"] == hostcfg.prepare(dict(base, savedetflag=w)).c.savedetflag
+    for dbg in ("R", "M", "P", "T", "MP"):
+        assert session(["-D", dbg])["DebugFlag"] == hostcfg.prepare(dict(base, debuglevel=dbg, maxjumpdebug=1000)).c.debuglevel
+    for ot in "XFEL":
+        assert hostcfg.OUTPUTTYPES[session(["-O", ot])["OutputType"]] == hostcfg.prepare(dict(base, outputtype=ot.lower())).c.outputtype
+
+
 def test_seed_table_is_glibc_rand(lib):
     """src/mcx_host.cpp:696-700, 759-768: srand(seed); seeds[i] = rand().  Compared with the C library itself."""
     libc = C.CDLL("libc.so.6")
